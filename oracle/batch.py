@@ -1,0 +1,319 @@
+"""Vectorised CPU restatement of the four native ``step()`` / ``reset()`` pairs.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py) — never imported by the product.
+
+One code path, two arithmetic types:
+
+* ``dtype=np.float64``  -> tier T0: what the reference computes (it works in
+  float64 NumPy on 2-/3-vectors).  Pinned to the reference's own source by
+  tests/golden/*.npz (made by oracle/make_golden.py from /root/reference).
+* ``dtype=np.float32``  -> tier T1: the same formulas, same left-to-right
+  evaluation order, every operation rounded to float32, no FMA; sin/cos from
+  oracle/sincos32.py.  The CUDA path must match T1 bit for bit.
+
+All paths below are relative to /root/reference/gym_reinmav/envs/native/.
+
+State is struct-of-arrays ``[S, N]``.  Per-env bookkeeping the reference keeps
+on the Python object: ``ever_done`` (``steps_beyond_done is not None``,
+quadrotor3d.py:68,112-122 — set on the first done of an env instance and never
+cleared by ``reset()``) and the episode counter that indexes the Philox reset
+stream (replaces the MT19937 stream of quadrotor3d.py:77-79,184).
+"""
+import numpy as np
+
+from . import philox
+from .sincos32 import sincos32
+
+QUAD2D, QUAD2D_SLUNG, QUAD3D, QUAD3D_SLUNG = 0, 1, 2, 3
+KIND_OF_ID = {
+    "quadrotor2d-v0": QUAD2D,
+    "quadrotor2d-slungload-v0": QUAD2D_SLUNG,
+    "quadrotor3d-v0": QUAD3D,
+    "quadrotor3d-slungload-v0": QUAD3D_SLUNG,
+}
+STATE_DIM = {QUAD2D: 5, QUAD2D_SLUNG: 9, QUAD3D: 10, QUAD3D_SLUNG: 16}
+ACTION_DIM = {QUAD2D: 2, QUAD2D_SLUNG: 2, QUAD3D: 4, QUAD3D_SLUNG: 4}
+# U(action_space) bounds: quadrotor2d.py:62, quadrotor2d_slungload.py:68, quadrotor3d.py:70, quadrotor3d_slungload.py:75
+ACTION_BOUNDS = {QUAD2D: (-10.0, 10.0), QUAD2D_SLUNG: (-10.0, 10.0), QUAD3D: (0.0, 10.0), QUAD3D_SLUNG: (-10.0, 10.0)}
+
+
+def default_params(kind, repair="A"):
+    """Constants hard-coded in each ``__init__`` (quadrotor3d.py:45-56,
+    quadrotor3d_slungload.py:45-59, quadrotor2d.py:44-54 + literals :95-96,
+    quadrotor2d_slungload.py:44-58)."""
+    p = dict(mass=1.0, load_mass=0.1, dt=0.01, gravity=9.8, tether_len=0.0,
+             pos_done=3.0, vel_done=10.0, thrust_scale=1.0, thrust_clamp=0,
+             first_done_reward=1.0, later_done_reward=0.0)
+    if kind == QUAD2D:
+        p.update(thrust_scale=10.0, thrust_clamp=1)          # quadrotor2d.py:75-77
+        if repair == "B":
+            p.update(vel_done=2.0)                           # :54 via the repaired :96-98
+    elif kind == QUAD2D_SLUNG:
+        p.update(tether_len=0.5, pos_done=2.0)               # quadrotor2d_slungload.py:54-58
+    elif kind == QUAD3D_SLUNG:
+        p.update(tether_len=1.5)                             # quadrotor3d_slungload.py:59
+    return p
+
+
+class BatchOracle:
+    def __init__(self, kind, n_envs, seed=0, env_id_offset=0, params=None, dtype=np.float64, repair="A"):
+        if isinstance(kind, str):
+            kind = KIND_OF_ID[kind]
+        self.kind, self.n, self.seed = kind, int(n_envs), int(seed)
+        self.dtype = np.dtype(dtype).type
+        self.S, self.A = STATE_DIM[kind], ACTION_DIM[kind]
+        self.env_ids = np.arange(env_id_offset, env_id_offset + self.n, dtype=np.uint64)
+        self.p = default_params(kind, repair)
+        if params:
+            self.p.update(params)
+        self.state = np.zeros((self.S, self.n), dtype=self.dtype)
+        self.episode = np.zeros(self.n, dtype=np.uint32)      # number of resets so far
+        self.ever_done = np.zeros(self.n, dtype=bool)
+        self.taut_override = None           # tests only: force the slung-load branch
+        self.tether_margin = None           # |tether| - L of the last step (slung kinds)
+        self.done_margin = None             # min distance of the two done norms to their thresholds
+
+    # ------------------------------------------------------------------ reset
+    def _draws(self, sel):
+        return philox.uniform_f32(self.seed, self.env_ids[sel], self.episode[sel],
+                                  philox.STREAM_RESET_BASE + self.kind, self.S, -1.0, 1.0)
+
+    def reset(self, mask=None):
+        """``state = U[-1,1)^S`` (quadrotor3d.py:182-185 and twins); every call
+        advances the episode counter of the envs it touches."""
+        sel = np.arange(self.n) if mask is None else np.flatnonzero(mask)
+        self.episode[sel] += np.uint32(1)
+        self.state[:, sel] = self._draws(sel).astype(self.dtype)
+        return self.obs()
+
+    def obs(self):
+        return np.ascontiguousarray(self.state.T)
+
+    # ------------------------------------------------------------------ helpers
+    def _c(self, v):
+        return self.dtype(v)
+
+    def _norm(self, comps):
+        acc = comps[0] * comps[0]
+        for c in comps[1:]:
+            acc = acc + c * c
+        return np.sqrt(acc)
+
+    def _thrust_axis_3d(self, q):
+        """pyquaternion ``Quaternion(att).rotation_matrix.dot([0,0,1])``
+        (quadrotor3d.py:94-96): normalise in place unless |1-q.q| < 1e-14, then
+        column 3 of (Q Qbar^T)[1:,1:].  Returns (unit quaternion, R e3)."""
+        w, x, y, z = q
+        n2 = ((w * w + x * x) + y * y) + z * z
+        n = np.sqrt(n2)
+        need = ~(np.abs(self._c(1.0) - n2) < self._c(1e-14)) & (n > 0)
+        safe = np.where(need, n, self._c(1.0))
+        w, x, y, z = (np.where(need, c / safe, c) for c in (w, x, y, z))
+        rx = ((x * z + w * y) + z * x) + y * w
+        ry = ((y * z + z * y) - w * x) - x * w
+        rz = ((z * z - y * y) - x * x) + w * w
+        return (w, x, y, z), (rx, ry, rz)
+
+    def _qdot(self, qh, om):
+        """``Quaternion.derivative(w)`` = (0.5*q) * (0, w) on the ALREADY
+        normalised object (quadrotor3d.py:101 after :96)."""
+        h = self._c(0.5)
+        w, x, y, z = (h * c for c in qh)
+        ox, oy, oz = om
+        return ((-x * ox - y * oy) - z * oz,
+                (w * ox - z * oy) + y * oz,
+                (z * ox + w * oy) - x * oz,
+                (-y * ox + x * oy) + w * oz)
+
+    def _planar_axis(self, theta):
+        """[cos(att+pi/2), sin(att+pi/2)] (quadrotor2d.py:88)."""
+        if self.dtype is np.float64:
+            a = theta + np.pi / 2
+            return np.cos(a), np.sin(a)
+        s, c = sincos32(theta)
+        return -s, c
+
+    def _taut(self, pos, lp, nt):
+        """``linalg.norm(tether_vec) >= tether_length`` (quadrotor3d_slungload.py:104,
+        quadrotor2d_slungload.py:96).
+
+        After every taut step the constraint projection (:126-127) leaves the
+        load at distance L(1 +- ulp), so this predicate sits on rounding noise.
+        T1 therefore evaluates it in float64 FROM THE float32 STATE (exact
+        differences, individually rounded float64 products/sums, IEEE sqrt): given
+        the same float32 state the CUDA path and the float64 reference then take
+        the same branch except on ~1e-16-relative ties.  ``taut_override`` lets a
+        test force the branch to show that a fixture step is explained by one of
+        the two."""
+        L = self.p["tether_len"]
+        if self.dtype is np.float64:
+            margin = nt - L
+        else:
+            d = [lp[i].astype(np.float64) - pos[i].astype(np.float64) for i in range(len(pos))]
+            margin = self._norm(d) - np.float64(np.float32(L))
+        self.tether_margin = margin
+        if self.taut_override is not None:
+            return np.asarray(self.taut_override, dtype=bool)
+        return margin >= 0
+
+    # ------------------------------------------------------------------ the four steps
+    def _step_quad3d(self, s, a):
+        """quadrotor3d.py:81-104."""
+        p = self.p
+        dt, m = self._c(p["dt"]), self._c(p["mass"])
+        g = (self._c(0.0), self._c(0.0), self._c(-p["gravity"]))
+        T, om = self._c(p["thrust_scale"]) * a[0], (a[1], a[2], a[3])
+        pos, q, vel = s[0:3], s[3:7], s[7:10]
+        qh, e3 = self._thrust_axis_3d(q)
+        tm = T / m
+        acc = [tm * e3[i] + g[i] for i in range(3)]
+        half = self._c(0.5)
+        pos2 = [pos[i] + vel[i] * dt + half * acc[i] * dt * dt for i in range(3)]
+        vel2 = [vel[i] + acc[i] * dt for i in range(3)]
+        qd = self._qdot(qh, om)
+        q2 = [q[i] + qd[i] * dt for i in range(4)]
+        new = pos2 + q2 + vel2
+        return new, self._norm(pos2), self._norm(vel2), self._norm(pos2)
+
+    def _step_quad3d_slung(self, s, a):
+        """quadrotor3d_slungload.py:87-147."""
+        p = self.p
+        dt, m, ml, L = self._c(p["dt"]), self._c(p["mass"]), self._c(p["load_mass"]), self._c(p["tether_len"])
+        g = (self._c(0.0), self._c(0.0), self._c(-p["gravity"]))
+        half = self._c(0.5)
+        T, om = self._c(p["thrust_scale"]) * a[0], (a[1], a[2], a[3])
+        pos, q, vel, lp, lv = s[0:3], s[3:7], s[7:10], s[10:13], s[13:16]
+        tv = [lp[i] - pos[i] for i in range(3)]
+        nt = self._norm(tv)
+        u = [tv[i] / nt for i in range(3)]
+        taut = self._taut(pos, lp, nt)
+        qh, e3 = self._thrust_axis_3d(q)
+        qd = self._qdot(qh, om)
+        q2 = [q[i] + qd[i] * dt for i in range(4)]
+        tm = T / m
+        # --- taut (:104-128)
+        thr = [T * e3[i] for i in range(3)]
+        c = m * L * ((lv[0] * lv[0] + lv[1] * lv[1]) + lv[2] * lv[2])          # scalar, broadcast-subtracted (:110)
+        inner = (u[0] * (thr[0] - c) + u[1] * (thr[1] - c)) + u[2] * (thr[2] - c)
+        inv = self._c(1.0) / (m + ml)
+        la = [inv * (inner * u[i]) + g[i] for i in range(3)]
+        lp_t = [lp[i] + lv[i] * dt + half * la[i] * dt * dt for i in range(3)]   # old lv (:112)
+        lv_t = [lv[i] + la[i] * dt for i in range(3)]
+        tn = ml * self._norm([-g[i] + la[i] for i in range(3)])
+        ten = [tn * u[i] for i in range(3)]
+        acc_t = [tm * e3[i] + g[i] + ten[i] / m for i in range(3)]
+        p_t = [pos[i] + vel[i] * dt + half * acc_t[i] * dt * dt for i in range(3)]
+        v_t = [vel[i] + acc_t[i] * dt for i in range(3)]
+        dv = [lp_t[i] - p_t[i] for i in range(3)]
+        nd = self._norm(dv)
+        d = [dv[i] / nd for i in range(3)]
+        lp_c = [p_t[i] + d[i] * L for i in range(3)]
+        rel = ((lv_t[0] - v_t[0]) * d[0] + (lv_t[1] - v_t[1]) * d[1]) + (lv_t[2] - v_t[2]) * d[2]
+        lv_c = [lv_t[i] - rel * d[i] for i in range(3)]
+        # --- slack (:131-145)
+        lp_s = [lp[i] + lv[i] * dt + half * g[i] * dt * dt for i in range(3)]
+        lv_s = [lv[i] + g[i] * dt for i in range(3)]
+        acc_s = [tm * e3[i] + g[i] for i in range(3)]
+        p_s = [pos[i] + vel[i] * dt + half * acc_s[i] * dt * dt for i in range(3)]
+        v_s = [vel[i] + acc_s[i] * dt for i in range(3)]
+        sel = lambda t_, s_: [np.where(taut, t_[i], s_[i]) for i in range(len(t_))]
+        pos2, vel2, lp2, lv2 = sel(p_t, p_s), sel(v_t, v_s), sel(lp_c, lp_s), sel(lv_c, lv_s)
+        new = pos2 + q2 + vel2 + lp2 + lv2
+        # done: LOAD position, QUAD velocity (:149-152); reward: load position (:156)
+        return new, self._norm(lp2), self._norm(vel2), self._norm(lp2)
+
+    def _step_quad2d(self, s, a):
+        """quadrotor2d.py:74-93 (+ done literals :95-96)."""
+        p = self.p
+        dt, m, half = self._c(p["dt"]), self._c(p["mass"]), self._c(0.5)
+        g = (self._c(0.0), self._c(-p["gravity"]))
+        T = self._c(p["thrust_scale"]) * a[0]
+        if p["thrust_clamp"]:
+            T = np.where(T < 0, self._c(0.0), T)
+        om = a[1]
+        pos, th, vel = s[0:2], s[2], s[3:5]
+        ax = self._planar_axis(th)
+        tm = T / m
+        acc = [tm * ax[i] + g[i] for i in range(2)]
+        pos2 = [pos[i] + vel[i] * dt + half * acc[i] * dt * dt for i in range(2)]
+        vel2 = [vel[i] + acc[i] * dt for i in range(2)]
+        th2 = th + om * dt
+        new = pos2 + [th2] + vel2
+        return new, self._norm(pos2), self._norm(vel2), self._norm(pos2)
+
+    def _step_quad2d_slung(self, s, a):
+        """quadrotor2d_slungload.py:79-134."""
+        p = self.p
+        dt, m, ml, L = self._c(p["dt"]), self._c(p["mass"]), self._c(p["load_mass"]), self._c(p["tether_len"])
+        g = (self._c(0.0), self._c(-p["gravity"]))
+        half = self._c(0.5)
+        T = self._c(p["thrust_scale"]) * a[0]
+        if p["thrust_clamp"]:
+            T = np.where(T < 0, self._c(0.0), T)
+        om = a[1]
+        pos, th, vel, lp, lv = s[0:2], s[2], s[3:5], s[5:7], s[7:9]
+        tv = [lp[i] - pos[i] for i in range(2)]
+        nt = self._norm(tv)
+        u = [tv[i] / nt for i in range(2)]
+        taut = self._taut(pos, lp, nt)
+        ax = self._planar_axis(th)
+        tm = T / m
+        th2 = th + om * dt
+        # --- taut (:96-116): velocity first, then position with the NEW velocity
+        thr = [T * ax[i] for i in range(2)]
+        c = m * L * (lv[0] * lv[0] + lv[1] * lv[1])
+        inner = u[0] * (thr[0] - c) + u[1] * (thr[1] - c)
+        inv = self._c(1.0) / (m + ml)
+        la = [inv * (inner * u[i]) + g[i] for i in range(2)]
+        lv_t = [lv[i] + la[i] * dt for i in range(2)]
+        lp_t = [lp[i] + lv_t[i] * dt + half * la[i] * dt * dt for i in range(2)]
+        tn = ml * self._norm([-g[i] + la[i] for i in range(2)])
+        ten = [tn * u[i] for i in range(2)]
+        acc_t = [tm * ax[i] + g[i] + ten[i] / m for i in range(2)]
+        v_t = [vel[i] + acc_t[i] * dt for i in range(2)]
+        p_t = [pos[i] + v_t[i] * dt + half * acc_t[i] * dt * dt for i in range(2)]
+        dv = [lp_t[i] - p_t[i] for i in range(2)]
+        nd = self._norm(dv)
+        d = [dv[i] / nd for i in range(2)]
+        lp_c = [p_t[i] + d[i] * L for i in range(2)]
+        rel = (lv_t[0] - v_t[0]) * d[0] + (lv_t[1] - v_t[1]) * d[1]
+        lv_c = [lv_t[i] - rel * d[i] for i in range(2)]
+        # --- slack (:119-132)
+        lv_s = [lv[i] + g[i] * dt for i in range(2)]
+        lp_s = [lp[i] + lv_s[i] * dt + half * g[i] * dt * dt for i in range(2)]
+        acc_s = [tm * ax[i] + g[i] for i in range(2)]
+        v_s = [vel[i] + acc_s[i] * dt for i in range(2)]
+        p_s = [pos[i] + v_s[i] * dt + half * acc_s[i] * dt * dt for i in range(2)]
+        sel = lambda t_, s_: [np.where(taut, t_[i], s_[i]) for i in range(len(t_))]
+        pos2, vel2, lp2, lv2 = sel(p_t, p_s), sel(v_t, v_s), sel(lp_c, lp_s), sel(lv_c, lv_s)
+        new = pos2 + [th2] + vel2 + lp2 + lv2
+        # done: load position / load velocity (:136-139); reward: QUAD position (:143)
+        return new, self._norm(lp2), self._norm(lv2), self._norm(pos2)
+
+    # ------------------------------------------------------------------ public step
+    def step(self, actions, auto_reset=True):
+        """One step of all envs.  ``actions`` is ``[N, A]``.
+
+        Returns (obs [N,S], reward [N], done [N] bool).  With ``auto_reset`` the
+        done envs are re-drawn and ``obs`` carries the reset state (the VecEnv
+        convention the reference's launcher relies on, gym_reinmav/run.py:89);
+        without it the terminal state stays (gym.Env convention,
+        test/test_quadrotor3d.py:21-22)."""
+        a = np.asarray(actions).astype(self.dtype).T
+        fn = {QUAD2D: self._step_quad2d, QUAD2D_SLUNG: self._step_quad2d_slung,
+              QUAD3D: self._step_quad3d, QUAD3D_SLUNG: self._step_quad3d_slung}[self.kind]
+        with np.errstate(all="ignore"):
+            new, n_pos, n_vel, n_rew = fn(self.state, a)
+            # strict '>' on the norms; the '< -threshold' clauses are dead (quadrotor3d.py:106-110); NaN -> not done
+            done = (n_pos > self._c(self.p["pos_done"])) | (n_vel > self._c(self.p["vel_done"]))
+            self.done_margin = np.minimum(np.abs(n_pos - self._c(self.p["pos_done"])),
+                                          np.abs(n_vel - self._c(self.p["vel_done"])))
+        self.state = np.stack([np.asarray(c, dtype=self.dtype) for c in new])
+        # reward (quadrotor3d.py:112-122)
+        reward = np.where(done,
+                          np.where(self.ever_done, self._c(self.p["later_done_reward"]), self._c(self.p["first_done_reward"])),
+                          -n_rew).astype(self.dtype)
+        self.ever_done |= done
+        if auto_reset and done.any():
+            self.reset(mask=done)
+        return self.obs(), reward, done
