@@ -1,0 +1,202 @@
+/* rmv.h — C-ABI of librmv.so: the batched native-quadrotor step()/reset() path on B200.
+ *
+ * This is the drop-in boundary for ONE path of ethz-asl/reinmav-gym: the native envs'
+ * step()/reset() (dynamics + reward + done + reset-on-done).  The reference has no FFI of
+ * its own (it is pure Python), so each entry point cites the Python method it replaces;
+ * paths are relative to /root/reference/gym_reinmav/.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative RMV_E* code on failure; it never
+ *     throws or aborts.  rmv_last_error() returns a thread-local message for the last failure.
+ *   - rmv_env is an opaque handle that owns the struct-of-arrays state of n envs on ONE device.
+ *     A handle is not thread-safe; distinct handles are independent (one per GPU).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All device work
+ *     is enqueued on it and nothing synchronises the host, except the *_host entry points and
+ *     calls with host-side destination/source buffers, which say so.
+ *   - pointers named *_dev are device pointers on the handle's device; the caller keeps them
+ *     alive until the stream has run past the call.
+ *   - state layout in HBM: float32 [S][ld], component-major, ld = rmv_padded_ld(n).
+ *     Component order is the reference's tuple order:
+ *       quadrotor2d            [x y theta vx vy]                          envs/native/quadrotor2d.py:93
+ *       quadrotor2d-slungload  [x y theta vx vy lx ly lvx lvy]            envs/native/quadrotor2d_slungload.py:134
+ *       quadrotor3d            [px py pz qw qx qy qz vx vy vz]            envs/native/quadrotor3d.py:104
+ *       quadrotor3d-slungload  [.. quadrotor3d .. lx ly lz lvx lvy lvz]   envs/native/quadrotor3d_slungload.py:147
+ *   - there is no CPU implementation behind this ABI: without a CUDA device every call that
+ *     needs one fails with RMV_ECUDA.
+ */
+#ifndef RMV_H_
+#define RMV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define RMV_API __attribute__((visibility("default")))
+#else
+#define RMV_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMV_ABI_VERSION 1
+
+/* env kinds = the four registered native ids, gym_reinmav/__init__.py:8-26 */
+enum {
+  RMV_QUAD2D = 0,        /* quadrotor2d-v0            envs/native/quadrotor2d.py            */
+  RMV_QUAD2D_SLUNG = 1,  /* quadrotor2d-slungload-v0  envs/native/quadrotor2d_slungload.py  */
+  RMV_QUAD3D = 2,        /* quadrotor3d-v0            envs/native/quadrotor3d.py            */
+  RMV_QUAD3D_SLUNG = 3,  /* quadrotor3d-slungload-v0  envs/native/quadrotor3d_slungload.py  */
+  RMV_NUM_KINDS = 4
+};
+
+enum {
+  RMV_OK = 0,
+  RMV_EINVAL = -1,   /* bad argument                                   */
+  RMV_ECUDA = -2,    /* CUDA runtime / driver error, or no device      */
+  RMV_ENOMEM = -3,   /* host or device allocation failed               */
+  RMV_EALIGN = -4    /* pointer / leading dimension not aligned enough */
+};
+
+/* action buffer layouts */
+enum {
+  RMV_ACT_AOS = 0,   /* [n][A]      — what a policy emits (row per env)                   */
+  RMV_ACT_SOA = 1    /* [A][act_ld] — component-major, act_ld >= n                         */
+};
+
+/* rmv_create flags */
+enum {
+  RMV_TRACK_EPISODES = 1u  /* keep per-env episode return/length (baselines Monitor's info['episode']);
+                              costs 8 extra bytes per env-step */
+};
+
+/* Model constants.  The reference hard-codes them in each __init__ (quadrotor3d.py:45-56,
+ * quadrotor3d_slungload.py:45-59, quadrotor2d.py:44-54, quadrotor2d_slungload.py:44-58);
+ * rmv_default_params() returns exactly those. */
+typedef struct rmv_params {
+  float mass;               /* 1.0                                                            */
+  float load_mass;          /* 0.1 (slung-load kinds)                                         */
+  float dt;                 /* 0.01                                                           */
+  float gravity;            /* 9.8, acts along -y (2D) / -z (3D)                               */
+  float tether_len;         /* 1.5 (3D slung) | 0.5 (2D slung)                                 */
+  float pos_done;           /* 3.0 | 2.0 (2D slung): done when the position norm exceeds it     */
+  float vel_done;           /* 10.0 | 2.0 (2D, repair B of quadrotor2d.py:95-98)                */
+  float thrust_scale;       /* 10.0 for quadrotor2d (quadrotor2d.py:75), else 1.0              */
+  int32_t thrust_clamp;     /* 1 for quadrotor2d: thrust = max(thrust, 0) (quadrotor2d.py:76-77) */
+  float first_done_reward;  /* 1.0  first done ever returned by an env (quadrotor3d.py:114-117)  */
+  float later_done_reward;  /* 0.0  every later done (quadrotor3d.py:118-122)                   */
+} rmv_params;
+
+typedef struct rmv_env rmv_env;
+
+/* ---- queries that need no device -------------------------------------------------------- */
+RMV_API int rmv_abi_version(void);
+RMV_API const char* rmv_last_error(void);
+/* state / action dimensions of a kind: 5/2, 9/2, 10/4, 16/4 (observation_space / action_space
+ * shapes, e.g. quadrotor3d.py:70-71) */
+RMV_API int rmv_kind_dims(int kind, int* state_dim, int* action_dim);
+RMV_API int rmv_default_params(int kind, rmv_params* out);
+/* leading dimension used for n envs (n rounded up to a multiple of 128 floats) */
+RMV_API int64_t rmv_padded_ld(int64_t n_envs);
+/* U(action_space) bounds of a kind (quadrotor2d.py:62, quadrotor3d.py:70, ...) */
+RMV_API int rmv_action_bounds(int kind, float* low, float* high);
+
+/* ---- lifetime --------------------------------------------------------------------------- */
+/* Replaces constructing n env objects (Quadrotor3D.__init__, quadrotor3d.py:44-74) + seed()
+ * (:77-79).  env_id_offset is the global index of env 0 of this shard: reset draws are keyed by
+ * (seed, global env id, episode) so results do not depend on how envs are sharded over GPUs.
+ * params == NULL -> rmv_default_params(kind).  State is zero until rmv_reset(). */
+RMV_API int rmv_create(rmv_env** out, int kind, int64_t n_envs, int64_t env_id_offset, int device,
+               uint64_t seed, const rmv_params* params, uint32_t flags);
+RMV_API int rmv_destroy(rmv_env* env);
+RMV_API int rmv_dims(const rmv_env* env, int* state_dim, int* action_dim, int64_t* n_envs, int64_t* ld);
+RMV_API int rmv_get_params(const rmv_env* env, rmv_params* out);
+/* seed(): re-key the reset stream (Quadrotor3D.seed, quadrotor3d.py:77-79).  State is untouched. */
+RMV_API int rmv_set_seed(rmv_env* env, uint64_t seed);
+
+/* Launch tuning (benchmarks / sweeps): vec = envs per thread (0 = auto, 1, 2, 4),
+ * block = threads per CTA (multiple of 32, <= 256). */
+RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block);
+
+/* ---- state access (parity tests, checkpoint/resume, zero-copy views) --------------------- */
+/* device pointers of the handle-owned buffers: state float32 [S][ld]; episode uint32 [ld]
+ * (bit 31 = this env has returned done at least once — the reference's
+ * `steps_beyond_done is not None`, quadrotor3d.py:68,114-122; bits 0..30 = number of resets,
+ * the Philox episode index). */
+RMV_API int rmv_state_ptr(rmv_env* env, float** state_dev, uint32_t** episode_dev);
+/* copy state in/out as [n][S] rows (the reference's `env.state` tuples).  is_device != 0: the
+ * buffer is a device pointer (transposed by a kernel on `stream`); == 0: a host pointer — the
+ * call then synchronises `stream` before returning. */
+RMV_API int rmv_set_state(rmv_env* env, const float* aos, int is_device, void* stream);
+RMV_API int rmv_get_state(rmv_env* env, float* aos, int is_device, void* stream);
+RMV_API int rmv_set_episode(rmv_env* env, const uint32_t* episode, int is_device, void* stream);
+RMV_API int rmv_get_episode(rmv_env* env, uint32_t* episode, int is_device, void* stream);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+/* reset(): state <- U[-1,1)^S (quadrotor3d.py:182-185 and twins), episode index += 1.
+ * mask_dev == NULL resets every env, else only envs with mask_dev[i] != 0.
+ * obs_aos_dev, if not NULL, receives the new observation rows [n][S]. */
+RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* obs_aos_dev, void* stream);
+
+/* step(): ONE fused kernel = dynamics + done + reward + (optional) reset-on-done for all n envs.
+ * Replaces Quadrotor2D.step (quadrotor2d.py:74-113), Quadrotor2DSlungload.step
+ * (quadrotor2d_slungload.py:79-154), Quadrotor3D.step (quadrotor3d.py:81-124),
+ * Quadrotor3DSlungload.step (quadrotor3d_slungload.py:87-167) and, with auto_reset, the
+ * reset-on-done of the caller (test/test_quadrotor3d.py:21-22) / of baselines' vec-envs behind
+ * make_vec_env (run.py:89).
+ *   act_dev      float32 actions, layout RMV_ACT_AOS ([n][A]) or RMV_ACT_SOA ([A][act_ld])
+ *   reward_dev   float32 [n]
+ *   done_dev     uint8   [n]  (0 / 1)
+ *   obs_aos_dev  NULL, or float32 [n][S]: observation rows after the step (obs == state in the
+ *                reference; with auto_reset a done env reports its RESET state, the VecEnv
+ *                convention).  NULL saves 4*S bytes per env: the state buffer itself is the
+ *                observation in component-major form.
+ *   auto_reset   0: gym.Env semantics — the terminal state stays, the caller resets;
+ *                1: VecEnv semantics — done envs are re-drawn inside the same kernel. */
+RMV_API int rmv_step(rmv_env* env, const float* act_dev, int act_layout, int64_t act_ld,
+             float* reward_dev, uint8_t* done_dev, float* obs_aos_dev, int auto_reset,
+             void* stream);
+
+/* T consecutive steps with auto-reset from a pre-generated action block (random-policy or
+ * replayed rollouts).  act_dev is [T][A][act_ld] (SOA) or [T][n][A] (AOS); reward_dev / done_dev
+ * are [T][out_ld] or NULL.
+ *   fused == 0: T launches of the step kernel (state streams through HBM every step — the
+ *               access pattern of a policy-in-the-loop rollout);
+ *   fused == 1: ONE launch, each thread keeps its envs' state in registers for all T steps
+ *               (state is read and written once per call). Results are identical. */
+RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act_dev, int act_layout, int64_t act_ld,
+                  float* reward_dev, uint8_t* done_dev, int64_t out_ld, int fused, void* stream);
+
+/* Same as rmv_step with HOST buffers (pinned memory recommended: rmv_host_alloc): copies the
+ * actions host->device, runs the step kernel, copies reward/done/(obs) back and synchronises
+ * `stream`.  This is what the Python VecEnv's numpy step() calls. */
+RMV_API int rmv_step_host(rmv_env* env, const float* act_host /*[n][A]*/, float* reward_host,
+                  uint8_t* done_host, float* obs_host /*[n][S] or NULL*/, int auto_reset,
+                  void* stream);
+RMV_API int rmv_reset_host(rmv_env* env, float* obs_host /*[n][S]*/, void* stream);
+
+/* ---- synthetic inputs --------------------------------------------------------------------- */
+/* Random-policy actions ~ U[low, high) for n envs from Philox4x32-10 keyed by
+ * (seed, global env id, step index): the `env.action_space.sample()` of README.md:124-131 made
+ * lane-parallel.  Writes layout AOS [n][A] or SOA [A][act_ld]. */
+RMV_API int rmv_fill_uniform_actions(float* act_dev, int64_t n_envs, int action_dim, int act_layout,
+                             int64_t act_ld, float low, float high, uint64_t seed,
+                             int64_t env_id_offset, uint32_t step_index, int device, void* stream);
+
+/* ---- episode statistics (needs RMV_TRACK_EPISODES) ---------------------------------------- */
+/* out[0] = number of finished episodes, out[1] = sum of their returns, out[2] = sum of their
+ * lengths, out[3] = env-steps taken, all since creation.  Synchronises `stream`. */
+RMV_API int rmv_episode_stats(rmv_env* env, double out[4], void* stream);
+/* per-env return / length of the most recently finished episode, device pointers [ld] */
+RMV_API int rmv_episode_ptr(rmv_env* env, float** last_return_dev, uint32_t** last_length_dev);
+
+/* ---- pinned host memory helpers ------------------------------------------------------------ */
+RMV_API int rmv_host_alloc(void** out, size_t bytes);
+RMV_API int rmv_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMV_H_ */

@@ -125,6 +125,14 @@ class BatchOracle:
                 (z * ox + w * oy) - x * oz,
                 (-y * ox + x * oy) + w * oz)
 
+    def _thrust(self, a0):
+        """``thrust = 10.0 * action[0]; if thrust < 0: thrust = 0`` (quadrotor2d.py:75-77);
+        scale 1 / no clamp for the other kinds (quadrotor3d.py:82)."""
+        T = self._c(self.p["thrust_scale"]) * a0
+        if self.p["thrust_clamp"]:
+            T = np.where(T < 0, self._c(0.0), T)
+        return T
+
     def _planar_axis(self, theta):
         """[cos(att+pi/2), sin(att+pi/2)] (quadrotor2d.py:88)."""
         if self.dtype is np.float64:
@@ -162,7 +170,7 @@ class BatchOracle:
         p = self.p
         dt, m = self._c(p["dt"]), self._c(p["mass"])
         g = (self._c(0.0), self._c(0.0), self._c(-p["gravity"]))
-        T, om = self._c(p["thrust_scale"]) * a[0], (a[1], a[2], a[3])
+        T, om = self._thrust(a[0]), (a[1], a[2], a[3])
         pos, q, vel = s[0:3], s[3:7], s[7:10]
         qh, e3 = self._thrust_axis_3d(q)
         tm = T / m
@@ -181,7 +189,7 @@ class BatchOracle:
         dt, m, ml, L = self._c(p["dt"]), self._c(p["mass"]), self._c(p["load_mass"]), self._c(p["tether_len"])
         g = (self._c(0.0), self._c(0.0), self._c(-p["gravity"]))
         half = self._c(0.5)
-        T, om = self._c(p["thrust_scale"]) * a[0], (a[1], a[2], a[3])
+        T, om = self._thrust(a[0]), (a[1], a[2], a[3])
         pos, q, vel, lp, lv = s[0:3], s[3:7], s[7:10], s[10:13], s[13:16]
         tv = [lp[i] - pos[i] for i in range(3)]
         nt = self._norm(tv)
@@ -227,10 +235,7 @@ class BatchOracle:
         p = self.p
         dt, m, half = self._c(p["dt"]), self._c(p["mass"]), self._c(0.5)
         g = (self._c(0.0), self._c(-p["gravity"]))
-        T = self._c(p["thrust_scale"]) * a[0]
-        if p["thrust_clamp"]:
-            T = np.where(T < 0, self._c(0.0), T)
-        om = a[1]
+        T, om = self._thrust(a[0]), a[1]
         pos, th, vel = s[0:2], s[2], s[3:5]
         ax = self._planar_axis(th)
         tm = T / m
@@ -247,10 +252,7 @@ class BatchOracle:
         dt, m, ml, L = self._c(p["dt"]), self._c(p["mass"]), self._c(p["load_mass"]), self._c(p["tether_len"])
         g = (self._c(0.0), self._c(-p["gravity"]))
         half = self._c(0.5)
-        T = self._c(p["thrust_scale"]) * a[0]
-        if p["thrust_clamp"]:
-            T = np.where(T < 0, self._c(0.0), T)
-        om = a[1]
+        T, om = self._thrust(a[0]), a[1]
         pos, th, vel, lp, lv = s[0:2], s[2], s[3:5], s[5:7], s[7:9]
         tv = [lp[i] - pos[i] for i in range(2)]
         nt = self._norm(tv)

@@ -1,0 +1,516 @@
+// rmv_api.cu — implementation of the C-ABI declared in include/rmv.h.
+// Host side only decides launch shapes and owns buffers; all arithmetic is in rmv_kernels.cuh.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <limits>
+#include <new>
+#include <string>
+
+#include "rmv.h"
+#include "rmv_kernels.cuh"
+
+using namespace rmv;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define RMV_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t err__ = (expr);                                                             \
+    if (err__ != cudaSuccess)                                                               \
+      return fail(err__ == cudaErrorMemoryAllocation ? RMV_ENOMEM : RMV_ECUDA, "%s: %s (%s:%d)", \
+                  #expr, cudaGetErrorString(err__), __FILE__, __LINE__);                    \
+  } while (0)
+
+#define RMV_REQUIRE(cond, ...)                      \
+  do {                                              \
+    if (!(cond)) return fail(RMV_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+#define RMV_ON_DEVICE(dev)  \
+  DeviceGuard guard__(dev); \
+  if (!guard__.ok) return fail(RMV_ECUDA, "cannot select CUDA device %d: %s", (dev), cudaGetErrorString(cudaGetLastError()))
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct rmv_env {
+  int kind = 0, device = 0, S = 0, A = 0;
+  int64_t n = 0, ld = 0, env_id_offset = 0;
+  uint64_t seed = 0;
+  uint32_t flags = 0, step_index = 0;
+  rmv_params params{};
+  DevParams dp{};
+  float* state = nullptr;
+  uint32_t* episode = nullptr;
+  // tracking
+  float* ep_return = nullptr;
+  uint32_t* ep_start = nullptr;
+  float* last_return = nullptr;
+  uint32_t* last_length = nullptr;
+  double* cum_return = nullptr;
+  unsigned long long* cum_length = nullptr;
+  uint32_t* fin_count = nullptr;
+  double* stats_dev = nullptr;
+  // staging for the *_host entry points (lazy)
+  float* h_act = nullptr;
+  float* h_rew = nullptr;
+  uint8_t* h_done = nullptr;
+  float* h_obs = nullptr;
+  // tuning
+  int vec = 0;     // 0 = auto
+  int block = 256;
+};
+
+static const int kS[RMV_NUM_KINDS] = {5, 9, 10, 16};
+static const int kA[RMV_NUM_KINDS] = {2, 2, 4, 4};
+
+static DevParams to_dev(const rmv_params& p) {
+  DevParams d;
+  d.mass = p.mass; d.load_mass = p.load_mass; d.dt = p.dt; d.neg_gravity = -p.gravity;
+  d.tether_len = p.tether_len; d.pos_done = p.pos_done; d.vel_done = p.vel_done;
+  d.thrust_scale = p.thrust_scale; d.first_done_reward = p.first_done_reward;
+  d.later_done_reward = p.later_done_reward; d.thrust_clamp = p.thrust_clamp;
+  volatile float total = p.mass + p.load_mass;   // two separately rounded float32 operations
+  d.inv_total_mass = 1.0f / total;
+  return d;
+}
+
+extern "C" RMV_API int rmv_abi_version(void) { return RMV_ABI_VERSION; }
+extern "C" RMV_API const char* rmv_last_error(void) { return g_err.c_str(); }
+
+extern "C" RMV_API int rmv_kind_dims(int kind, int* state_dim, int* action_dim) {
+  RMV_REQUIRE(kind >= 0 && kind < RMV_NUM_KINDS, "unknown env kind %d", kind);
+  if (state_dim) *state_dim = kS[kind];
+  if (action_dim) *action_dim = kA[kind];
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_default_params(int kind, rmv_params* out) {
+  RMV_REQUIRE(kind >= 0 && kind < RMV_NUM_KINDS, "unknown env kind %d", kind);
+  RMV_REQUIRE(out != nullptr, "out is NULL");
+  rmv_params p;
+  p.mass = 1.0f; p.load_mass = 0.1f; p.dt = 0.01f; p.gravity = 9.8f; p.tether_len = 0.0f;
+  p.pos_done = 3.0f; p.vel_done = 10.0f; p.thrust_scale = 1.0f; p.thrust_clamp = 0;
+  p.first_done_reward = 1.0f; p.later_done_reward = 0.0f;
+  if (kind == RMV_QUAD2D) { p.thrust_scale = 10.0f; p.thrust_clamp = 1; }
+  if (kind == RMV_QUAD2D_SLUNG) { p.tether_len = 0.5f; p.pos_done = 2.0f; }
+  if (kind == RMV_QUAD3D_SLUNG) { p.tether_len = 1.5f; }
+  *out = p;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int64_t rmv_padded_ld(int64_t n_envs) { return n_envs <= 0 ? 0 : ((n_envs + 127) / 128) * 128; }
+
+extern "C" RMV_API int rmv_action_bounds(int kind, float* low, float* high) {
+  RMV_REQUIRE(kind >= 0 && kind < RMV_NUM_KINDS, "unknown env kind %d", kind);
+  if (low) *low = (kind == RMV_QUAD3D) ? 0.0f : -10.0f;
+  if (high) *high = 10.0f;
+  return RMV_OK;
+}
+
+template <typename T>
+static cudaError_t alloc_zero(T** p, size_t count) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemset(*p, 0, count * sizeof(T));
+}
+
+static void free_all(rmv_env* e) {
+  cudaFree(e->state); cudaFree(e->episode); cudaFree(e->ep_return); cudaFree(e->ep_start);
+  cudaFree(e->last_return); cudaFree(e->last_length); cudaFree(e->cum_return);
+  cudaFree(e->cum_length); cudaFree(e->fin_count); cudaFree(e->stats_dev);
+  cudaFree(e->h_act); cudaFree(e->h_rew); cudaFree(e->h_done); cudaFree(e->h_obs);
+}
+
+extern "C" RMV_API int rmv_create(rmv_env** out, int kind, int64_t n_envs, int64_t env_id_offset, int device,
+                          uint64_t seed, const rmv_params* params, uint32_t flags) {
+  RMV_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  RMV_REQUIRE(kind >= 0 && kind < RMV_NUM_KINDS, "unknown env kind %d", kind);
+  RMV_REQUIRE(n_envs > 0, "n_envs must be positive (got %lld)", (long long)n_envs);
+  RMV_REQUIRE(env_id_offset >= 0, "env_id_offset must be >= 0");
+  RMV_REQUIRE(n_envs < (int64_t)1 << 40, "n_envs too large");
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count <= 0)
+    return fail(RMV_ECUDA, "no CUDA device available (%s); librmv has no CPU path", cudaGetErrorString(ce));
+  RMV_REQUIRE(device >= 0 && device < count, "device %d out of range (have %d)", device, count);
+  RMV_ON_DEVICE(device);
+  rmv_env* e = new (std::nothrow) rmv_env();
+  if (!e) return fail(RMV_ENOMEM, "host allocation failed");
+  e->kind = kind; e->device = device; e->S = kS[kind]; e->A = kA[kind];
+  e->n = n_envs; e->ld = rmv_padded_ld(n_envs); e->env_id_offset = env_id_offset;
+  e->seed = seed; e->flags = flags;
+  if (params) e->params = *params; else rmv_default_params(kind, &e->params);
+  e->dp = to_dev(e->params);
+  cudaError_t err = alloc_zero(&e->state, (size_t)e->S * e->ld);
+  if (err == cudaSuccess) err = alloc_zero(&e->episode, (size_t)e->ld);
+  if (err == cudaSuccess && (flags & RMV_TRACK_EPISODES)) {
+    err = alloc_zero(&e->ep_return, (size_t)e->ld);
+    if (err == cudaSuccess) err = alloc_zero(&e->ep_start, (size_t)e->ld);
+    if (err == cudaSuccess) err = alloc_zero(&e->last_return, (size_t)e->ld);
+    if (err == cudaSuccess) err = alloc_zero(&e->last_length, (size_t)e->ld);
+    if (err == cudaSuccess) err = alloc_zero(&e->cum_return, (size_t)e->ld);
+    if (err == cudaSuccess) err = alloc_zero(&e->cum_length, (size_t)e->ld);
+    if (err == cudaSuccess) err = alloc_zero(&e->fin_count, (size_t)e->ld);
+    if (err == cudaSuccess) err = alloc_zero(&e->stats_dev, 4);
+  }
+  if (err == cudaSuccess) err = cudaDeviceSynchronize();   // memsets done before any user stream touches the buffers
+  if (err != cudaSuccess) {
+    free_all(e);
+    delete e;
+    return fail(err == cudaErrorMemoryAllocation ? RMV_ENOMEM : RMV_ECUDA, "rmv_create: %s", cudaGetErrorString(err));
+  }
+  *out = e;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_destroy(rmv_env* env) {
+  if (!env) return RMV_OK;
+  {
+    RMV_ON_DEVICE(env->device);
+    cudaDeviceSynchronize();
+    free_all(env);
+  }
+  delete env;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_dims(const rmv_env* env, int* state_dim, int* action_dim, int64_t* n_envs, int64_t* ld) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  if (state_dim) *state_dim = env->S;
+  if (action_dim) *action_dim = env->A;
+  if (n_envs) *n_envs = env->n;
+  if (ld) *ld = env->ld;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_get_params(const rmv_env* env, rmv_params* out) {
+  RMV_REQUIRE(env != nullptr && out != nullptr, "NULL argument");
+  *out = env->params;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_set_seed(rmv_env* env, uint64_t seed) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  env->seed = seed;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(vec == 0 || vec == 1 || vec == 2 || vec == 4, "vec must be 0 (auto), 1, 2 or 4");
+  RMV_REQUIRE(block >= 32 && block <= kMaxBlock && block % 32 == 0, "block must be a multiple of 32 in [32, %d]", kMaxBlock);
+  env->vec = vec; env->block = block;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_state_ptr(rmv_env* env, float** state_dev, uint32_t** episode_dev) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  if (state_dev) *state_dev = env->state;
+  if (episode_dev) *episode_dev = env->episode;
+  return RMV_OK;
+}
+
+static inline unsigned blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ------------------------------------------------------------------------------------------
+// state in / out
+// ------------------------------------------------------------------------------------------
+static int ensure_staging(rmv_env* e) {
+  if (!e->h_act) RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->h_act), (size_t)e->n * e->A * sizeof(float)));
+  if (!e->h_rew) RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->h_rew), (size_t)e->n * sizeof(float)));
+  if (!e->h_done) RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->h_done), (size_t)e->n));
+  if (!e->h_obs) RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->h_obs), (size_t)e->n * e->S * sizeof(float)));
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_set_state(rmv_env* env, const float* aos, int is_device, void* stream) {
+  RMV_REQUIRE(env != nullptr && aos != nullptr, "NULL argument");
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float* src = aos;
+  if (!is_device) {
+    int rc = ensure_staging(env);
+    if (rc) return rc;
+    RMV_CUDA(cudaMemcpyAsync(env->h_obs, aos, (size_t)env->n * env->S * sizeof(float), cudaMemcpyHostToDevice, st));
+    src = env->h_obs;
+  }
+  k_rows_to_cols<<<blocks_for(env->n, 256), 256, 0, st>>>(src, env->state, env->n, env->ld, env->S);
+  RMV_CUDA(cudaGetLastError());
+  if (!is_device) RMV_CUDA(cudaStreamSynchronize(st));
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_get_state(rmv_env* env, float* aos, int is_device, void* stream) {
+  RMV_REQUIRE(env != nullptr && aos != nullptr, "NULL argument");
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* dst = aos;
+  if (!is_device) {
+    int rc = ensure_staging(env);
+    if (rc) return rc;
+    dst = env->h_obs;
+  }
+  k_cols_to_rows<<<blocks_for(env->n, 256), 256, 0, st>>>(env->state, dst, env->n, env->ld, env->S);
+  RMV_CUDA(cudaGetLastError());
+  if (!is_device) {
+    RMV_CUDA(cudaMemcpyAsync(aos, dst, (size_t)env->n * env->S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RMV_CUDA(cudaStreamSynchronize(st));
+  }
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_set_episode(rmv_env* env, const uint32_t* episode, int is_device, void* stream) {
+  RMV_REQUIRE(env != nullptr && episode != nullptr, "NULL argument");
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RMV_CUDA(cudaMemcpyAsync(env->episode, episode, (size_t)env->n * sizeof(uint32_t),
+                           is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  if (!is_device) RMV_CUDA(cudaStreamSynchronize(st));
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_get_episode(rmv_env* env, uint32_t* episode, int is_device, void* stream) {
+  RMV_REQUIRE(env != nullptr && episode != nullptr, "NULL argument");
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RMV_CUDA(cudaMemcpyAsync(episode, env->episode, (size_t)env->n * sizeof(uint32_t),
+                           is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (!is_device) RMV_CUDA(cudaStreamSynchronize(st));
+  return RMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// reset
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+static void launch_reset(rmv_env* e, const uint8_t* mask, float* obs, cudaStream_t st) {
+  k_reset<KIND><<<blocks_for(e->n, 256), 256, 0, st>>>(e->state, e->episode, e->ld, e->n, mask, e->seed,
+                                                      e->env_id_offset, obs, e->ep_return, e->ep_start,
+                                                      e->step_index);
+}
+
+extern "C" RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* obs_aos_dev, void* stream) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (env->kind) {
+    case RMV_QUAD2D: launch_reset<QUAD2D>(env, mask_dev, obs_aos_dev, st); break;
+    case RMV_QUAD2D_SLUNG: launch_reset<QUAD2D_SLUNG>(env, mask_dev, obs_aos_dev, st); break;
+    case RMV_QUAD3D: launch_reset<QUAD3D>(env, mask_dev, obs_aos_dev, st); break;
+    default: launch_reset<QUAD3D_SLUNG>(env, mask_dev, obs_aos_dev, st); break;
+  }
+  RMV_CUDA(cudaGetLastError());
+  return RMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// step
+// ------------------------------------------------------------------------------------------
+static inline bool aligned(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+template <int KIND, int V>
+static cudaError_t launch_step_kv(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
+  constexpr int S = Dims<KIND>::S;
+  constexpr int SP = (S % 2 == 0) ? S + 1 : S;
+  const int block = e->block;
+  const int64_t groups = (e->n + V - 1) / V;
+  const size_t smem = args.obs ? (size_t)(block / 32) * 32 * SP * sizeof(float) : 0;
+  k_step<KIND, V><<<blocks_for(groups, block), block, smem, st>>>(args);
+  return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t launch_step_k(const rmv_env* e, const StepArgs& args, int vec, cudaStream_t st) {
+  switch (vec) {
+    case 4: return launch_step_kv<KIND, 4>(e, args, st);
+    case 2: return launch_step_kv<KIND, 2>(e, args, st);
+    default: return launch_step_kv<KIND, 1>(e, args, st);
+  }
+}
+
+static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act_ld, int64_t act_step_stride,
+                       float* rew, uint8_t* done, int64_t out_ld, float* obs, int auto_reset, int n_steps,
+                       cudaStream_t st) {
+  RMV_REQUIRE(act != nullptr, "act_dev is NULL");
+  RMV_REQUIRE(act_layout == RMV_ACT_AOS || act_layout == RMV_ACT_SOA, "bad act_layout %d", act_layout);
+  if (act_layout == RMV_ACT_SOA) RMV_REQUIRE(act_ld >= e->n, "act_ld (%lld) < n_envs", (long long)act_ld);
+  RMV_REQUIRE(aligned(act, 4) && aligned(rew, 4) && aligned(obs, 4), "float buffers must be 4-byte aligned");
+  // widest vector width every buffer supports
+  int vec = e->vec ? e->vec : 2;
+  auto ok_for = [&](int v) {
+    if (v == 1) return true;
+    const size_t fb = 4u * v;
+    if (!aligned(rew, fb) || !aligned(done, v)) return false;
+    if (n_steps > 1 && (out_ld % v) != 0) return false;
+    if (act_layout == RMV_ACT_SOA) {
+      if (!aligned(act, fb) || (act_ld % v) != 0 || (act_step_stride % v) != 0) return false;
+    } else {
+      const size_t ab = (size_t)v * e->A * 4u >= 16u ? 16u : 8u;
+      if (!aligned(act, ab) || ((act_step_stride * 4) % (int64_t)ab) != 0) return false;
+    }
+    return true;
+  };
+  while (vec > 1 && !ok_for(vec)) vec >>= 1;
+  if (e->vec && vec != e->vec)
+    return fail(RMV_EALIGN, "buffers are not aligned for the forced vector width %d", e->vec);
+
+  StepArgs a;
+  a.state = e->state; a.episode = e->episode; a.act = act; a.reward = rew; a.done = done; a.obs = obs;
+  a.ep_return = e->ep_return; a.ep_start = e->ep_start; a.last_return = e->last_return;
+  a.last_length = e->last_length; a.cum_return = e->cum_return; a.cum_length = e->cum_length;
+  a.fin_count = e->fin_count;
+  a.ld = e->ld; a.n = e->n; a.act_ld = act_ld; a.out_ld = out_ld; a.act_step_stride = act_step_stride;
+  a.env_id_offset = e->env_id_offset; a.seed = e->seed; a.step_index = e->step_index;
+  a.n_steps = n_steps; a.act_soa = (act_layout == RMV_ACT_SOA); a.auto_reset = auto_reset ? 1 : 0;
+  a.P = e->dp;
+  cudaError_t err;
+  switch (e->kind) {
+    case RMV_QUAD2D: err = launch_step_k<QUAD2D>(e, a, vec, st); break;
+    case RMV_QUAD2D_SLUNG: err = launch_step_k<QUAD2D_SLUNG>(e, a, vec, st); break;
+    case RMV_QUAD3D: err = launch_step_k<QUAD3D>(e, a, vec, st); break;
+    default: err = launch_step_k<QUAD3D_SLUNG>(e, a, vec, st); break;
+  }
+  if (err != cudaSuccess) return fail(RMV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(err));
+  e->step_index += (uint32_t)n_steps;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_step(rmv_env* env, const float* act_dev, int act_layout, int64_t act_ld, float* reward_dev,
+                        uint8_t* done_dev, float* obs_aos_dev, int auto_reset, void* stream) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_ON_DEVICE(env->device);
+  return launch_step(env, act_dev, act_layout, act_ld, 0, reward_dev, done_dev, env->n, obs_aos_dev, auto_reset, 1,
+                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act_dev, int act_layout, int64_t act_ld,
+                             float* reward_dev, uint8_t* done_dev, int64_t out_ld, int fused, void* stream) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(n_steps > 0, "n_steps must be positive");
+  if (reward_dev || done_dev) RMV_REQUIRE(out_ld >= env->n, "out_ld (%lld) < n_envs", (long long)out_ld);
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t stride = (act_layout == RMV_ACT_SOA) ? (int64_t)env->A * act_ld : env->n * env->A;
+  if (fused) return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st);
+  for (int t = 0; t < n_steps; ++t) {
+    int rc = launch_step(env, act_dev + (int64_t)t * stride, act_layout, act_ld, 0,
+                         reward_dev ? reward_dev + (int64_t)t * out_ld : nullptr,
+                         done_dev ? done_dev + (int64_t)t * out_ld : nullptr, out_ld, nullptr, 1, 1, st);
+    if (rc) return rc;
+  }
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float* reward_host, uint8_t* done_host,
+                             float* obs_host, int auto_reset, void* stream) {
+  RMV_REQUIRE(env != nullptr && act_host != nullptr, "NULL argument");
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_staging(env);
+  if (rc) return rc;
+  RMV_CUDA(cudaMemcpyAsync(env->h_act, act_host, (size_t)env->n * env->A * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = launch_step(env, env->h_act, RMV_ACT_AOS, 0, 0, env->h_rew, env->h_done, env->n,
+                   obs_host ? env->h_obs : nullptr, auto_reset, 1, st);
+  if (rc) return rc;
+  if (reward_host) RMV_CUDA(cudaMemcpyAsync(reward_host, env->h_rew, (size_t)env->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (done_host) RMV_CUDA(cudaMemcpyAsync(done_host, env->h_done, (size_t)env->n, cudaMemcpyDeviceToHost, st));
+  if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host, env->h_obs, (size_t)env->n * env->S * sizeof(float), cudaMemcpyDeviceToHost, st));
+  RMV_CUDA(cudaStreamSynchronize(st));
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_reset_host(rmv_env* env, float* obs_host, void* stream) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_staging(env);
+  if (rc) return rc;
+  rc = rmv_reset(env, nullptr, obs_host ? env->h_obs : nullptr, stream);
+  if (rc) return rc;
+  if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host, env->h_obs, (size_t)env->n * env->S * sizeof(float), cudaMemcpyDeviceToHost, st));
+  RMV_CUDA(cudaStreamSynchronize(st));
+  return RMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic actions, statistics, pinned memory
+// ------------------------------------------------------------------------------------------
+extern "C" RMV_API int rmv_fill_uniform_actions(float* act_dev, int64_t n_envs, int action_dim, int act_layout,
+                                        int64_t act_ld, float low, float high, uint64_t seed,
+                                        int64_t env_id_offset, uint32_t step_index, int device, void* stream) {
+  RMV_REQUIRE(act_dev != nullptr && n_envs > 0, "bad buffer");
+  RMV_REQUIRE(action_dim > 0 && action_dim <= 16, "bad action_dim");
+  RMV_REQUIRE(act_layout == RMV_ACT_AOS || act_layout == RMV_ACT_SOA, "bad act_layout %d", act_layout);
+  if (act_layout == RMV_ACT_SOA) RMV_REQUIRE(act_ld >= n_envs, "act_ld < n_envs");
+  RMV_ON_DEVICE(device);
+  const float width = high - low;
+  k_fill_uniform<<<blocks_for(n_envs, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      act_dev, n_envs, action_dim, act_layout == RMV_ACT_SOA, act_ld, low, width, seed, env_id_offset, step_index);
+  RMV_CUDA(cudaGetLastError());
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_episode_stats(rmv_env* env, double out[4], void* stream) {
+  RMV_REQUIRE(env != nullptr && out != nullptr, "NULL argument");
+  RMV_REQUIRE(env->flags & RMV_TRACK_EPISODES, "handle was created without RMV_TRACK_EPISODES");
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RMV_CUDA(cudaMemsetAsync(env->stats_dev, 0, 4 * sizeof(double), st));
+  k_episode_stats<<<296, 256, 0, st>>>(env->fin_count, env->cum_return, env->cum_length, env->n, env->stats_dev);
+  RMV_CUDA(cudaGetLastError());
+  RMV_CUDA(cudaMemcpyAsync(out, env->stats_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RMV_CUDA(cudaStreamSynchronize(st));
+  out[3] = (double)env->step_index * (double)env->n;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_episode_ptr(rmv_env* env, float** last_return_dev, uint32_t** last_length_dev) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(env->flags & RMV_TRACK_EPISODES, "handle was created without RMV_TRACK_EPISODES");
+  if (last_return_dev) *last_return_dev = env->last_return;
+  if (last_length_dev) *last_length_dev = env->last_length;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_host_alloc(void** out, size_t bytes) {
+  RMV_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  RMV_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_host_free(void* p) {
+  if (p) RMV_CUDA(cudaFreeHost(p));
+  return RMV_OK;
+}

@@ -1,0 +1,409 @@
+// rmv_math.cuh — per-env arithmetic of the four native quadrotor step() functions.
+//
+// One env = one set of registers; no memory access in this file.  Every floating-point
+// operation goes through rf / rd below, which map to the individually rounded IEEE
+// intrinsics (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn, ...).  Those are never
+// contracted into FMAs or re-associated, so the evaluation order written here IS the
+// arithmetic: it is the reference's own left-to-right NumPy expression order
+// (gym_reinmav/envs/native/*.py, cited per function) rounded to float32.  tests/ check the
+// kernel against an independent NumPy float32 evaluation of the same expressions bit for bit.
+//
+// The file also compiles as plain C++ (tests/host_twin builds it with g++ -ffp-contract=off)
+// so the arithmetic can be checked in a container without a GPU.  That build is test
+// infrastructure only; the product has no CPU path.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RMV_HD __host__ __device__ __forceinline__
+#else
+#define RMV_HD inline
+#endif
+
+namespace rmv {
+
+// ------------------------------------------------------------------------------------------
+// rounded scalar types
+// ------------------------------------------------------------------------------------------
+struct rf {
+  float v;
+  RMV_HD rf() : v(0.0f) {}
+  RMV_HD rf(float x) : v(x) {}
+};
+#if defined(__CUDA_ARCH__)
+RMV_HD rf operator+(rf a, rf b) { return rf(__fadd_rn(a.v, b.v)); }
+RMV_HD rf operator-(rf a, rf b) { return rf(__fsub_rn(a.v, b.v)); }
+RMV_HD rf operator*(rf a, rf b) { return rf(__fmul_rn(a.v, b.v)); }
+RMV_HD rf operator/(rf a, rf b) { return rf(__fdiv_rn(a.v, b.v)); }
+RMV_HD rf rsqrt_exact(rf a) { return rf(__fsqrt_rn(a.v)); }
+#else
+RMV_HD rf operator+(rf a, rf b) { return rf(a.v + b.v); }
+RMV_HD rf operator-(rf a, rf b) { return rf(a.v - b.v); }
+RMV_HD rf operator*(rf a, rf b) { return rf(a.v * b.v); }
+RMV_HD rf operator/(rf a, rf b) { return rf(a.v / b.v); }
+RMV_HD rf rsqrt_exact(rf a) { return rf(sqrtf(a.v)); }
+#endif
+RMV_HD rf operator-(rf a) { return rf(-a.v); }
+RMV_HD rf sqrt(rf a) { return rsqrt_exact(a); }
+
+struct rd {
+  double v;
+  RMV_HD rd() : v(0.0) {}
+  RMV_HD rd(double x) : v(x) {}
+};
+#if defined(__CUDA_ARCH__)
+RMV_HD rd operator+(rd a, rd b) { return rd(__dadd_rn(a.v, b.v)); }
+RMV_HD rd operator-(rd a, rd b) { return rd(__dsub_rn(a.v, b.v)); }
+RMV_HD rd operator*(rd a, rd b) { return rd(__dmul_rn(a.v, b.v)); }
+RMV_HD rd sqrt(rd a) { return rd(__dsqrt_rn(a.v)); }
+#else
+RMV_HD rd operator+(rd a, rd b) { return rd(a.v + b.v); }
+RMV_HD rd operator-(rd a, rd b) { return rd(a.v - b.v); }
+RMV_HD rd operator*(rd a, rd b) { return rd(a.v * b.v); }
+RMV_HD rd sqrt(rd a) { return rd(::sqrt(a.v)); }
+#endif
+
+// ------------------------------------------------------------------------------------------
+// constants of one handle, pre-rounded to float32 on the host
+// ------------------------------------------------------------------------------------------
+struct DevParams {
+  float mass, load_mass, dt, neg_gravity, tether_len;
+  float pos_done, vel_done, thrust_scale;
+  float first_done_reward, later_done_reward;
+  float inv_total_mass;   // 1.0f / (mass + load_mass), two float32 ops
+  int thrust_clamp;
+};
+
+enum { QUAD2D = 0, QUAD2D_SLUNG = 1, QUAD3D = 2, QUAD3D_SLUNG = 3 };
+
+template <int KIND> struct Dims;
+template <> struct Dims<QUAD2D> { static constexpr int S = 5, A = 2, D = 2; };
+template <> struct Dims<QUAD2D_SLUNG> { static constexpr int S = 9, A = 2, D = 2; };
+template <> struct Dims<QUAD3D> { static constexpr int S = 10, A = 4, D = 3; };
+template <> struct Dims<QUAD3D_SLUNG> { static constexpr int S = 16, A = 4, D = 3; };
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  Counter/key convention: oracle/philox.py.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+constexpr uint32_t STREAM_RESET_BASE = 0u, STREAM_ACTION = 16u;
+
+RMV_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                          uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+    const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += PHILOX_W0;
+    k1 += PHILOX_W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// top 24 bits -> [0,1), exact; then lo + (hi-lo)*u with two rounded float32 ops
+RMV_HD float uniform_from_bits(uint32_t bits, float lo, float width) {
+  const rf u = rf((float)(bits >> 8)) * rf(5.9604644775390625e-08f);  // 2^-24, exact product
+  return (rf(lo) + rf(width) * u).v;
+}
+
+// reset(): S draws of U[-1,1) for (seed, global env id, episode) — replaces
+// self.np_random.uniform(low=-1.0, high=1.0, size=(S,)), quadrotor3d.py:184 and twins.
+template <int KIND>
+RMV_HD void reset_draws(uint64_t seed, uint64_t env_id, uint32_t episode, float s[Dims<KIND>::S]) {
+  constexpr int S = Dims<KIND>::S;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int b = 0; b < (S + 3) / 4; ++b) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), episode,
+                  ((STREAM_RESET_BASE + (uint32_t)KIND) << 8) | (uint32_t)b, k0, k1, w);
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if (4 * b + l < S) s[4 * b + l] = uniform_from_bits(w[l], -1.0f, 2.0f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// sin / cos in float32 with a pinned sequence (mirror of oracle/sincos32.py)
+// ------------------------------------------------------------------------------------------
+RMV_HD void sincos_pinned(float xin, float& s_out, float& c_out) {
+  const rf x(xin);
+  rf r;
+  int quad;
+  if (fabsf(xin) <= 1.0e5f) {
+    const rf kf(rintf((x * rf(0.63661977236758134f)).v));
+    r = ((x - kf * rf(1.5703125f)) - kf * rf(4.837512969970703125e-4f)) - kf * rf(7.54978995489188216e-8f);
+    quad = ((int)kf.v) & 3;
+  } else {  // huge, inf or NaN: reduce in float64 (rare, exact-sequence as well)
+    const rd xd((double)xin);
+    const rd kd(rint((xd * rd(0.6366197723675814)).v));
+    const rd rr = (xd - kd * rd(1.5707963267948966)) - kd * rd(6.123233995736766e-17);
+    const rd qd = kd - rd(4.0) * rd(floor((kd * rd(0.25)).v));
+    r = rf((float)rr.v);
+    quad = (qd.v == qd.v && fabs(qd.v) < 8.0) ? (int)qd.v : 0;
+  }
+  const rf z = r * r;
+  rf t = rf(-1.9515295891e-4f) * z;
+  t = t + rf(8.3321608736e-3f);
+  t = t * z;
+  t = t + rf(-1.6666654611e-1f);
+  t = t * z;
+  t = t * r;
+  const rf sr = t + r;
+  t = rf(2.443315711809948e-5f) * z;
+  t = t + rf(-1.388731625493765e-3f);
+  t = t * z;
+  t = t + rf(4.166664568298827e-2f);
+  t = t * z;
+  t = t * z;
+  t = t - rf(0.5f) * z;
+  const rf cr = t + rf(1.0f);
+  switch (quad) {
+    case 0: s_out = sr.v; c_out = cr.v; break;
+    case 1: s_out = cr.v; c_out = -sr.v; break;
+    case 2: s_out = -sr.v; c_out = -cr.v; break;
+    default: s_out = -cr.v; c_out = sr.v; break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared pieces
+// ------------------------------------------------------------------------------------------
+template <int D> RMV_HD rf norm(const rf (&c)[D]) {
+  rf acc = c[0] * c[0];
+#pragma unroll
+  for (int i = 1; i < D; ++i) acc = acc + c[i] * c[i];
+  return sqrt(acc);
+}
+
+// x' and v' of one body.  VEL_FIRST = quadrotor2d_slungload.py:100-101,109-110 (velocity, then
+// position with the NEW velocity); otherwise quadrotor3d.py:98-99 (position with the OLD velocity).
+template <int D, bool VEL_FIRST>
+RMV_HD void advance(rf (&x)[D], rf (&v)[D], const rf (&a)[D], rf dt) {
+  const rf half(0.5f);
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    if (VEL_FIRST) {
+      v[i] = v[i] + a[i] * dt;
+      x[i] = x[i] + v[i] * dt + half * a[i] * dt * dt;
+    } else {
+      x[i] = x[i] + v[i] * dt + half * a[i] * dt * dt;
+      v[i] = v[i] + a[i] * dt;
+    }
+  }
+}
+
+// pyquaternion semantics of Quaternion(att).rotation_matrix.dot([0,0,1]) followed by
+// .derivative(w) on the same (now normalised) object — quadrotor3d.py:94-96,101-102.
+// in:  q (un-normalised state quaternion), om (body rates)
+// out: e3 = R(q^) e_z, qdot = (0.5 q^) (x) (0, om)
+RMV_HD void attitude_3d(const rf (&q)[4], const rf (&om)[3], rf (&e3)[3], rf (&qdot)[4]) {
+  rf w = q[0], x = q[1], y = q[2], z = q[3];
+  const rf n2 = ((w * w + x * x) + y * y) + z * z;
+  const rf n = sqrt(n2);
+  const bool need = !(fabsf((rf(1.0f) - n2).v) < 1e-14f) && (n.v > 0.0f);
+  if (need) { w = w / n; x = x / n; y = y / n; z = z / n; }
+  e3[0] = ((x * z + w * y) + z * x) + y * w;
+  e3[1] = ((y * z + z * y) - w * x) - x * w;
+  e3[2] = ((z * z - y * y) - x * x) + w * w;
+  const rf h(0.5f);
+  const rf hw = h * w, hx = h * x, hy = h * y, hz = h * z;
+  qdot[0] = ((-hx) * om[0] - hy * om[1]) - hz * om[2];
+  qdot[1] = (hw * om[0] - hz * om[1]) + hy * om[2];
+  qdot[2] = (hz * om[0] + hw * om[1]) - hx * om[2];
+  qdot[3] = ((-hy) * om[0] + hx * om[1]) + hw * om[2];
+}
+
+// [cos(att + pi/2), sin(att + pi/2)] = [-sin att, cos att]  (quadrotor2d.py:88)
+RMV_HD void attitude_2d(rf theta, rf (&axis)[2]) {
+  float s, c;
+  sincos_pinned(theta.v, s, c);
+  axis[0] = rf(-s);
+  axis[1] = rf(c);
+}
+
+RMV_HD rf commanded_thrust(const DevParams& P, float a0) {
+  rf T = rf(P.thrust_scale) * rf(a0);               // quadrotor2d.py:75 (scale is 1 elsewhere)
+  if (P.thrust_clamp && T.v < 0.0f) T = rf(0.0f);    // quadrotor2d.py:76-77
+  return T;
+}
+
+// free quadrotor: acc = T/m * axis + g ; advance (quadrotor3d.py:96-99, quadrotor2d.py:88-90)
+template <int D>
+RMV_HD void quad_free(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[D], rf (&vel)[D]) {
+  const rf tm = T / rf(P.mass);
+  rf acc[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) acc[i] = tm * axis[i] + rf(i == D - 1 ? P.neg_gravity : 0.0f);
+  advance<D, false>(pos, vel, acc, rf(P.dt));
+}
+
+// quadrotor + tethered point load (quadrotor3d_slungload.py:101-145, quadrotor2d_slungload.py:93-132)
+template <int D, bool VEL_FIRST>
+RMV_HD void quad_slung(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[D], rf (&vel)[D],
+                       rf (&lp)[D], rf (&lv)[D]) {
+  const rf dt(P.dt), m(P.mass), ml(P.load_mass), L(P.tether_len);
+  rf g[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) g[i] = rf(i == D - 1 ? P.neg_gravity : 0.0f);
+  rf tv[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) tv[i] = lp[i] - pos[i];
+  // Switching predicate |tether| >= L (quadrotor3d_slungload.py:104).  After a taut step the
+  // projection (:126-127) leaves |tether| = L(1 +- ulp), so the branch rides on rounding noise;
+  // it is evaluated in float64 from the float32 state so that, given the same state, this path
+  // takes the float64 reference's branch (DESIGN.md "Switching surface").
+  rd acc2;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const rd d = rd((double)lp[i].v) - rd((double)pos[i].v);
+    acc2 = (i == 0) ? d * d : acc2 + d * d;
+  }
+  const bool taut = sqrt(acc2).v >= (double)P.tether_len;
+  const rf tm = T / m;
+  if (taut) {
+    const rf nt = norm<D>(tv);
+    rf u[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) u[i] = tv[i] / nt;
+    rf lv2 = lv[0] * lv[0];
+#pragma unroll
+    for (int i = 1; i < D; ++i) lv2 = lv2 + lv[i] * lv[i];
+    const rf c = m * L * lv2;  // SCALAR, broadcast-subtracted from every component (:110)
+    rf inner = u[0] * (T * axis[0] - c);
+#pragma unroll
+    for (int i = 1; i < D; ++i) inner = inner + u[i] * (T * axis[i] - c);
+    const rf inv(P.inv_total_mass);
+    rf la[D], back[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      la[i] = inv * (inner * u[i]) + g[i];
+      back[i] = (-g[i]) + la[i];  // the (x + g) - g rounding of :111,115
+    }
+    advance<D, VEL_FIRST>(lp, lv, la, dt);
+    const rf tn = ml * norm<D>(back);
+    rf acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = tm * axis[i] + g[i] + (tn * u[i]) / m;
+    advance<D, VEL_FIRST>(pos, vel, acc, dt);
+    // kinematic constraint (:126-128)
+    rf dv[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) dv[i] = lp[i] - pos[i];
+    const rf nd = norm<D>(dv);
+    rf dir[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) dir[i] = dv[i] / nd;
+    rf rel = (lv[0] - vel[0]) * dir[0];
+#pragma unroll
+    for (int i = 1; i < D; ++i) rel = rel + (lv[i] - vel[i]) * dir[i];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      lp[i] = pos[i] + dir[i] * L;
+      lv[i] = lv[i] - rel * dir[i];
+    }
+  } else {
+    advance<D, VEL_FIRST>(lp, lv, g, dt);
+    rf acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = tm * axis[i] + g[i];
+    advance<D, VEL_FIRST>(pos, vel, acc, dt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// one env, one step.  s: state components in the reference's tuple order; a: action.
+// Outputs the three norms the reward/done block needs (quadrotor3d.py:106-113 and twins).
+// ------------------------------------------------------------------------------------------
+template <int KIND> struct EnvStep;
+
+template <> struct EnvStep<QUAD3D> {  // quadrotor3d.py:81-113
+  static RMV_HD void run(const DevParams& P, float (&s)[10], const float (&a)[4], float& n_pos,
+                         float& n_vel, float& n_rew) {
+    rf pos[3] = {s[0], s[1], s[2]}, q[4] = {s[3], s[4], s[5], s[6]}, vel[3] = {s[7], s[8], s[9]};
+    const rf om[3] = {a[1], a[2], a[3]};
+    rf e3[3], qdot[4];
+    attitude_3d(q, om, e3, qdot);
+    quad_free<3>(P, commanded_thrust(P, a[0]), e3, pos, vel);
+    const rf dt(P.dt);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[3 + i] = (q[i] + qdot[i] * dt).v;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { s[i] = pos[i].v; s[7 + i] = vel[i].v; }
+    n_pos = norm<3>(pos).v;
+    n_vel = norm<3>(vel).v;
+    n_rew = n_pos;
+  }
+};
+
+template <> struct EnvStep<QUAD3D_SLUNG> {  // quadrotor3d_slungload.py:87-156
+  static RMV_HD void run(const DevParams& P, float (&s)[16], const float (&a)[4], float& n_pos,
+                         float& n_vel, float& n_rew) {
+    rf pos[3] = {s[0], s[1], s[2]}, q[4] = {s[3], s[4], s[5], s[6]}, vel[3] = {s[7], s[8], s[9]};
+    rf lp[3] = {s[10], s[11], s[12]}, lv[3] = {s[13], s[14], s[15]};
+    const rf om[3] = {a[1], a[2], a[3]};
+    rf e3[3], qdot[4];
+    attitude_3d(q, om, e3, qdot);
+    quad_slung<3, false>(P, commanded_thrust(P, a[0]), e3, pos, vel, lp, lv);
+    const rf dt(P.dt);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[3 + i] = (q[i] + qdot[i] * dt).v;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { s[i] = pos[i].v; s[7 + i] = vel[i].v; s[10 + i] = lp[i].v; s[13 + i] = lv[i].v; }
+    n_pos = norm<3>(lp).v;   // done: LOAD position, QUAD velocity (:149-152)
+    n_vel = norm<3>(vel).v;
+    n_rew = n_pos;           // reward: load position (:156)
+  }
+};
+
+template <> struct EnvStep<QUAD2D> {  // quadrotor2d.py:74-102
+  static RMV_HD void run(const DevParams& P, float (&s)[5], const float (&a)[2], float& n_pos,
+                         float& n_vel, float& n_rew) {
+    rf pos[2] = {s[0], s[1]}, vel[2] = {s[3], s[4]};
+    const rf th(s[2]);
+    rf axis[2];
+    attitude_2d(th, axis);
+    quad_free<2>(P, commanded_thrust(P, a[0]), axis, pos, vel);
+    s[2] = (th + rf(a[1]) * rf(P.dt)).v;
+    s[0] = pos[0].v; s[1] = pos[1].v; s[3] = vel[0].v; s[4] = vel[1].v;
+    n_pos = norm<2>(pos).v;
+    n_vel = norm<2>(vel).v;
+    n_rew = n_pos;
+  }
+};
+
+template <> struct EnvStep<QUAD2D_SLUNG> {  // quadrotor2d_slungload.py:79-143
+  static RMV_HD void run(const DevParams& P, float (&s)[9], const float (&a)[2], float& n_pos,
+                         float& n_vel, float& n_rew) {
+    rf pos[2] = {s[0], s[1]}, vel[2] = {s[3], s[4]}, lp[2] = {s[5], s[6]}, lv[2] = {s[7], s[8]};
+    const rf th(s[2]);
+    rf axis[2];
+    attitude_2d(th, axis);
+    quad_slung<2, true>(P, commanded_thrust(P, a[0]), axis, pos, vel, lp, lv);
+    s[2] = (th + rf(a[1]) * rf(P.dt)).v;
+    s[0] = pos[0].v; s[1] = pos[1].v; s[3] = vel[0].v; s[4] = vel[1].v;
+    s[5] = lp[0].v; s[6] = lp[1].v; s[7] = lv[0].v; s[8] = lv[1].v;
+    n_pos = norm<2>(lp).v;   // done: load position / load velocity (:136-139)
+    n_vel = norm<2>(lv).v;
+    n_rew = norm<2>(pos).v;  // reward: QUAD position (:143)
+  }
+};
+
+// done / reward block shared by the four envs (quadrotor3d.py:106-122).  Strict '>' so that a
+// NaN norm is "not done", as in the reference; `ever_done` is steps_beyond_done is not None.
+RMV_HD bool is_done(const DevParams& P, float n_pos, float n_vel) {
+  return (n_pos > P.pos_done) || (n_vel > P.vel_done);
+}
+RMV_HD float reward_of(const DevParams& P, bool done, bool ever_done, float n_rew) {
+  return done ? (ever_done ? P.later_done_reward : P.first_done_reward) : -n_rew;
+}
+
+}  // namespace rmv

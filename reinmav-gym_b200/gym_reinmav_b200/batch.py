@@ -1,0 +1,182 @@
+"""QuadBatch — Python owner of one ``rmv_env`` handle (N envs of one kind on one GPU).
+
+Thin by design: it converts arguments to raw device pointers / a stream handle and calls the
+C-ABI.  Device buffers may be passed as ``torch.Tensor`` (CUDA), as any object with
+``__cuda_array_interface__``, or as an integer address.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from ._capi import ACT_AOS, ACT_SOA, check, lib
+
+ENV_IDS = {
+    "quadrotor2d-v0": _capi.QUAD2D,
+    "quadrotor2d-slungload-v0": _capi.QUAD2D_SLUNG,
+    "quadrotor3d-v0": _capi.QUAD3D,
+    "quadrotor3d-slungload-v0": _capi.QUAD3D_SLUNG,
+}
+
+
+def _ptr(x):
+    """Raw address of a device (or pinned host) buffer; None -> NULL."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):                       # torch.Tensor
+        if not x.is_contiguous():
+            raise ValueError("tensor passed to librmv must be contiguous")
+        return x.data_ptr()
+    cai = getattr(x, "__cuda_array_interface__", None)
+    if cai is not None:
+        return cai["data"][0]
+    if isinstance(x, np.ndarray):                    # host buffer (for the *_host entry points)
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array passed to librmv must be C-contiguous")
+        return x.ctypes.data
+    raise TypeError("cannot take the address of %r" % type(x))
+
+
+def _stream(stream, device):
+    if stream is None:
+        import sys
+        torch = sys.modules.get("torch")
+        if torch is not None and torch.cuda.is_available():
+            return torch.cuda.current_stream(device).cuda_stream
+        return None
+    if isinstance(stream, int):
+        return stream or None
+    return stream.cuda_stream                        # torch.cuda.Stream
+
+
+class _DeviceView:
+    """Zero-copy window onto handle-owned device memory (``torch.as_tensor(view, device=...)``)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2, "strides": None}
+        self._owner = owner                           # keeps the handle alive
+
+
+class QuadBatch:
+    def __init__(self, kind, num_envs, device=0, seed=0, env_id_offset=0, params=None, track_episodes=False):
+        if isinstance(kind, str):
+            if kind not in ENV_IDS:
+                raise KeyError("unknown env id %r (have %s)" % (kind, sorted(ENV_IDS)))
+            kind = ENV_IDS[kind]
+        self.kind, self.device, self.seed = int(kind), int(device), int(seed)
+        self._h = ctypes.c_void_p()
+        p = None
+        if params is not None:
+            p = _capi.default_params(self.kind)
+            for k, v in dict(params).items():
+                if not hasattr(p, k):
+                    raise KeyError("rmv_params has no field %r" % k)
+                setattr(p, k, v)
+        flags = _capi.TRACK_EPISODES if track_episodes else 0
+        check(lib().rmv_create(ctypes.byref(self._h), self.kind, int(num_envs), int(env_id_offset), self.device,
+                               self.seed & 0xFFFFFFFFFFFFFFFF, ctypes.byref(p) if p is not None else None, flags))
+        s, a, n, ld = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
+        check(lib().rmv_dims(self._h, ctypes.byref(s), ctypes.byref(a), ctypes.byref(n), ctypes.byref(ld)))
+        self.state_dim, self.action_dim, self.num_envs, self.ld = s.value, a.value, n.value, ld.value
+        self.env_id_offset = int(env_id_offset)
+        self.track_episodes = bool(track_episodes)
+        self.launches = 0                               # kernels launched through this handle
+
+    # ---------------------------------------------------------------- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().rmv_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def params(self):
+        p = _capi.Params()
+        check(lib().rmv_get_params(self._h, ctypes.byref(p)))
+        return p.as_dict()
+
+    def set_seed(self, seed):
+        self.seed = int(seed)
+        check(lib().rmv_set_seed(self._h, self.seed & 0xFFFFFFFFFFFFFFFF))
+
+    def set_tuning(self, vec=0, block=256):
+        check(lib().rmv_set_tuning(self._h, int(vec), int(block)))
+
+    # ---------------------------------------------------------------- hot path (device buffers)
+    def reset(self, mask=None, obs=None, stream=None):
+        check(lib().rmv_reset(self._h, _ptr(mask), _ptr(obs), _stream(stream, self.device)))
+        self.launches += 1
+
+    def step(self, actions, reward, done, obs=None, auto_reset=True, layout=ACT_AOS, act_ld=0, stream=None):
+        check(lib().rmv_step(self._h, _ptr(actions), layout, int(act_ld), _ptr(reward), _ptr(done), _ptr(obs),
+                             1 if auto_reset else 0, _stream(stream, self.device)))
+        self.launches += 1
+
+    def step_many(self, n_steps, actions, reward=None, done=None, out_ld=0, layout=ACT_SOA, act_ld=0, fused=False,
+                  stream=None):
+        check(lib().rmv_step_many(self._h, int(n_steps), _ptr(actions), layout, int(act_ld), _ptr(reward), _ptr(done),
+                                  int(out_ld or self.num_envs), 1 if fused else 0, _stream(stream, self.device)))
+        self.launches += 1 if fused else int(n_steps)
+
+    # ---------------------------------------------------------------- hot path (host buffers)
+    def step_host(self, actions, reward, done, obs=None, auto_reset=True, stream=None):
+        check(lib().rmv_step_host(self._h, _ptr(actions), _ptr(reward), _ptr(done), _ptr(obs),
+                                  1 if auto_reset else 0, _stream(stream, self.device)))
+        self.launches += 1
+
+    def reset_host(self, obs, stream=None):
+        check(lib().rmv_reset_host(self._h, _ptr(obs), _stream(stream, self.device)))
+        self.launches += 1
+
+    # ---------------------------------------------------------------- state access
+    def get_state(self, stream=None):
+        out = np.empty((self.num_envs, self.state_dim), dtype=np.float32)
+        check(lib().rmv_get_state(self._h, out.ctypes.data, 0, _stream(stream, self.device)))
+        return out
+
+    def set_state(self, rows, stream=None):
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.shape != (self.num_envs, self.state_dim):
+            raise ValueError("state must be [%d, %d]" % (self.num_envs, self.state_dim))
+        check(lib().rmv_set_state(self._h, rows.ctypes.data, 0, _stream(stream, self.device)))
+
+    def get_episode_words(self, stream=None):
+        out = np.empty(self.num_envs, dtype=np.uint32)
+        check(lib().rmv_get_episode(self._h, out.ctypes.data, 0, _stream(stream, self.device)))
+        return out
+
+    def set_episode_words(self, words, stream=None):
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        check(lib().rmv_set_episode(self._h, words.ctypes.data, 0, _stream(stream, self.device)))
+
+    def state_view(self):
+        """Device view of the component-major state, shape [S, ld] float32 (columns >= N are padding)."""
+        sp, ep = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib().rmv_state_ptr(self._h, ctypes.byref(sp), ctypes.byref(ep)))
+        return _DeviceView(sp.value, (self.state_dim, self.ld), "<f4", self)
+
+    def episode_stats(self, stream=None):
+        out = (ctypes.c_double * 4)()
+        check(lib().rmv_episode_stats(self._h, out, _stream(stream, self.device)))
+        return {"episodes": out[0], "return_sum": out[1], "length_sum": out[2], "env_steps": out[3]}
+
+    def last_episode_views(self):
+        rp, lp = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib().rmv_episode_ptr(self._h, ctypes.byref(rp), ctypes.byref(lp)))
+        return (_DeviceView(rp.value, (self.ld,), "<f4", self), _DeviceView(lp.value, (self.ld,), "<u4", self))
+
+
+def fill_uniform_actions(actions, num_envs, action_dim, low, high, seed, env_id_offset=0, step_index=0,
+                         layout=ACT_AOS, act_ld=0, device=0, stream=None):
+    """Random-policy actions ~ U[low, high) written on the device (Philox, keyed by global env id)."""
+    check(lib().rmv_fill_uniform_actions(_ptr(actions), int(num_envs), int(action_dim), layout, int(act_ld),
+                                         float(low), float(high), int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_id_offset),
+                                         int(step_index), int(device), _stream(stream, device)))

@@ -1,0 +1,208 @@
+"""QuadVecEnv — N quadrotor envs behind the baselines ``VecEnv`` protocol.
+
+The reference vectorises by process fan-out: ``make_vec_env(env_id, 'native', num_env, ...)``
+(/root/reference/gym_reinmav/run.py:89) builds a ``DummyVecEnv``/``SubprocVecEnv`` of N Python
+env objects behind ``Monitor`` wrappers, and ``ppo2``'s Runner drives it with
+``obs, rews, dones, infos = env.step(actions)`` (run.py:63-68, --play loop :192-211).  This class
+exposes the same surface (``num_envs``, ``observation_space``, ``action_space``, ``reset``,
+``step_async``/``step_wait``/``step``, ``close``, auto-reset on done with the reset observation
+returned, ``infos[i]['episode'] = {'r','l'}`` at episode end) over ONE fused CUDA kernel per step.
+
+Two ways to step:
+
+* ``step(actions_numpy)`` — host buffers in, host buffers out (pinned staging, H2D + kernel +
+  D2H inside ``rmv_step_host``); what an unmodified baselines/stable-baselines learner calls.
+* ``step_tensor(actions_cuda_tensor)`` — everything stays on the device; returns torch tensors
+  that alias internal buffers (valid until the next call).
+"""
+import ctypes
+from collections.abc import Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, lib
+from .batch import ENV_IDS, QuadBatch
+from .spaces import Box
+
+# action_space / observation_space as the reference declares them
+# (quadrotor2d.py:62-65, quadrotor2d_slungload.py:68-71, quadrotor3d.py:70-71, quadrotor3d_slungload.py:75-78)
+_ACTION_BOX = {_capi.QUAD2D: (-10.0, 10.0), _capi.QUAD2D_SLUNG: (-10.0, 10.0),
+               _capi.QUAD3D: (0.0, 10.0), _capi.QUAD3D_SLUNG: (-10.0, 10.0)}
+
+
+def make_spaces(kind):
+    s, a = _capi.kind_dims(kind)
+    lo, hi = _ACTION_BOX[kind]
+    return (Box(low=-10.0, high=10.0, shape=(s,), dtype=np.float32),
+            Box(low=lo, high=hi, shape=(a,), dtype=np.float32))
+
+
+class _Pinned:
+    """Page-locked host array (cudaHostAlloc through the C-ABI) exposed as a NumPy array."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = ctypes.c_void_p()
+        check(lib().rmv_host_alloc(ctypes.byref(self._p), self.nbytes))
+        raw = (ctypes.c_char * max(self.nbytes, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().rmv_host_free(self._p)
+            self._p = ctypes.c_void_p()
+
+
+class SparseInfos(Sequence):
+    """``infos`` without building N dicts per step: ``infos[i]`` is ``{}`` unless env i just
+    finished an episode, in which case it is ``{'episode': {'r': return, 'l': length}}``
+    (the key baselines' ppo2 Runner collects: ``info.get('episode')``)."""
+
+    _EMPTY = {}
+
+    def __init__(self, n, finished):
+        self._n, self._fin = n, finished
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        return self._fin.get(i, self._EMPTY)
+
+    def episodes(self):
+        """Only the finished ones: {env index: {'r':..., 'l':...}}."""
+        return {i: d["episode"] for i, d in self._fin.items()}
+
+
+class QuadVecEnv:
+    metadata = {"render.modes": ["human"]}
+    reward_range = (-float("inf"), float("inf"))
+    spec = None
+
+    def __init__(self, env_id, num_envs, device=0, seed=0, env_id_offset=0, params=None, monitor=True,
+                 return_obs=True):
+        self.env_id = env_id
+        self.batch = QuadBatch(env_id, num_envs, device=device, seed=seed, env_id_offset=env_id_offset,
+                               params=params, track_episodes=monitor)
+        self.num_envs = self.batch.num_envs
+        self.device = device
+        self.monitor = monitor
+        self.return_obs = return_obs
+        self.observation_space, self.action_space = make_spaces(self.batch.kind)
+        n, S, A = self.num_envs, self.batch.state_dim, self.batch.action_dim
+        self._act = _Pinned((n, A), np.float32)
+        self._obs = _Pinned((n, S), np.float32)
+        self._rew = _Pinned((n,), np.float32)
+        self._done = _Pinned((n,), np.uint8)
+        self._pending = None
+        self._t = None            # torch buffers for step_tensor, made on first use
+        self.closed = False
+
+    # ------------------------------------------------------------------ VecEnv protocol (host)
+    def seed(self, seed=None):
+        if seed is not None:
+            self.batch.set_seed(seed)
+        return [seed]
+
+    def reset(self):
+        self.batch.reset_host(self._obs.array)
+        return self._obs.array.copy()
+
+    def step_async(self, actions):
+        a = np.asarray(actions, dtype=np.float32)
+        if a.shape != self._act.array.shape:
+            raise ValueError("actions must have shape %s, got %s" % (self._act.array.shape, a.shape))
+        self._act.array[...] = a
+        self._pending = True
+
+    def step_wait(self):
+        if not self._pending:
+            raise RuntimeError("step_wait() without step_async()")
+        self._pending = None
+        self.batch.step_host(self._act.array, self._rew.array, self._done.array,
+                             self._obs.array if self.return_obs else None, auto_reset=True)
+        done = self._done.array.astype(bool)
+        infos = SparseInfos(self.num_envs, self._finished(done) if self.monitor else {})
+        obs = self._obs.array.copy() if self.return_obs else None
+        return obs, self._rew.array.copy(), done, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def _finished(self, done):
+        idx = np.flatnonzero(done)
+        if idx.size == 0:
+            return {}
+        import torch
+        rv, lv = self.batch.last_episode_views()
+        dev = "cuda:%d" % self.device
+        sel = torch.as_tensor(idx, device=dev)
+        r = torch.as_tensor(rv, device=dev)[sel].cpu().numpy()
+        l = torch.as_tensor(lv, device=dev).view(torch.int32)[sel].cpu().numpy()
+        return {int(i): {"episode": {"r": float(r[k]), "l": int(l[k])}} for k, i in enumerate(idx)}
+
+    # ------------------------------------------------------------------ device-resident stepping
+    def _tensors(self):
+        if self._t is None:
+            import torch
+            dev = "cuda:%d" % self.device
+            n, S = self.num_envs, self.batch.state_dim
+            self._t = dict(obs=torch.empty((n, S), dtype=torch.float32, device=dev),
+                           rew=torch.empty((n,), dtype=torch.float32, device=dev),
+                           done=torch.empty((n,), dtype=torch.uint8, device=dev),
+                           state=torch.as_tensor(self.batch.state_view(), device=dev))
+        return self._t
+
+    def reset_tensor(self):
+        t = self._tensors()
+        self.batch.reset(obs=t["obs"])
+        return t["obs"]
+
+    def step_tensor(self, actions, want_obs=True):
+        """actions: float32 CUDA tensor [N, A] (row per env).  Returns (obs [N,S] or None,
+        reward [N], done [N] uint8) as tensors aliasing internal buffers."""
+        t = self._tensors()
+        self.batch.step(actions, t["rew"], t["done"], obs=t["obs"] if want_obs else None, auto_reset=True)
+        return (t["obs"] if want_obs else None), t["rew"], t["done"]
+
+    def state_tensor(self):
+        """Component-major state [S, N] (a view; obs == state in these envs)."""
+        return self._tensors()["state"][:, :self.num_envs]
+
+    def episode_stats(self):
+        return self.batch.episode_stats()
+
+    # ------------------------------------------------------------------ misc protocol
+    def render(self, mode="human"):
+        return None           # the reference's viewers (pyglet / vpython) need a display; not part of this path
+
+    def get_images(self):
+        return []
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def close(self):
+        if self.closed:
+            return
+        self.closed = True
+        self._t = None
+        for b in (self._act, self._obs, self._rew, self._done):
+            b.free()
+        self.batch.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

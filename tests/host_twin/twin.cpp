@@ -1,0 +1,66 @@
+// Host build of csrc/rmv_math.cuh — TEST INFRASTRUCTURE ONLY.
+// Lets the CPU test-suite check, without a GPU, that the arithmetic the kernels inline
+// equals the NumPy float32 model (oracle/batch.py, dtype=float32) bit for bit.
+// Built by tests/host_twin/build.py with  g++ -O2 -ffp-contract=off -fno-fast-math.
+#include "rmv_math.cuh"
+#include "rmv.h"
+#include <string.h>
+
+using namespace rmv;
+
+static DevParams to_dev(const rmv_params& p) {
+  DevParams d;
+  d.mass = p.mass; d.load_mass = p.load_mass; d.dt = p.dt; d.neg_gravity = -p.gravity;
+  d.tether_len = p.tether_len; d.pos_done = p.pos_done; d.vel_done = p.vel_done;
+  d.thrust_scale = p.thrust_scale; d.first_done_reward = p.first_done_reward;
+  d.later_done_reward = p.later_done_reward; d.thrust_clamp = p.thrust_clamp;
+  volatile float tot = p.mass + p.load_mass;
+  d.inv_total_mass = 1.0f / tot;
+  return d;
+}
+
+template <int KIND>
+static void run(const DevParams& P, long n, const float* s_in, const float* a_in, float* s_out,
+                float* norms) {
+  constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
+  for (long e = 0; e < n; ++e) {
+    float s[S], a[A];
+    memcpy(s, s_in + e * S, sizeof(s));
+    memcpy(a, a_in + e * A, sizeof(a));
+    EnvStep<KIND>::run(P, s, a, norms[3 * e], norms[3 * e + 1], norms[3 * e + 2]);
+    memcpy(s_out + e * S, s, sizeof(s));
+  }
+}
+
+extern "C" int twin_step(int kind, const rmv_params* p, long n, const float* s_in,
+                         const float* a_in, float* s_out, float* norms) {
+  const DevParams P = to_dev(*p);
+  switch (kind) {
+    case QUAD2D: run<QUAD2D>(P, n, s_in, a_in, s_out, norms); break;
+    case QUAD2D_SLUNG: run<QUAD2D_SLUNG>(P, n, s_in, a_in, s_out, norms); break;
+    case QUAD3D: run<QUAD3D>(P, n, s_in, a_in, s_out, norms); break;
+    case QUAD3D_SLUNG: run<QUAD3D_SLUNG>(P, n, s_in, a_in, s_out, norms); break;
+    default: return -1;
+  }
+  return 0;
+}
+
+extern "C" int twin_reset_draws(int kind, unsigned long long seed, unsigned long long env_id,
+                                unsigned episode, float* out) {
+  switch (kind) {
+    case QUAD2D: { float s[5]; reset_draws<QUAD2D>(seed, env_id, episode, s); memcpy(out, s, sizeof(s)); } break;
+    case QUAD2D_SLUNG: { float s[9]; reset_draws<QUAD2D_SLUNG>(seed, env_id, episode, s); memcpy(out, s, sizeof(s)); } break;
+    case QUAD3D: { float s[10]; reset_draws<QUAD3D>(seed, env_id, episode, s); memcpy(out, s, sizeof(s)); } break;
+    case QUAD3D_SLUNG: { float s[16]; reset_draws<QUAD3D_SLUNG>(seed, env_id, episode, s); memcpy(out, s, sizeof(s)); } break;
+    default: return -1;
+  }
+  return 0;
+}
+
+extern "C" void twin_sincos(long n, const float* x, float* s, float* c) {
+  for (long i = 0; i < n; ++i) sincos_pinned(x[i], s[i], c[i]);
+}
+
+extern "C" void twin_philox(const unsigned* ctr, const unsigned* key, unsigned* out) {
+  philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}

@@ -1,0 +1,71 @@
+"""The C-ABI library loads, exports every symbol include/rmv.h declares, and its device-free
+queries answer correctly.  No compute call is made here (CPU only)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "rmv.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rmv_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from gym_reinmav_b200 import _capi
+    _capi.lib()
+    return _capi
+
+
+def test_header_and_binding_agree(capi):
+    declared = _declared()
+    assert len(declared) >= 25
+    assert sorted(capi.SIGNATURES) == declared
+
+
+def test_library_exports_every_declared_symbol(capi):
+    raw = ctypes.CDLL(capi.LIB_PATH)
+    for name in _declared():
+        assert hasattr(raw, name), name
+
+
+def test_device_free_queries(capi):
+    lib = capi.lib()
+    assert lib.rmv_abi_version() == 1
+    assert [capi.kind_dims(k) for k in range(4)] == [(5, 2), (9, 2), (10, 4), (16, 4)]
+    assert capi.action_bounds(capi.QUAD3D) == (0.0, 10.0)
+    assert capi.action_bounds(capi.QUAD2D) == (-10.0, 10.0)
+    assert lib.rmv_padded_ld(1) == 128 and lib.rmv_padded_ld(128) == 128 and lib.rmv_padded_ld(129) == 256
+    assert lib.rmv_padded_ld(1 << 20) == 1 << 20
+
+
+def test_default_params_are_the_reference_constants(capi):
+    from oracle.batch import default_params
+    for kind in range(4):
+        got = capi.default_params(kind).as_dict()
+        want = default_params(kind)
+        for k, v in want.items():
+            assert got[k] == np.float32(v) if isinstance(v, float) else got[k] == v, (kind, k)
+
+
+def test_errors_are_reported_not_raised_in_c(capi):
+    lib = capi.lib()
+    assert lib.rmv_kind_dims(7, None, None) == -1
+    assert b"unknown env kind" in lib.rmv_last_error()
+    with pytest.raises(capi.RmvError):
+        capi.kind_dims(-1)
+
+
+def test_sparse_infos():
+    from gym_reinmav_b200.vec_env import SparseInfos
+    infos = SparseInfos(5, {3: {"episode": {"r": 1.5, "l": 7}}})
+    assert len(infos) == 5 and infos[0] == {} and infos[3]["episode"]["l"] == 7 and infos[-2]["episode"]["r"] == 1.5
+    assert [i.get("episode") for i in infos].count(None) == 4
+    with pytest.raises(IndexError):
+        infos[5]

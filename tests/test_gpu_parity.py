@@ -1,0 +1,325 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle.  Needs a GPU.
+
+Bars (BASELINE.json north_star):
+  * done masks bit-exact, state / reward bit-exact against the float32 model T1
+    (same formulas, same operation order, no FMA) — every kind, every launch variant;
+  * against the float64 reference arithmetic T0 (pinned to the reference source by
+    tests/golden): |x_gpu - x_ref| <= TOL * max(1, |x_ref|), TOL = 1e-5, over 1000 free-running
+    steps with identical (seed, action) sequences, done masks identical;
+  * against the committed reference trajectories tests/golden/*.npz.
+"""
+import numpy as np
+import pytest
+
+from oracle import philox
+from oracle.batch import ACTION_BOUNDS, ACTION_DIM, KIND_OF_ID, STATE_DIM, BatchOracle
+from tests.util import load_golden, random_actions, same_bits, wide_states
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+ENV_IDS = list(KIND_OF_ID)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    torch.cuda.init()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def rmv():
+    import gym_reinmav_b200
+    return gym_reinmav_b200
+
+
+def _buffers(torch, n, S):
+    dev = "cuda:0"
+    return (torch.empty(n, dtype=torch.float32, device=dev), torch.empty(n, dtype=torch.uint8, device=dev),
+            torch.empty((n, S), dtype=torch.float32, device=dev))
+
+
+def _close(scale_ref, got, ref, tol=TOL):
+    return np.abs(got.astype(np.float64) - ref) <= tol * np.maximum(1.0, np.abs(scale_ref))
+
+
+# ------------------------------------------------------------------------------------------ reset
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_reset_draws_match_oracle(torch, rmv, env_id):
+    n, off, seed = 1000, 12345678901, 77
+    b = rmv.QuadBatch(env_id, n, seed=seed, env_id_offset=off)
+    o = BatchOracle(env_id, n, seed=seed, env_id_offset=off, dtype=np.float32)
+    assert (b.get_state() == 0).all()
+    b.reset()
+    assert same_bits(b.get_state(), o.reset())
+    mask = (np.arange(n) % 3 == 0)
+    obs = torch.empty((n, b.state_dim), dtype=torch.float32, device="cuda:0")
+    b.reset(mask=torch.as_tensor(mask.astype(np.uint8), device="cuda:0"), obs=obs)
+    want = o.reset(mask=mask)
+    assert same_bits(b.get_state(), want) and same_bits(obs.cpu().numpy(), want)
+    words = b.get_episode_words()
+    assert np.array_equal(words, o.episode) and (words[mask] == 2).all() and (words[~mask] == 1).all()
+    b.close()
+
+
+# ------------------------------------------------------------------------------------------ one step, every variant
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+@pytest.mark.parametrize("vec", [1, 2, 4])
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_single_step_bitwise(torch, rmv, env_id, vec, layout):
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    rng = np.random.RandomState(kind * 10 + vec)
+    n = 20000 + 3                                         # ragged tail: not a multiple of the vector width
+    s0 = wide_states(kind, n, rng)
+    a = random_actions(kind, (n,), rng)
+    o = BatchOracle(kind, n, dtype=np.float32)
+    o.state = s0.T.copy()
+    obs_ref, rew_ref, done_ref = o.step(a, auto_reset=False)
+
+    b = rmv.QuadBatch(env_id, n)
+    b.set_tuning(vec=vec)
+    b.set_state(s0)
+    rew, done, obs = _buffers(torch, n, S)
+    if layout == "aos":
+        act = torch.as_tensor(a, device="cuda:0")
+        b.step(act, rew, done, obs=obs, auto_reset=False)
+    else:
+        ld = b.ld
+        act = torch.zeros((A, ld), dtype=torch.float32, device="cuda:0")
+        act[:, :n] = torch.as_tensor(a.T.copy(), device="cuda:0")
+        b.step(act, rew, done, obs=obs, auto_reset=False, layout=1, act_ld=ld)
+    torch.cuda.synchronize()
+    got = b.get_state()
+    nan_both = np.isnan(got) & np.isnan(obs_ref)
+    assert ((got.view(np.uint32) == obs_ref.view(np.uint32)) | nan_both).all()
+    assert np.array_equal(done.cpu().numpy().astype(bool), done_ref)
+    assert same_bits(rew.cpu().numpy(), rew_ref)
+    o_np = obs.cpu().numpy()
+    assert ((o_np.view(np.uint32) == obs_ref.view(np.uint32)) | nan_both).all()
+    assert 0.02 < done_ref.mean() < 0.6
+    # gym.Env semantics: nothing was reset, the ever-done bit is set exactly on the done envs
+    words = b.get_episode_words()
+    assert np.array_equal((words >> 31).astype(bool), done_ref) and ((words & 0x7FFFFFFF) == 0).all()
+    b.close()
+
+
+# ------------------------------------------------------------------------------------------ rollouts vs T1 (bit-exact)
+def _rollout_bitwise(torch, rmv, env_id, n, steps, vec, seed, check_state_every):
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    lo, hi = ACTION_BOUNDS[kind]
+    off = 5 * n
+    b = rmv.QuadBatch(env_id, n, seed=seed, env_id_offset=off)
+    b.set_tuning(vec=vec)
+    o = BatchOracle(kind, n, seed=seed, env_id_offset=off, dtype=np.float32)
+    b.reset()
+    o.reset()
+    rew, done, _ = _buffers(torch, n, S)
+    act = torch.empty((n, A), dtype=torch.float32, device="cuda:0")
+    n_done = 0
+    for t in range(steps):
+        rmv.fill_uniform_actions(act, n, A, lo, hi, seed, env_id_offset=off, step_index=t)
+        b.step(act, rew, done)
+        a_ref = philox.uniform_f32(seed, o.env_ids, np.full(n, t), philox.STREAM_ACTION, A, lo, hi).T
+        if t % 97 == 0:
+            assert same_bits(act.cpu().numpy(), np.ascontiguousarray(a_ref)), "action generator, step %d" % t
+        _, rew_ref, done_ref = o.step(a_ref)
+        assert np.array_equal(done.cpu().numpy().astype(bool), done_ref), "done mask, step %d" % t
+        assert same_bits(rew.cpu().numpy(), rew_ref), "reward, step %d" % t
+        n_done += int(done_ref.sum())
+        if (t + 1) % check_state_every == 0 or t == steps - 1:
+            assert same_bits(b.get_state(), o.obs()), "state, step %d" % t
+    words = b.get_episode_words()
+    assert np.array_equal(words & 0x7FFFFFFF, o.episode) and np.array_equal((words >> 31).astype(bool), o.ever_done)
+    b.close()
+    return n_done
+
+
+def test_quadrotor3d_65536_envs_1000_steps_bitwise(torch, rmv):
+    """BASELINE config 2: quadrotor3d-v0, N = 65536, random-policy actions, 1000 steps."""
+    n_done = _rollout_bitwise(torch, rmv, "quadrotor3d-v0", 65536, 1000, vec=0, seed=0, check_state_every=100)
+    assert 0.005 < n_done / (65536 * 1000) < 0.03        # ~1.3 % of env-steps end an episode
+
+
+def test_quadrotor3d_slungload_65536_envs_bitwise(torch, rmv):
+    """BASELINE config 3: slung-load variant, N = 65536 (16-dim state, both tether branches)."""
+    _rollout_bitwise(torch, rmv, "quadrotor3d-slungload-v0", 65536, 300, vec=0, seed=1, check_state_every=100)
+
+
+@pytest.mark.parametrize("env_id", ["quadrotor2d-v0", "quadrotor2d-slungload-v0"])
+def test_planar_rollouts_bitwise(torch, rmv, env_id):
+    _rollout_bitwise(torch, rmv, env_id, 65536, 300, vec=0, seed=2, check_state_every=100)
+
+
+@pytest.mark.parametrize("vec", [1, 4])
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_small_ragged_rollouts_bitwise(torch, rmv, env_id, vec):
+    _rollout_bitwise(torch, rmv, env_id, 1000 + 1, 200, vec=vec, seed=3, check_state_every=50)
+
+
+# ------------------------------------------------------------------------------------------ vs float64 reference arithmetic
+@pytest.mark.parametrize("env_id", ["quadrotor3d-v0", "quadrotor2d-v0"])
+def test_free_running_1000_steps_vs_float64(torch, rmv, env_id):
+    """north_star: state/reward within 1e-5 and done masks bit-exact vs the reference over 1000 steps."""
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    lo, hi = ACTION_BOUNDS[kind]
+    n, steps, seed = 16384, 1000, 3
+    b = rmv.QuadBatch(env_id, n, seed=seed)
+    o = BatchOracle(kind, n, seed=seed, dtype=np.float64)
+    b.reset()
+    o.reset()
+    rew, done, obs = _buffers(torch, n, S)
+    worst = 0.0
+    for t in range(steps):
+        a = philox.uniform_f32(seed, o.env_ids, np.full(n, t), philox.STREAM_ACTION, A, lo, hi).T.copy()
+        b.step(torch.as_tensor(a, device="cuda:0"), rew, done, obs=obs)
+        obs_ref, rew_ref, done_ref = o.step(a)
+        d = done.cpu().numpy().astype(bool)
+        mism = d != done_ref
+        # a float32 path can only disagree where the reference's own norm sits within rounding of the
+        # threshold; such events are counted, must be provably ambiguous, and the env is re-synchronised
+        assert (o.done_margin[mism] < 1e-5).all()
+        assert mism.sum() <= 2
+        ok = ~mism
+        got, r = obs.cpu().numpy(), rew.cpu().numpy()
+        assert _close(obs_ref[ok], got[ok], obs_ref[ok]).all(), "state, step %d" % t
+        assert _close(rew_ref[ok], r[ok], rew_ref[ok]).all(), "reward, step %d" % t
+        worst = max(worst, float(np.abs(got[ok] - obs_ref[ok]).max()))
+        if mism.any():
+            st = b.get_state()
+            st[mism] = o.obs()[mism].astype(np.float32)
+            b.set_state(st)
+            w = b.get_episode_words()
+            w[mism] = (o.episode[mism] | (o.ever_done[mism].astype(np.uint32) << 31)).astype(np.uint32)
+            b.set_episode_words(w)
+    print("%s: worst |state - ref| over %d env-steps = %.3g" % (env_id, n * steps, worst))
+    b.close()
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_teacher_forced_vs_float64(torch, rmv, env_id):
+    """Each step the float64 oracle starts from the kernel's own float32 state (exact in float64).
+    For the slung-load kinds this is the meaningful comparison: free-running, the reference itself
+    decides the taut/slack branch on 1-ulp noise after every taut step."""
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    lo, hi = ACTION_BOUNDS[kind]
+    n, steps, seed = 8192, 300, 11
+    b = rmv.QuadBatch(env_id, n, seed=seed)
+    o = BatchOracle(kind, n, seed=seed, dtype=np.float64)
+    b.reset()
+    o.reset()
+    rew, done, obs = _buffers(torch, n, S)
+    state = b.get_state()
+    taut_steps = branch_mismatch = done_mismatch = 0
+    for t in range(steps):
+        a = philox.uniform_f32(seed, o.env_ids, np.full(n, t), philox.STREAM_ACTION, A, lo, hi).T.copy()
+        o.state = state.T.astype(np.float64)
+        words = b.get_episode_words()
+        o.episode, o.ever_done = (words & 0x7FFFFFFF).astype(np.uint32), (words >> 31).astype(bool)
+        b.step(torch.as_tensor(a, device="cuda:0"), rew, done, obs=obs)
+        obs_ref, rew_ref, done_ref = o.step(a)
+        d, got, r = done.cpu().numpy().astype(bool), obs.cpu().numpy(), rew.cpu().numpy()
+        mism = d != done_ref
+        assert (o.done_margin[mism] < 1e-5).all()
+        done_mismatch += int(mism.sum())
+        ok = ~mism
+        good = _close(obs_ref, got, obs_ref, tol=2e-6).all(axis=1) & _close(rew_ref, r, rew_ref, tol=2e-6)
+        if o.tether_margin is not None:
+            taut_steps += int((o.tether_margin >= 0).sum())
+            # the only admissible disagreement: exactly on the switching surface (float64 tie)
+            bad = ok & ~good
+            assert (np.abs(o.tether_margin[bad]) < 1e-12).all()
+            branch_mismatch += int(bad.sum())
+        else:
+            assert good[ok].all(), "step %d" % t
+        state = got
+    assert done_mismatch <= 2
+    if o.tether_margin is not None:
+        assert taut_steps > 0.2 * n * steps and branch_mismatch <= 5, (taut_steps, branch_mismatch)
+    b.close()
+
+
+# ------------------------------------------------------------------------------------------ reference fixtures
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_golden_single_steps(torch, rmv, env_id):
+    """tests/golden kat_*: outputs of the reference's own step() (float64) from float32-exact inputs."""
+    g = load_golden(env_id)
+    k, S = g["kat_s0"].shape
+    b = rmv.QuadBatch(env_id, k)
+    b.set_state(g["kat_s0"].astype(np.float32))
+    rew, done, obs = _buffers(torch, k, S)
+    b.step(torch.as_tensor(g["kat_a"].astype(np.float32), device="cuda:0"), rew, done, obs=obs, auto_reset=False)
+    assert np.array_equal(done.cpu().numpy().astype(bool), g["kat_done"])
+    assert _close(g["kat_s1"], obs.cpu().numpy(), g["kat_s1"], tol=2e-6).all()
+    assert _close(g["kat_r"], rew.cpu().numpy(), g["kat_r"], tol=2e-6).all()
+    b.close()
+
+
+@pytest.mark.parametrize("env_id,repair", [("quadrotor3d-v0", "A"), ("quadrotor2d-v0", "A"), ("quadrotor2d-v0", "B")])
+def test_golden_trajectories_free_running(torch, rmv, env_id, repair):
+    """400 reference steps x 6 envs with reset-on-done: same seed, same actions, free running."""
+    g = load_golden(env_id, repair)
+    T, E, A = g["traj_a"].shape
+    S = g["traj_obs"].shape[2]
+    params = {"vel_done": 2.0} if repair == "B" else None
+    b = rmv.QuadBatch(env_id, E, seed=int(g["traj_seed"]), params=params)
+    b.reset()
+    assert np.array_equal(b.get_state().astype(np.float64), g["traj_obs0"])
+    rew, done, obs = _buffers(torch, E, S)
+    for t in range(T):
+        b.step(torch.as_tensor(g["traj_a"][t].astype(np.float32), device="cuda:0"), rew, done, obs=obs)
+        assert np.array_equal(done.cpu().numpy().astype(bool), g["traj_done"][t]), t
+        assert _close(g["traj_obs"][t], obs.cpu().numpy(), g["traj_obs"][t]).all(), t
+        assert _close(g["traj_r"][t], rew.cpu().numpy(), g["traj_r"][t]).all(), t
+    term = g["traj_r"][g["traj_done"]]
+    assert (term == 1.0).sum() >= 1 and (term == 0.0).sum() >= 1     # first-ever done pays +1, later ones 0
+    b.close()
+
+
+# ------------------------------------------------------------------------------------------ properties at full size
+def test_full_size_properties_quadrotor3d_2pow20(torch, rmv):
+    """N = 2^20 (the metric's size): size-independent properties instead of a per-element oracle."""
+    n, A, S, seed = 1 << 20, 4, 10, 5
+    dev = "cuda:0"
+    T = 32
+    acts = torch.empty((T, A, n), dtype=torch.float32, device=dev)
+    for t in range(T):
+        rmv.fill_uniform_actions(acts[t], n, A, 0.0, 10.0, seed, step_index=t, layout=1, act_ld=n)
+    rew = torch.empty((T, n), dtype=torch.float32, device=dev)
+    done = torch.empty((T, n), dtype=torch.uint8, device=dev)
+
+    def run(fused, vec, shards):
+        outs = []
+        per = n // shards
+        for k in range(shards):
+            b = rmv.QuadBatch("quadrotor3d-v0", per, seed=seed, env_id_offset=k * per)
+            b.set_tuning(vec=vec)
+            b.reset()
+            r = torch.empty((T, per), dtype=torch.float32, device=dev)
+            d = torch.empty((T, per), dtype=torch.uint8, device=dev)
+            a = acts[:, :, k * per:(k + 1) * per].contiguous()
+            b.step_many(T, a, r, d, out_ld=per, layout=1, act_ld=per, fused=fused)
+            torch.cuda.synchronize()
+            outs.append((torch.as_tensor(b.state_view(), device=dev)[:, :per].clone(), r, d))
+            b.close()
+        return (torch.cat([o[0] for o in outs], 1), torch.cat([o[1] for o in outs], 1), torch.cat([o[2] for o in outs], 1))
+
+    s1, r1, d1 = run(fused=False, vec=2, shards=1)
+    # (1) T launches == one fused launch, bit for bit; (2) independent of the vector width;
+    # (3) independent of how the envs are sharded (global env ids key the reset stream)
+    for fused, vec, shards in [(True, 2, 1), (False, 1, 1), (True, 4, 1), (False, 2, 4)]:
+        s2, r2, d2 = run(fused, vec, shards)
+        assert torch.equal(s1.view(torch.int32), s2.view(torch.int32)), (fused, vec, shards)
+        assert torch.equal(r1.view(torch.int32), r2.view(torch.int32)) and torch.equal(d1, d2), (fused, vec, shards)
+    # (4) reward is -|p'| where not done, and a first-ever done pays exactly +1
+    frac = d1.float().mean().item()
+    assert 0.005 < frac < 0.03
+    assert ((r1 <= 0) | (d1 == 1)).all() and (r1[d1 == 1] >= 0).all()
+    # (5) a done env was re-drawn: its state is inside the reset cube right after
+    last = d1[-1].bool()
+    assert (s1[:, last].abs() <= 1).all()
+    assert torch.isfinite(s1).all()

@@ -1,0 +1,85 @@
+"""Launch-shape sweep of the step kernel (developer tool; prints a table).  Needs a GPU."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "reinmav-gym_b200")]
+
+import torch  # noqa: E402
+
+import gym_reinmav_b200 as rmv  # noqa: E402
+
+BYTES = {"quadrotor2d-v0": 53, "quadrotor2d-slungload-v0": 85, "quadrotor3d-v0": 101, "quadrotor3d-slungload-v0": 149}
+BOUNDS = {"quadrotor2d-v0": (-10, 10), "quadrotor2d-slungload-v0": (-10, 10), "quadrotor3d-v0": (0, 10),
+          "quadrotor3d-slungload-v0": (-10, 10)}
+
+
+def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak):
+    dev = "cuda:0"
+    b = rmv.QuadBatch(env_id, n, seed=0)
+    b.set_tuning(vec=vec, block=block)
+    b.reset()
+    A = b.action_dim
+    lo, hi = BOUNDS[env_id]
+    if layout == "soa":
+        acts = torch.empty((ring, A, n), dtype=torch.float32, device=dev)
+        for t in range(ring):
+            rmv.fill_uniform_actions(acts[t], n, A, lo, hi, 0, step_index=t, layout=1, act_ld=n)
+    else:
+        acts = torch.empty((ring, n, A), dtype=torch.float32, device=dev)
+        for t in range(ring):
+            rmv.fill_uniform_actions(acts[t], n, A, lo, hi, 0, step_index=t)
+    rew = torch.empty((ring, n), dtype=torch.float32, device=dev)
+    done = torch.empty((ring, n), dtype=torch.uint8, device=dev)
+    lay = 1 if layout == "soa" else 0
+
+    def run(k):
+        left = k
+        while left > 0:
+            m = min(left, ring)
+            b.step_many(m, acts, rew, done, out_ld=n, layout=lay, act_ld=n, fused=fused)
+            left -= m
+
+    run(ring)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / steps)
+    b.close()
+    sps = n / (best * 1e-3)
+    gbs = sps * BYTES[env_id] / 1e9
+    return best * 1e3, sps, gbs, gbs / peak
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", default="quadrotor3d-v0")
+    ap.add_argument("--n", default="1048576")
+    ap.add_argument("--vec", default="1,2,4")
+    ap.add_argument("--block", default="128,256")
+    ap.add_argument("--layout", default="soa,aos")
+    ap.add_argument("--fused", default="0")
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--ring", type=int, default=16)
+    ap.add_argument("--peak", type=float, default=6546.2)
+    args = ap.parse_args()
+    print("%-26s %9s %3s %5s %4s %5s %9s %11s %9s %6s" % ("env", "n", "vec", "block", "lay", "fused", "us/step", "steps/s", "GB/s(alg)", "frac"))
+    for env_id in args.envs.split(","):
+        for n in (int(x) for x in args.n.split(",")):
+            for fused in (int(x) for x in args.fused.split(",")):
+                for layout in args.layout.split(","):
+                    for vec in (int(x) for x in args.vec.split(",")):
+                        for block in (int(x) for x in args.block.split(",")):
+                            ring = max(2, min(args.ring, int(6e9 // (n * 4 * 6))))
+                            us, sps, gbs, frac = time_cfg(env_id, n, vec, block, layout, bool(fused), args.steps, ring, args.peak)
+                            print("%-26s %9d %3d %5d %4s %5d %9.2f %11.4g %9.1f %6.3f" % (env_id, n, vec, block, layout, fused, us, sps, gbs, frac), flush=True)
+
+
+if __name__ == "__main__":
+    main()
