@@ -16,7 +16,9 @@
  *     calls with host-side destination/source buffers, which say so.
  *   - pointers named *_dev are device pointers on the handle's device; the caller keeps them
  *     alive until the stream has run past the call.
- *   - state layout in HBM: float32 [S][ld], component-major, ld = rmv_padded_ld(n).
+ *   - state layout in HBM: float32 [n_pad/128][S][128] — tiled struct-of-arrays: env e is lane
+ *     e%128 of tile e/128, a tile holds the S components of 128 consecutive envs contiguously
+ *     (component-major inside the tile); n_pad = rmv_padded_ld(n).
  *     Component order is the reference's tuple order:
  *       quadrotor2d            [x y theta vx vy]                          envs/native/quadrotor2d.py:93
  *       quadrotor2d-slungload  [x y theta vx vy lx ly lvx lvy]            envs/native/quadrotor2d_slungload.py:134
@@ -98,7 +100,7 @@ RMV_API const char* rmv_last_error(void);
  * shapes, e.g. quadrotor3d.py:70-71) */
 RMV_API int rmv_kind_dims(int kind, int* state_dim, int* action_dim);
 RMV_API int rmv_default_params(int kind, rmv_params* out);
-/* leading dimension used for n envs (n rounded up to a multiple of 128 floats) */
+/* padded env count used for n envs (n rounded up to a multiple of the 128-env state tile) */
 RMV_API int64_t rmv_padded_ld(int64_t n_envs);
 /* U(action_space) bounds of a kind (quadrotor2d.py:62, quadrotor3d.py:70, ...) */
 RMV_API int rmv_action_bounds(int kind, float* low, float* high);
@@ -121,7 +123,7 @@ RMV_API int rmv_set_seed(rmv_env* env, uint64_t seed);
 RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block);
 
 /* ---- state access (parity tests, checkpoint/resume, zero-copy views) --------------------- */
-/* device pointers of the handle-owned buffers: state float32 [S][ld]; episode uint32 [ld]
+/* device pointers of the handle-owned buffers: state float32 [n_pad/128][S][128]; episode uint32 [n_pad]
  * (bit 31 = this env has returned done at least once — the reference's
  * `steps_beyond_done is not None`, quadrotor3d.py:68,114-122; bits 0..30 = number of resets,
  * the Philox episode index). */
@@ -152,7 +154,7 @@ RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* obs_aos_dev,
  *   obs_aos_dev  NULL, or float32 [n][S]: observation rows after the step (obs == state in the
  *                reference; with auto_reset a done env reports its RESET state, the VecEnv
  *                convention).  NULL saves 4*S bytes per env: the state buffer itself is the
- *                observation in component-major form.
+ *                observation in tiled component-major form.
  *   auto_reset   0: gym.Env semantics — the terminal state stays, the caller resets;
  *                1: VecEnv semantics — done envs are re-drawn inside the same kernel. */
 RMV_API int rmv_step(rmv_env* env, const float* act_dev, int act_layout, int64_t act_ld,

@@ -93,6 +93,19 @@ class BatchOracle:
     def _c(self, v):
         return self.dtype(v)
 
+    def _over(self, comps, n):
+        """``vec / n``.  float64: the quotient, as the reference.  float32 (T1): one IEEE reciprocal
+        and a product per component — what the CUDA path does (<= 1 ulp from the quotient)."""
+        if self.dtype is np.float64:
+            return [c / n for c in comps]
+        inv = self._c(1.0) / n
+        return [c * inv for c in comps]
+
+    def _per_mass(self, x):
+        """``x / self.mass`` (exact for the reference's mass = 1 either way)."""
+        m = self._c(self.p["mass"])
+        return x / m if self.dtype is np.float64 else x * (self._c(1.0) / m)
+
     def _norm(self, comps):
         acc = comps[0] * comps[0]
         for c in comps[1:]:
@@ -108,7 +121,7 @@ class BatchOracle:
         n = np.sqrt(n2)
         need = ~(np.abs(self._c(1.0) - n2) < self._c(1e-14)) & (n > 0)
         safe = np.where(need, n, self._c(1.0))
-        w, x, y, z = (np.where(need, c / safe, c) for c in (w, x, y, z))
+        w, x, y, z = (np.where(need, c, q0) for c, q0 in zip(self._over((w, x, y, z), safe), (w, x, y, z)))
         rx = ((x * z + w * y) + z * x) + y * w
         ry = ((y * z + z * y) - w * x) - x * w
         rz = ((z * z - y * y) - x * x) + w * w
@@ -173,7 +186,7 @@ class BatchOracle:
         T, om = self._thrust(a[0]), (a[1], a[2], a[3])
         pos, q, vel = s[0:3], s[3:7], s[7:10]
         qh, e3 = self._thrust_axis_3d(q)
-        tm = T / m
+        tm = self._per_mass(T)
         acc = [tm * e3[i] + g[i] for i in range(3)]
         half = self._c(0.5)
         pos2 = [pos[i] + vel[i] * dt + half * acc[i] * dt * dt for i in range(3)]
@@ -193,12 +206,12 @@ class BatchOracle:
         pos, q, vel, lp, lv = s[0:3], s[3:7], s[7:10], s[10:13], s[13:16]
         tv = [lp[i] - pos[i] for i in range(3)]
         nt = self._norm(tv)
-        u = [tv[i] / nt for i in range(3)]
+        u = self._over(tv, nt)
         taut = self._taut(pos, lp, nt)
         qh, e3 = self._thrust_axis_3d(q)
         qd = self._qdot(qh, om)
         q2 = [q[i] + qd[i] * dt for i in range(4)]
-        tm = T / m
+        tm = self._per_mass(T)
         # --- taut (:104-128)
         thr = [T * e3[i] for i in range(3)]
         c = m * L * ((lv[0] * lv[0] + lv[1] * lv[1]) + lv[2] * lv[2])          # scalar, broadcast-subtracted (:110)
@@ -209,12 +222,12 @@ class BatchOracle:
         lv_t = [lv[i] + la[i] * dt for i in range(3)]
         tn = ml * self._norm([-g[i] + la[i] for i in range(3)])
         ten = [tn * u[i] for i in range(3)]
-        acc_t = [tm * e3[i] + g[i] + ten[i] / m for i in range(3)]
+        acc_t = [tm * e3[i] + g[i] + self._per_mass(ten[i]) for i in range(3)]
         p_t = [pos[i] + vel[i] * dt + half * acc_t[i] * dt * dt for i in range(3)]
         v_t = [vel[i] + acc_t[i] * dt for i in range(3)]
         dv = [lp_t[i] - p_t[i] for i in range(3)]
         nd = self._norm(dv)
-        d = [dv[i] / nd for i in range(3)]
+        d = self._over(dv, nd)
         lp_c = [p_t[i] + d[i] * L for i in range(3)]
         rel = ((lv_t[0] - v_t[0]) * d[0] + (lv_t[1] - v_t[1]) * d[1]) + (lv_t[2] - v_t[2]) * d[2]
         lv_c = [lv_t[i] - rel * d[i] for i in range(3)]
@@ -238,7 +251,7 @@ class BatchOracle:
         T, om = self._thrust(a[0]), a[1]
         pos, th, vel = s[0:2], s[2], s[3:5]
         ax = self._planar_axis(th)
-        tm = T / m
+        tm = self._per_mass(T)
         acc = [tm * ax[i] + g[i] for i in range(2)]
         pos2 = [pos[i] + vel[i] * dt + half * acc[i] * dt * dt for i in range(2)]
         vel2 = [vel[i] + acc[i] * dt for i in range(2)]
@@ -256,10 +269,10 @@ class BatchOracle:
         pos, th, vel, lp, lv = s[0:2], s[2], s[3:5], s[5:7], s[7:9]
         tv = [lp[i] - pos[i] for i in range(2)]
         nt = self._norm(tv)
-        u = [tv[i] / nt for i in range(2)]
+        u = self._over(tv, nt)
         taut = self._taut(pos, lp, nt)
         ax = self._planar_axis(th)
-        tm = T / m
+        tm = self._per_mass(T)
         th2 = th + om * dt
         # --- taut (:96-116): velocity first, then position with the NEW velocity
         thr = [T * ax[i] for i in range(2)]
@@ -271,12 +284,12 @@ class BatchOracle:
         lp_t = [lp[i] + lv_t[i] * dt + half * la[i] * dt * dt for i in range(2)]
         tn = ml * self._norm([-g[i] + la[i] for i in range(2)])
         ten = [tn * u[i] for i in range(2)]
-        acc_t = [tm * ax[i] + g[i] + ten[i] / m for i in range(2)]
+        acc_t = [tm * ax[i] + g[i] + self._per_mass(ten[i]) for i in range(2)]
         v_t = [vel[i] + acc_t[i] * dt for i in range(2)]
         p_t = [pos[i] + v_t[i] * dt + half * acc_t[i] * dt * dt for i in range(2)]
         dv = [lp_t[i] - p_t[i] for i in range(2)]
         nd = self._norm(dv)
-        d = [dv[i] / nd for i in range(2)]
+        d = self._over(dv, nd)
         lp_c = [p_t[i] + d[i] * L for i in range(2)]
         rel = (lv_t[0] - v_t[0]) * d[0] + (lv_t[1] - v_t[1]) * d[1]
         lv_c = [lv_t[i] - rel * d[i] for i in range(2)]

@@ -87,7 +87,8 @@ struct rmv_env {
   float* h_obs = nullptr;
   // tuning
   int vec = 0;     // 0 = auto
-  int block = 256;
+  int block = 128;
+  int force_rollout = 0;   // tests: run the multi-step kernel even for one step
 };
 
 static const int kS[RMV_NUM_KINDS] = {5, 9, 10, 16};
@@ -99,8 +100,7 @@ static DevParams to_dev(const rmv_params& p) {
   d.tether_len = p.tether_len; d.pos_done = p.pos_done; d.vel_done = p.vel_done;
   d.thrust_scale = p.thrust_scale; d.first_done_reward = p.first_done_reward;
   d.later_done_reward = p.later_done_reward; d.thrust_clamp = p.thrust_clamp;
-  volatile float total = p.mass + p.load_mass;   // two separately rounded float32 operations
-  d.inv_total_mass = 1.0f / total;
+  finish_params(d);
   return d;
 }
 
@@ -229,7 +229,7 @@ extern "C" RMV_API int rmv_set_seed(rmv_env* env, uint64_t seed) {
 extern "C" RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
   RMV_REQUIRE(vec == 0 || vec == 1 || vec == 2 || vec == 4, "vec must be 0 (auto), 1, 2 or 4");
-  RMV_REQUIRE(block >= 32 && block <= kMaxBlock && block % 32 == 0, "block must be a multiple of 32 in [32, %d]", kMaxBlock);
+  RMV_REQUIRE(block == 128 || block == 256, "block must be 128 or 256");
   env->vec = vec; env->block = block;
   return RMV_OK;
 }
@@ -241,7 +241,7 @@ extern "C" RMV_API int rmv_state_ptr(rmv_env* env, float** state_dev, uint32_t**
   return RMV_OK;
 }
 
-static inline unsigned blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+static inline unsigned blocks_for(int64_t n, int64_t block) { return (unsigned)((n + block - 1) / block); }
 
 // ------------------------------------------------------------------------------------------
 // state in / out
@@ -265,7 +265,7 @@ extern "C" RMV_API int rmv_set_state(rmv_env* env, const float* aos, int is_devi
     RMV_CUDA(cudaMemcpyAsync(env->h_obs, aos, (size_t)env->n * env->S * sizeof(float), cudaMemcpyHostToDevice, st));
     src = env->h_obs;
   }
-  k_rows_to_cols<<<blocks_for(env->n, 256), 256, 0, st>>>(src, env->state, env->n, env->ld, env->S);
+  k_rows_to_tiles<<<blocks_for(env->n, 256), 256, 0, st>>>(src, env->state, env->n, env->S);
   RMV_CUDA(cudaGetLastError());
   if (!is_device) RMV_CUDA(cudaStreamSynchronize(st));
   return RMV_OK;
@@ -281,7 +281,7 @@ extern "C" RMV_API int rmv_get_state(rmv_env* env, float* aos, int is_device, vo
     if (rc) return rc;
     dst = env->h_obs;
   }
-  k_cols_to_rows<<<blocks_for(env->n, 256), 256, 0, st>>>(env->state, dst, env->n, env->ld, env->S);
+  k_tiles_to_rows<<<blocks_for(env->n, 256), 256, 0, st>>>(env->state, dst, env->n, env->S);
   RMV_CUDA(cudaGetLastError());
   if (!is_device) {
     RMV_CUDA(cudaMemcpyAsync(aos, dst, (size_t)env->n * env->S * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -315,7 +315,7 @@ extern "C" RMV_API int rmv_get_episode(rmv_env* env, uint32_t* episode, int is_d
 // ------------------------------------------------------------------------------------------
 template <int KIND>
 static void launch_reset(rmv_env* e, const uint8_t* mask, float* obs, cudaStream_t st) {
-  k_reset<KIND><<<blocks_for(e->n, 256), 256, 0, st>>>(e->state, e->episode, e->ld, e->n, mask, e->seed,
+  k_reset<KIND><<<blocks_for(e->n, 256), 256, 0, st>>>(e->state, e->episode, e->n, mask, e->seed,
                                                       e->env_id_offset, obs, e->ep_return, e->ep_start,
                                                       e->step_index);
 }
@@ -339,15 +339,24 @@ extern "C" RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* o
 // ------------------------------------------------------------------------------------------
 static inline bool aligned(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-template <int KIND, int V>
-static cudaError_t launch_step_kv(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
+template <int KIND, int V, int BLOCK>
+static cudaError_t launch_step_kvb(const StepArgs& args, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;
-  const int block = e->block;
-  const int64_t groups = (e->n + V - 1) / V;
-  const size_t smem = args.obs ? (size_t)(block / 32) * 32 * SP * sizeof(float) : 0;
-  k_step<KIND, V><<<blocks_for(groups, block), block, smem, st>>>(args);
+  const int64_t per_cta = (int64_t)BLOCK * V;
+  const size_t smem = args.obs ? (size_t)(BLOCK / 32) * 32 * SP * sizeof(float) : 0;
+  k_step<KIND, V, BLOCK><<<blocks_for(args.n, per_cta), BLOCK, smem, st>>>(args);
   return cudaGetLastError();
+}
+
+template <int KIND, int V>
+static cudaError_t launch_step_kv(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
+  if (args.n_steps > 1 || e->force_rollout) {
+    const int64_t groups = (args.n + V - 1) / V;
+    k_rollout<KIND, V><<<blocks_for(groups, 128), 128, 0, st>>>(args);
+    return cudaGetLastError();
+  }
+  return e->block == 256 ? launch_step_kvb<KIND, V, 256>(args, st) : launch_step_kvb<KIND, V, 128>(args, st);
 }
 
 template <int KIND>
@@ -390,7 +399,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
   a.ep_return = e->ep_return; a.ep_start = e->ep_start; a.last_return = e->last_return;
   a.last_length = e->last_length; a.cum_return = e->cum_return; a.cum_length = e->cum_length;
   a.fin_count = e->fin_count;
-  a.ld = e->ld; a.n = e->n; a.act_ld = act_ld; a.out_ld = out_ld; a.act_step_stride = act_step_stride;
+  a.n = e->n; a.act_ld = act_ld; a.out_ld = out_ld; a.act_step_stride = act_step_stride;
   a.env_id_offset = e->env_id_offset; a.seed = e->seed; a.step_index = e->step_index;
   a.n_steps = n_steps; a.act_soa = (act_layout == RMV_ACT_SOA); a.auto_reset = auto_reset ? 1 : 0;
   a.P = e->dp;

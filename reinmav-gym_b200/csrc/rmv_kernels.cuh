@@ -1,15 +1,22 @@
 // rmv_kernels.cuh — the fused step kernel and its small companions (sm_100a).
 //
 // Data layout in HBM (DESIGN.md "Layout"):
-//   state    float32 [S][ld]   component-major; env e of this shard is column e
-//   episode  uint32  [ld]      bit 31 = ever-done flag, bits 0..30 = reset count (Philox index)
-//   actions  float32 [n][A] (AOS) or [A][act_ld] (SOA), read with streaming loads
-//   reward   float32 [n], done uint8 [n], written with streaming stores
+//   state    float32 [n_tiles][S][128]  tiled struct-of-arrays: env e lives in tile e/128, lane e%128;
+//                                       one tile = the S components of 128 consecutive envs = S*512
+//                                       contiguous bytes.  A warp reads 32*V consecutive envs of one
+//                                       component with one coalesced V-wide vector load, the rows of
+//                                       a tile sit at COMPILE-TIME offsets from the thread's base
+//                                       pointer (no per-row address arithmetic), and a CTA's whole
+//                                       footprint is one contiguous block of DRAM pages.
+//   episode  uint32  [n_pad]            bit 31 = ever-done flag, bits 0..30 = reset count (Philox index)
+//   actions  float32 [n][A] (AOS, what a policy emits) or [A][act_ld] (SOA); streaming loads
+//   reward   float32 [n], done uint8 [n]; streaming stores
 //
-// One thread owns V consecutive envs (V = 1, 2 or 4): every state row is then a V-wide vector
-// load/store that a warp covers with 32*V*4 contiguous bytes.  The path is HBM-bound (~1 flop/B):
-// no tensor cores, no shared-memory reuse; shared memory is used only to transpose the optional
-// row-per-env observation copy so that its stores coalesce.
+// One thread owns V consecutive envs (V = 1, 2 or 4).  The path is HBM-bound (~1.5 flop/B): no
+// tensor cores, no shared-memory reuse.  Shared memory is used for two things only: transposing
+// the optional row-per-env observation copy so its stores coalesce, and the per-CTA work list
+// that lets the rare done envs (~1.3 % of env-steps) be re-drawn by whichever threads are free
+// instead of serialising a Philox evaluation inside every warp that contains one.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,17 +25,23 @@
 
 namespace rmv {
 
+constexpr int kTile = 128;            // envs per state tile
 constexpr int kMaxBlock = 256;
 constexpr uint32_t kEverDone = 0x80000000u;
 
+// element offset of (env e, component c) in the tiled state buffer
+template <int S> __host__ __device__ __forceinline__ int64_t tiled_index(int64_t e, int c) {
+  return (e / kTile) * (int64_t)(S * kTile) + (int64_t)c * kTile + (e % kTile);
+}
+
 struct StepArgs {
-  float* state;            // [S][ld]
-  uint32_t* episode;       // [ld]
+  float* state;            // tiled [n_tiles][S][128]
+  uint32_t* episode;       // [n_pad]
   const float* act;        // see act_soa
   float* reward;           // [T][out_ld] or nullptr
   uint8_t* done;           // [T][out_ld] or nullptr
-  float* obs;              // [n][S] or nullptr (only with n_steps == 1)
-  // optional episode tracking (RMV_TRACK_EPISODES), all [ld]
+  float* obs;              // [n][S] or nullptr (single-step kernel only)
+  // optional episode tracking (RMV_TRACK_EPISODES), all [n_pad]
   float* ep_return;        // running return of the current episode
   uint32_t* ep_start;      // step index at which the current episode began
   float* last_return;      // return / length of the most recently finished episode
@@ -36,7 +49,7 @@ struct StepArgs {
   double* cum_return;      // sums over finished episodes
   unsigned long long* cum_length;
   uint32_t* fin_count;
-  int64_t ld, n, act_ld, out_ld, act_step_stride, env_id_offset;
+  int64_t n, act_ld, out_ld, act_step_stride, env_id_offset;
   uint64_t seed;
   uint32_t step_index;
   int n_steps, act_soa, auto_reset;
@@ -44,11 +57,6 @@ struct StepArgs {
 };
 
 // ---- V-wide global access ----------------------------------------------------------------
-template <int V> struct Vec;
-template <> struct Vec<1> { using T = float; };
-template <> struct Vec<2> { using T = float2; };
-template <> struct Vec<4> { using T = float4; };
-
 template <int V, bool STREAM>
 __device__ __forceinline__ void load_v(const float* p, float (&o)[V]) {
   if constexpr (V == 1) {
@@ -84,7 +92,7 @@ __device__ __forceinline__ void store_done(uint8_t* p, const uint8_t (&d)[V]) {
   }
 }
 
-// row-per-env actions: V*A contiguous floats starting at p
+// row-per-env actions: N contiguous floats starting at p
 template <int N>
 __device__ __forceinline__ void load_contig_stream(const float* p, float (&o)[N]) {
   if constexpr (N % 4 == 0) {
@@ -94,164 +102,288 @@ __device__ __forceinline__ void load_contig_stream(const float* p, float (&o)[N]
       o[4 * i] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w;
     }
   } else {
-    static_assert(N == 2, "unexpected action vector length");
+    static_assert(N == 2 || N % 4 == 0, "unexpected action vector length");
     const float2 t = __ldcs(reinterpret_cast<const float2*>(p));
     o[0] = t.x; o[1] = t.y;
   }
 }
 
-// ---- the fused step kernel -----------------------------------------------------------------
-// dynamics + done + reward + reset-on-done (+ optional episode bookkeeping, + optional
-// row-per-env observation copy) for n envs, n_steps consecutive steps with the state held in
-// registers in between (n_steps == 1 for the ordinary step()).
 template <int KIND, int V>
-__global__ void __launch_bounds__(kMaxBlock) k_step(const StepArgs a) {
-  constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
-  constexpr int SP = (S % 2 == 0) ? S + 1 : S;   // odd row pitch: conflict-free transposes
-  extern __shared__ float tile[];                // [warps][32][SP], only when a.obs != nullptr
-
-  const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
-  const bool active = e0 < a.n;
-  const bool full = e0 + V <= a.n;
-
-  float s[V][S];
-  float ep_ret[V];
-  if (active) {
+__device__ __forceinline__ void load_actions(const StepArgs& a, const float* ap, int64_t e0, bool full,
+                                             float (&act)[V][Dims<KIND>::A]) {
+  constexpr int A = Dims<KIND>::A;
+  if (a.act_soa) {
 #pragma unroll
-    for (int c = 0; c < S; ++c) {
+    for (int c = 0; c < A; ++c) {
       float t[V];
-      load_v<V, false>(a.state + c * a.ld + e0, t);   // rows are padded to ld: always in bounds
-#pragma unroll
-      for (int v = 0; v < V; ++v) s[v][c] = t[v];
-    }
-    if (a.ep_return) load_v<V, false>(a.ep_return + e0, ep_ret);
-  }
-
-  for (int step = 0; step < a.n_steps; ++step) {
-    float rew[V];
-    uint8_t dn[V];
-    if (active) {
-      float act[V][A];
-      const float* ap = a.act + (int64_t)step * a.act_step_stride;
-      if (a.act_soa) {
-#pragma unroll
-        for (int c = 0; c < A; ++c) {
-          float t[V];
-          if (full) {
-            load_v<V, true>(ap + c * a.act_ld + e0, t);
-          } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v) t[v] = (e0 + v < a.n) ? __ldcs(ap + c * a.act_ld + e0 + v) : 0.0f;
-          }
-#pragma unroll
-          for (int v = 0; v < V; ++v) act[v][c] = t[v];
-        }
-      } else {
-        float t[V * A];
-        if (full) {
-          load_contig_stream<V * A>(ap + e0 * A, t);
-        } else {
-#pragma unroll
-          for (int i = 0; i < V * A; ++i) t[i] = (e0 * A + i < a.n * A) ? __ldcs(ap + e0 * A + i) : 0.0f;
-        }
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-#pragma unroll
-          for (int c = 0; c < A; ++c) act[v][c] = t[v * A + c];
-      }
-
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        float n_pos, n_vel, n_rew;
-        EnvStep<KIND>::run(a.P, s[v], act[v], n_pos, n_vel, n_rew);
-        const bool done = is_done(a.P, n_pos, n_vel);
-        float r = -n_rew;
-        dn[v] = done ? 1 : 0;
-        const int64_t e = e0 + v;
-        if (done && e < a.n) {
-          // rare lane (~1.3 % of env-steps under a random policy): flag word, terminal reward, re-draw
-          const uint32_t word = a.episode[e];
-          r = reward_of(a.P, true, (word & kEverDone) != 0u, n_rew);
-          uint32_t count = word & ~kEverDone;
-          if (a.auto_reset) {
-            count += 1u;
-            reset_draws<KIND>(a.seed, (uint64_t)(a.env_id_offset + e), count, s[v]);
-          }
-          a.episode[e] = count | kEverDone;
-          if (a.ep_return) {
-            const float total = ep_ret[v] + r;
-            const uint32_t now = a.step_index + (uint32_t)step + 1u;
-            const uint32_t len = now - a.ep_start[e];
-            a.last_return[e] = total;
-            a.last_length[e] = len;
-            a.cum_return[e] += (double)total;
-            a.cum_length[e] += len;
-            a.fin_count[e] += 1u;
-            a.ep_start[e] = now;
-            ep_ret[v] = -r;          // becomes 0 after the "+= r" below
-          }
-        }
-        rew[v] = r;
-        if (a.ep_return) ep_ret[v] += r;
-      }
-
-      const int64_t o0 = (int64_t)step * a.out_ld + e0;
       if (full) {
-        if (a.reward) store_v<V, true>(a.reward + o0, rew);
-        if (a.done) store_done<V>(a.done + o0, dn);
+        load_v<V, true>(ap + c * a.act_ld + e0, t);
       } else {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          if (e0 + v < a.n) {
-            if (a.reward) __stcs(a.reward + o0 + v, rew[v]);
-            if (a.done) __stcs(reinterpret_cast<unsigned char*>(a.done) + o0 + v, (unsigned char)dn[v]);
-          }
-        }
+        for (int v = 0; v < V; ++v) t[v] = (e0 + v < a.n) ? __ldcs(ap + c * a.act_ld + e0 + v) : 0.0f;
       }
-    }
-  }
-
-  if (active) {
 #pragma unroll
-    for (int c = 0; c < S; ++c) {
-      float t[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) t[v] = s[v][c];
-      store_v<V, false>(a.state + c * a.ld + e0, t);
+      for (int v = 0; v < V; ++v) act[v][c] = t[v];
     }
-    if (a.ep_return) store_v<V, false>(a.ep_return + e0, ep_ret);
+  } else {
+    float t[V * A];
+    if (full) {
+      load_contig_stream<V * A>(ap + e0 * A, t);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V * A; ++i) t[i] = (e0 * A + i < a.n * A) ? __ldcs(ap + e0 * A + i) : 0.0f;
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int c = 0; c < A; ++c) act[v][c] = t[v * A + c];
   }
+}
 
-  if (a.obs) {
-    // row-per-env observation copy [n][S]: transpose through a per-warp shared tile so that
-    // each store instruction writes runs of S contiguous floats instead of 32 scattered words.
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* my = tile + warp * 32 * SP;
-    const int64_t warp_e0 = e0 - (int64_t)lane * V;   // first env of this warp
+template <int V>
+__device__ __forceinline__ void store_outputs(const StepArgs& a, int64_t o0, int64_t e0, bool full,
+                                              const float (&rew)[V], const uint8_t (&dn)[V]) {
+  if (full) {
+    if (a.reward) store_v<V, true>(a.reward + o0, rew);
+    if (a.done) store_done<V>(a.done + o0, dn);
+  } else {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < S; ++c) my[lane * SP + c] = s[v][c];
-      __syncwarp();
-#pragma unroll
-      for (int i = lane; i < 32 * S; i += 32) {
-        const int r = i / S, c = i - r * S;
-        const int64_t e = warp_e0 + (int64_t)r * V + v;
-        if (e < a.n) __stcs(a.obs + e * S + c, my[r * SP + c]);
+      if (e0 + v < a.n) {
+        if (a.reward) __stcs(a.reward + o0 + v, rew[v]);
+        if (a.done) __stcs(reinterpret_cast<unsigned char*>(a.done) + o0 + v, (unsigned char)dn[v]);
       }
     }
   }
 }
 
+// Book-keeping of an env that just returned done (quadrotor3d.py:112-122): terminal reward from the
+// ever-done flag, flag set, reset count advanced when the env is going to be re-drawn.
+// Returns the terminal reward; `count_out` = the new reset count (the Philox episode index).
+__device__ __forceinline__ float on_done(const StepArgs& a, int64_t e, float n_rew, float ep_ret_before,
+                                         uint32_t step_now, uint32_t& count_out) {
+  const uint32_t word = a.episode[e];
+  const float r = reward_of(a.P, true, (word & kEverDone) != 0u, n_rew);
+  uint32_t count = word & ~kEverDone;
+  if (a.auto_reset) count += 1u;
+  a.episode[e] = count | kEverDone;
+  count_out = count;
+  if (a.ep_return) {
+    const float total = ep_ret_before + r;
+    const uint32_t len = step_now - a.ep_start[e];
+    a.last_return[e] = total;
+    a.last_length[e] = len;
+    a.cum_return[e] += (double)total;
+    a.cum_length[e] += len;
+    a.fin_count[e] += 1u;
+    a.ep_start[e] = step_now;
+  }
+  return r;
+}
+
+// ---- the fused single-step kernel ------------------------------------------------------------
+// dynamics + done + reward + reset-on-done (+ optional episode bookkeeping, + optional
+// row-per-env observation copy) for n envs: the reference's step() and the caller's reset-on-done
+// in ONE launch.
+template <int KIND, int V, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_step(const StepArgs a) {
+  constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
+  constexpr int NB = (S + 3) / 4;                  // Philox blocks per reset
+  constexpr int SP = (S % 2 == 0) ? S + 1 : S;     // odd row pitch: conflict-free transposes
+  constexpr int kMaxList = BLOCK * V;
+  __shared__ uint32_t list_env[kMaxList];          // envs of this CTA to re-draw (index relative to the CTA)
+  __shared__ uint32_t list_episode[kMaxList];
+  __shared__ uint32_t list_len;
+  extern __shared__ float tile[];                  // [warps][32][SP], only when a.obs != nullptr
+
+  const uint32_t tid = threadIdx.x;
+  const int64_t cta_e0 = (int64_t)blockIdx.x * (BLOCK * V);
+  const int64_t e0 = cta_e0 + (int64_t)tid * V;
+  const bool active = e0 < a.n;
+  const bool full = e0 + V <= a.n;
+  if (tid == 0) list_len = 0u;
+
+  // thread's base pointer into the tiled state: rows of the tile are at constant offsets c*kTile
+  float* const sp = a.state + ((e0 >> 7) * (int64_t)(S * kTile) + (e0 & (kTile - 1)));
+  float s[V][S];
+  float ep_ret[V];
+  float rew[V];
+  uint8_t dn[V];
+  bool redraw[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) redraw[v] = false;
+  __syncthreads();                                 // list_len = 0 visible
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < S; ++c) {
+      float t[V];
+      load_v<V, false>(sp + c * kTile, t);         // tiles are padded: always in bounds
+#pragma unroll
+      for (int v = 0; v < V; ++v) s[v][c] = t[v];
+    }
+    if (a.ep_return) load_v<V, false>(a.ep_return + e0, ep_ret);
+    float act[V][A];
+    load_actions<KIND, V>(a, a.act, e0, full, act);
+
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float pos_sq, vel_sq, n_rew;
+      EnvStep<KIND>::run(a.P, s[v], act[v], pos_sq, vel_sq, n_rew);
+      const bool done = is_done(a.P, pos_sq, vel_sq);
+      float r = -n_rew;
+      dn[v] = done ? 1 : 0;
+      redraw[v] = false;
+      const int64_t e = e0 + v;
+      if (done && e < a.n) {
+        uint32_t count;
+        r = on_done(a, e, n_rew, a.ep_return ? ep_ret[v] : 0.0f, a.step_index + 1u, count);
+        if (a.ep_return) ep_ret[v] = -r;          // becomes 0 after the "+= r" below
+        if (a.auto_reset) {
+          const uint32_t slot = atomicAdd(&list_len, 1u);
+          list_env[slot] = tid * V + v;
+          list_episode[slot] = count;
+          redraw[v] = true;
+        }
+      }
+      rew[v] = r;
+      if (a.ep_return) ep_ret[v] += r;
+    }
+    store_outputs<V>(a, e0, e0, full, rew, dn);
+    // a done env's new state comes from the work list below, everything else is stored here
+    bool any_redraw = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) any_redraw |= redraw[v];
+    if (!any_redraw) {
+#pragma unroll
+      for (int c = 0; c < S; ++c) {
+        float t[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) t[v] = s[v][c];
+        store_v<V, false>(sp + c * kTile, t);
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (!redraw[v]) {
+#pragma unroll
+          for (int c = 0; c < S; ++c) sp[c * kTile + v] = s[v][c];
+        }
+    }
+    if (a.ep_return) store_v<V, false>(a.ep_return + e0, ep_ret);
+  }
+
+  if (a.obs) {
+    // row-per-env observation copy [n][S]: transpose through a per-warp shared tile so that each
+    // store instruction writes runs of S contiguous floats instead of 32 scattered words.
+    // Rows of re-drawn envs are written by the work-list pass instead.
+    const int lane = tid & 31, warp = tid >> 5;
+    float* my = tile + warp * 32 * SP;
+    const int64_t warp_e0 = e0 - (int64_t)lane * V;
+    uint32_t skip = 0u;                            // bit r: row r of this pass belongs to a re-drawn env
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < S; ++c) my[lane * SP + c] = s[v][c];
+      skip = __ballot_sync(0xffffffffu, active && redraw[v]);
+      __syncwarp();
+#pragma unroll
+      for (int i = lane; i < 32 * S; i += 32) {
+        const int r = i / S, c = i - r * S;
+        const int64_t e = warp_e0 + (int64_t)r * V + v;
+        if (e < a.n && !((skip >> r) & 1u)) __stcs(a.obs + e * S + c, my[r * SP + c]);
+      }
+    }
+  }
+
+  // ---- re-draw the done envs of this CTA: one (env, Philox block) pair per thread -------------
+  __syncthreads();
+  const uint32_t pairs = list_len * NB;
+  for (uint32_t i = tid; i < pairs; i += BLOCK) {
+    const uint32_t slot = i / NB, b = i - slot * NB;
+    const int64_t e = cta_e0 + list_env[slot];
+    const uint64_t id = (uint64_t)(a.env_id_offset + e);
+    uint32_t w[4];
+    philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), list_episode[slot],
+                  ((STREAM_RESET_BASE + (uint32_t)KIND) << 8) | b, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
+    float* const row = a.state + ((e >> 7) * (int64_t)(S * kTile) + (e & (kTile - 1)));
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int c = 4 * (int)b + l;
+      if (c < S) {
+        const float x = uniform_from_bits(w[l], -1.0f, 2.0f);
+        row[c * kTile] = x;
+        if (a.obs) a.obs[e * S + c] = x;
+      }
+    }
+  }
+}
+
+// ---- fused multi-step rollout ---------------------------------------------------------------------
+// n_steps consecutive steps with auto-reset; each thread keeps its envs' state in registers in
+// between, so state is read and written once per call (actions in, reward/done out every step).
+template <int KIND, int V>
+__global__ void __launch_bounds__(128) k_rollout(const StepArgs a) {
+  constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
+  const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (e0 >= a.n) return;
+  const bool full = e0 + V <= a.n;
+  float* const sp = a.state + ((e0 >> 7) * (int64_t)(S * kTile) + (e0 & (kTile - 1)));
+  float s[V][S];
+  float ep_ret[V];
+#pragma unroll
+  for (int c = 0; c < S; ++c) {
+    float t[V];
+    load_v<V, false>(sp + c * kTile, t);
+#pragma unroll
+    for (int v = 0; v < V; ++v) s[v][c] = t[v];
+  }
+  if (a.ep_return) load_v<V, false>(a.ep_return + e0, ep_ret);
+
+  for (int step = 0; step < a.n_steps; ++step) {
+    float rew[V];
+    uint8_t dn[V];
+    float act[V][A];
+    load_actions<KIND, V>(a, a.act + (int64_t)step * a.act_step_stride, e0, full, act);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float pos_sq, vel_sq, n_rew;
+      EnvStep<KIND>::run(a.P, s[v], act[v], pos_sq, vel_sq, n_rew);
+      const bool done = is_done(a.P, pos_sq, vel_sq);
+      float r = -n_rew;
+      dn[v] = done ? 1 : 0;
+      const int64_t e = e0 + v;
+      if (done && e < a.n) {
+        uint32_t count;
+        r = on_done(a, e, n_rew, a.ep_return ? ep_ret[v] : 0.0f, a.step_index + (uint32_t)step + 1u, count);
+        if (a.ep_return) ep_ret[v] = -r;
+        if (a.auto_reset) reset_draws<KIND>(a.seed, (uint64_t)(a.env_id_offset + e), count, s[v]);
+      }
+      rew[v] = r;
+      if (a.ep_return) ep_ret[v] += r;
+    }
+    store_outputs<V>(a, (int64_t)step * a.out_ld + e0, e0, full, rew, dn);
+  }
+
+#pragma unroll
+  for (int c = 0; c < S; ++c) {
+    float t[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) t[v] = s[v][c];
+    store_v<V, false>(sp + c * kTile, t);
+  }
+  if (a.ep_return) store_v<V, false>(a.ep_return + e0, ep_ret);
+}
+
 // ---- reset(): all envs or a masked subset --------------------------------------------------
 template <int KIND>
-__global__ void k_reset(float* state, uint32_t* episode, int64_t ld, int64_t n, const uint8_t* mask,
-                        uint64_t seed, int64_t env_id_offset, float* obs, float* ep_return,
-                        uint32_t* ep_start, uint32_t step_index) {
+__global__ void k_reset(float* state, uint32_t* episode, int64_t n, const uint8_t* mask, uint64_t seed,
+                        int64_t env_id_offset, float* obs, float* ep_return, uint32_t* ep_start,
+                        uint32_t step_index) {
   constexpr int S = Dims<KIND>::S;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
+  float* const row = state + (e / kTile) * (int64_t)(S * kTile) + (e % kTile);
   float s[S];
   if (mask == nullptr || mask[e] != 0) {
     const uint32_t word = episode[e];
@@ -259,11 +391,11 @@ __global__ void k_reset(float* state, uint32_t* episode, int64_t ld, int64_t n, 
     episode[e] = (word & kEverDone) | count;     // reset() never clears steps_beyond_done (quadrotor3d.py:182-185)
     reset_draws<KIND>(seed, (uint64_t)(env_id_offset + e), count, s);
 #pragma unroll
-    for (int c = 0; c < S; ++c) state[c * ld + e] = s[c];
+    for (int c = 0; c < S; ++c) row[c * kTile] = s[c];
     if (ep_return) { ep_return[e] = 0.0f; ep_start[e] = step_index; }
   } else if (obs) {
 #pragma unroll
-    for (int c = 0; c < S; ++c) s[c] = state[c * ld + e];
+    for (int c = 0; c < S; ++c) s[c] = row[c * kTile];
   }
   if (obs) {
 #pragma unroll
@@ -271,16 +403,18 @@ __global__ void k_reset(float* state, uint32_t* episode, int64_t ld, int64_t n, 
   }
 }
 
-// ---- [n][S] rows <-> [S][ld] columns (set_state / get_state; not on the hot path) ------------
-__global__ void k_rows_to_cols(const float* rows, float* cols, int64_t n, int64_t ld, int S) {
+// ---- [n][S] rows <-> tiled state (set_state / get_state; not on the hot path) ------------------
+__global__ void k_rows_to_tiles(const float* rows, float* tiles, int64_t n, int S) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  for (int c = 0; c < S; ++c) cols[c * ld + e] = rows[e * S + c];
+  float* const row = tiles + (e / kTile) * (int64_t)(S * kTile) + (e % kTile);
+  for (int c = 0; c < S; ++c) row[c * kTile] = rows[e * S + c];
 }
-__global__ void k_cols_to_rows(const float* cols, float* rows, int64_t n, int64_t ld, int S) {
+__global__ void k_tiles_to_rows(const float* tiles, float* rows, int64_t n, int S) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  for (int c = 0; c < S; ++c) rows[e * S + c] = cols[c * ld + e];
+  const float* const row = tiles + (e / kTile) * (int64_t)(S * kTile) + (e % kTile);
+  for (int c = 0; c < S; ++c) rows[e * S + c] = row[c * kTile];
 }
 
 // ---- random-policy actions ~ U[lo, hi) ---------------------------------------------------------

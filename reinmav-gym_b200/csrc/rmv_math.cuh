@@ -72,8 +72,34 @@ struct DevParams {
   float pos_done, vel_done, thrust_scale;
   float first_done_reward, later_done_reward;
   float inv_total_mass;   // 1.0f / (mass + load_mass), two float32 ops
+  float inv_mass;         // 1.0f / mass (exactly 1 for the reference's mass = 1)
+  float pos_sq_max;       // largest float32 y with sqrt_rn(y) <= pos_done: |p| > pos_done  <=>  p.p > pos_sq_max
+  float vel_sq_max;       // same for vel_done
   int thrust_clamp;
 };
+
+// Host-side completion of the derived fields.  Every value is produced by single float32 IEEE
+// operations so that the NumPy float32 model (oracle/batch.py) computes the same bits.
+inline float sq_threshold(float t) {
+  // sqrt_rn is monotone, so {y : sqrt_rn(y) <= t} is a down-set of the non-negative floats; its
+  // maximum turns the reference's `norm > t` into a comparison of the squared norm, bit for bit.
+  if (t != t) return t;                       // NaN threshold: never done
+  if (t < 0.0f) return -1.0f;                 // any norm exceeds a negative threshold
+  if (t == INFINITY) return INFINITY;
+  volatile float y = t * t;
+  if (y == INFINITY) y = 3.402823466e+38f;
+  while (sqrtf(nextafterf(y, INFINITY)) <= t && y < 3.402823466e+38f) y = nextafterf(y, INFINITY);
+  while (sqrtf(y) > t) y = nextafterf(y, -INFINITY);
+  return y;
+}
+inline void finish_params(DevParams& d) {
+  volatile float total = d.mass + d.load_mass;
+  d.inv_total_mass = 1.0f / total;
+  volatile float m = d.mass;
+  d.inv_mass = 1.0f / m;
+  d.pos_sq_max = sq_threshold(d.pos_done);
+  d.vel_sq_max = sq_threshold(d.vel_done);
+}
 
 enum { QUAD2D = 0, QUAD2D_SLUNG = 1, QUAD3D = 2, QUAD3D_SLUNG = 3 };
 
@@ -177,12 +203,13 @@ RMV_HD void sincos_pinned(float xin, float& s_out, float& c_out) {
 // ------------------------------------------------------------------------------------------
 // shared pieces
 // ------------------------------------------------------------------------------------------
-template <int D> RMV_HD rf norm(const rf (&c)[D]) {
+template <int D> RMV_HD rf sumsq(const rf (&c)[D]) {
   rf acc = c[0] * c[0];
 #pragma unroll
   for (int i = 1; i < D; ++i) acc = acc + c[i] * c[i];
-  return sqrt(acc);
+  return acc;
 }
+template <int D> RMV_HD rf norm(const rf (&c)[D]) { return sqrt(sumsq<D>(c)); }
 
 // x' and v' of one body.  VEL_FIRST = quadrotor2d_slungload.py:100-101,109-110 (velocity, then
 // position with the NEW velocity); otherwise quadrotor3d.py:98-99 (position with the OLD velocity).
@@ -209,8 +236,13 @@ RMV_HD void attitude_3d(const rf (&q)[4], const rf (&om)[3], rf (&e3)[3], rf (&q
   rf w = q[0], x = q[1], y = q[2], z = q[3];
   const rf n2 = ((w * w + x * x) + y * y) + z * z;
   const rf n = sqrt(n2);
-  const bool need = !(fabsf((rf(1.0f) - n2).v) < 1e-14f) && (n.v > 0.0f);
-  if (need) { w = w / n; x = x / n; y = y / n; z = z / n; }
+  // pyquaternion skips the division when |1 - q.q| < 1e-14; in float32 that means q.q == 1, where
+  // multiplying by 1/sqrt(1) = 1 is exact, so only the n > 0 guard is left.  float32 normalises
+  // with ONE IEEE reciprocal and four products (x/n -> x*(1/n)): <= 1 ulp from the quotient.
+  if (n.v > 0.0f) {
+    const rf inv = rf(1.0f) / n;
+    w = w * inv; x = x * inv; y = y * inv; z = z * inv;
+  }
   e3[0] = ((x * z + w * y) + z * x) + y * w;
   e3[1] = ((y * z + z * y) - w * x) - x * w;
   e3[2] = ((z * z - y * y) - x * x) + w * w;
@@ -239,7 +271,7 @@ RMV_HD rf commanded_thrust(const DevParams& P, float a0) {
 // free quadrotor: acc = T/m * axis + g ; advance (quadrotor3d.py:96-99, quadrotor2d.py:88-90)
 template <int D>
 RMV_HD void quad_free(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[D], rf (&vel)[D]) {
-  const rf tm = T / rf(P.mass);
+  const rf tm = T * rf(P.inv_mass);   // T/m with m = 1: exact; general m: reciprocal-multiply
   rf acc[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) acc[i] = tm * axis[i] + rf(i == D - 1 ? P.neg_gravity : 0.0f);
@@ -268,12 +300,12 @@ RMV_HD void quad_slung(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[
     acc2 = (i == 0) ? d * d : acc2 + d * d;
   }
   const bool taut = sqrt(acc2).v >= (double)P.tether_len;
-  const rf tm = T / m;
+  const rf tm = T * rf(P.inv_mass);
   if (taut) {
-    const rf nt = norm<D>(tv);
+    const rf inv_nt = rf(1.0f) / norm<D>(tv);
     rf u[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) u[i] = tv[i] / nt;
+    for (int i = 0; i < D; ++i) u[i] = tv[i] * inv_nt;
     rf lv2 = lv[0] * lv[0];
 #pragma unroll
     for (int i = 1; i < D; ++i) lv2 = lv2 + lv[i] * lv[i];
@@ -292,16 +324,16 @@ RMV_HD void quad_slung(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[
     const rf tn = ml * norm<D>(back);
     rf acc[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) acc[i] = tm * axis[i] + g[i] + (tn * u[i]) / m;
+    for (int i = 0; i < D; ++i) acc[i] = tm * axis[i] + g[i] + (tn * u[i]) * rf(P.inv_mass);
     advance<D, VEL_FIRST>(pos, vel, acc, dt);
     // kinematic constraint (:126-128)
     rf dv[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) dv[i] = lp[i] - pos[i];
-    const rf nd = norm<D>(dv);
+    const rf inv_nd = rf(1.0f) / norm<D>(dv);
     rf dir[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) dir[i] = dv[i] / nd;
+    for (int i = 0; i < D; ++i) dir[i] = dv[i] * inv_nd;
     rf rel = (lv[0] - vel[0]) * dir[0];
 #pragma unroll
     for (int i = 1; i < D; ++i) rel = rel + (lv[i] - vel[i]) * dir[i];
@@ -321,7 +353,9 @@ RMV_HD void quad_slung(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[
 
 // ------------------------------------------------------------------------------------------
 // one env, one step.  s: state components in the reference's tuple order; a: action.
-// Outputs the three norms the reward/done block needs (quadrotor3d.py:106-113 and twins).
+// Outputs what the reward/done block needs (quadrotor3d.py:106-113 and twins): the SQUARED norms
+// that `done` thresholds (compared against DevParams::*_sq_max, equivalent to norm > threshold)
+// and the norm the reward negates.
 // ------------------------------------------------------------------------------------------
 template <int KIND> struct EnvStep;
 
@@ -338,9 +372,10 @@ template <> struct EnvStep<QUAD3D> {  // quadrotor3d.py:81-113
     for (int i = 0; i < 4; ++i) s[3 + i] = (q[i] + qdot[i] * dt).v;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { s[i] = pos[i].v; s[7 + i] = vel[i].v; }
-    n_pos = norm<3>(pos).v;
-    n_vel = norm<3>(vel).v;
-    n_rew = n_pos;
+    const rf p2 = sumsq<3>(pos);
+    n_pos = p2.v;
+    n_vel = sumsq<3>(vel).v;
+    n_rew = sqrt(p2).v;
   }
 };
 
@@ -358,9 +393,10 @@ template <> struct EnvStep<QUAD3D_SLUNG> {  // quadrotor3d_slungload.py:87-156
     for (int i = 0; i < 4; ++i) s[3 + i] = (q[i] + qdot[i] * dt).v;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { s[i] = pos[i].v; s[7 + i] = vel[i].v; s[10 + i] = lp[i].v; s[13 + i] = lv[i].v; }
-    n_pos = norm<3>(lp).v;   // done: LOAD position, QUAD velocity (:149-152)
-    n_vel = norm<3>(vel).v;
-    n_rew = n_pos;           // reward: load position (:156)
+    const rf l2 = sumsq<3>(lp);
+    n_pos = l2.v;            // done: LOAD position, QUAD velocity (:149-152)
+    n_vel = sumsq<3>(vel).v;
+    n_rew = sqrt(l2).v;      // reward: load position (:156)
   }
 };
 
@@ -374,9 +410,10 @@ template <> struct EnvStep<QUAD2D> {  // quadrotor2d.py:74-102
     quad_free<2>(P, commanded_thrust(P, a[0]), axis, pos, vel);
     s[2] = (th + rf(a[1]) * rf(P.dt)).v;
     s[0] = pos[0].v; s[1] = pos[1].v; s[3] = vel[0].v; s[4] = vel[1].v;
-    n_pos = norm<2>(pos).v;
-    n_vel = norm<2>(vel).v;
-    n_rew = n_pos;
+    const rf p2 = sumsq<2>(pos);
+    n_pos = p2.v;
+    n_vel = sumsq<2>(vel).v;
+    n_rew = sqrt(p2).v;
   }
 };
 
@@ -391,16 +428,16 @@ template <> struct EnvStep<QUAD2D_SLUNG> {  // quadrotor2d_slungload.py:79-143
     s[2] = (th + rf(a[1]) * rf(P.dt)).v;
     s[0] = pos[0].v; s[1] = pos[1].v; s[3] = vel[0].v; s[4] = vel[1].v;
     s[5] = lp[0].v; s[6] = lp[1].v; s[7] = lv[0].v; s[8] = lv[1].v;
-    n_pos = norm<2>(lp).v;   // done: load position / load velocity (:136-139)
-    n_vel = norm<2>(lv).v;
+    n_pos = sumsq<2>(lp).v;  // done: load position / load velocity (:136-139)
+    n_vel = sumsq<2>(lv).v;
     n_rew = norm<2>(pos).v;  // reward: QUAD position (:143)
   }
 };
 
 // done / reward block shared by the four envs (quadrotor3d.py:106-122).  Strict '>' so that a
 // NaN norm is "not done", as in the reference; `ever_done` is steps_beyond_done is not None.
-RMV_HD bool is_done(const DevParams& P, float n_pos, float n_vel) {
-  return (n_pos > P.pos_done) || (n_vel > P.vel_done);
+RMV_HD bool is_done(const DevParams& P, float pos_sq, float vel_sq) {
+  return (pos_sq > P.pos_sq_max) || (vel_sq > P.vel_sq_max);
 }
 RMV_HD float reward_of(const DevParams& P, bool done, bool ever_done, float n_rew) {
   return done ? (ever_done ? P.later_done_reward : P.first_done_reward) : -n_rew;

@@ -158,10 +158,11 @@ class QuadBatch:
         check(lib().rmv_set_episode(self._h, words.ctypes.data, 0, _stream(stream, self.device)))
 
     def state_view(self):
-        """Device view of the component-major state, shape [S, ld] float32 (columns >= N are padding)."""
+        """Device view of the tiled state, float32 [ld/128, S, 128]: env e is [e // 128, :, e % 128]
+        (lanes of the last tile beyond N are padding)."""
         sp, ep = ctypes.c_void_p(), ctypes.c_void_p()
         check(lib().rmv_state_ptr(self._h, ctypes.byref(sp), ctypes.byref(ep)))
-        return _DeviceView(sp.value, (self.state_dim, self.ld), "<f4", self)
+        return _DeviceView(sp.value, (self.ld // 128, self.state_dim, 128), "<f4", self)
 
     def episode_stats(self, stream=None):
         out = (ctypes.c_double * 4)()

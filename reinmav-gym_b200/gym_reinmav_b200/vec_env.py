@@ -175,8 +175,9 @@ class QuadVecEnv:
         return (t["obs"] if want_obs else None), t["rew"], t["done"]
 
     def state_tensor(self):
-        """Component-major state [S, N] (a view; obs == state in these envs)."""
-        return self._tensors()["state"][:, :self.num_envs]
+        """The handle's state buffer itself, tiled [N_pad/128, S, 128] (a view; obs == state in these
+        envs): env e is ``[e // 128, :, e % 128]``."""
+        return self._tensors()["state"]
 
     def episode_stats(self):
         return self.batch.episode_stats()

@@ -14,8 +14,7 @@ static DevParams to_dev(const rmv_params& p) {
   d.tether_len = p.tether_len; d.pos_done = p.pos_done; d.vel_done = p.vel_done;
   d.thrust_scale = p.thrust_scale; d.first_done_reward = p.first_done_reward;
   d.later_done_reward = p.later_done_reward; d.thrust_clamp = p.thrust_clamp;
-  volatile float tot = p.mass + p.load_mass;
-  d.inv_total_mass = 1.0f / tot;
+  finish_params(d);
   return d;
 }
 
@@ -56,6 +55,13 @@ extern "C" int twin_reset_draws(int kind, unsigned long long seed, unsigned long
   }
   return 0;
 }
+
+// out[0..2] = pos_sq_max, vel_sq_max, inv_mass of the derived parameters
+extern "C" void twin_derived(const rmv_params* p, float* out) {
+  const DevParams P = to_dev(*p);
+  out[0] = P.pos_sq_max; out[1] = P.vel_sq_max; out[2] = P.inv_mass; out[3] = P.inv_total_mass;
+}
+extern "C" float twin_sq_threshold(float t) { return sq_threshold(t); }
 
 extern "C" void twin_sincos(long n, const float* x, float* s, float* c) {
   for (long i = 0; i < n; ++i) sincos_pinned(x[i], s[i], c[i]);

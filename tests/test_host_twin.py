@@ -77,7 +77,10 @@ def test_step_arithmetic_bitwise(host_twin, env_id):
     obs, rew, done = o.step(a, auto_reset=False)
     nan_both = np.isnan(so) & np.isnan(obs)
     assert ((so.view(np.uint32) == obs.view(np.uint32)) | nan_both).all()
-    done2 = (norms[:, 0] > np.float32(pd["pos_done"])) | (norms[:, 1] > np.float32(pd["vel_done"]))
+    derived = np.empty(4, np.float32)
+    host_twin.twin_derived(ctypes.byref(cp), _p(derived))
+    # the kernel thresholds SQUARED norms against the largest y with sqrt(y) <= threshold
+    done2 = (norms[:, 0] > derived[0]) | (norms[:, 1] > derived[1])
     assert np.array_equal(done, done2)
     assert 0.02 < done.mean() < 0.6
     rew2 = np.where(done2, np.float32(1.0), -norms[:, 2]).astype(np.float32)
@@ -85,3 +88,22 @@ def test_step_arithmetic_bitwise(host_twin, env_id):
     if o.tether_margin is not None:
         taut = (o.tether_margin >= 0).mean()
         assert 0.1 < taut < 0.95
+
+
+def test_squared_threshold_is_equivalent_to_the_norm_comparison(host_twin):
+    """sq_threshold(t) = max{y : sqrt_rn(y) <= t}, so  sqrt(y) > t  <=>  y > sq_threshold(t)  for every y."""
+    host_twin.twin_sq_threshold.restype = ctypes.c_float
+    host_twin.twin_sq_threshold.argtypes = [ctypes.c_float]
+    rng = np.random.RandomState(5)
+    for t in [3.0, 10.0, 2.0, 0.0, 1e-20, 1e19, 0.1, 2.5, 7.77] + list(rng.uniform(0, 100, 40)):
+        t = np.float32(t)
+        y = np.float32(host_twin.twin_sq_threshold(ctypes.c_float(float(t))))
+        around = y
+        for _ in range(4):
+            around = np.nextafter(around, np.float32(-np.inf))
+        for _ in range(9):
+            assert (np.sqrt(around) > t) == (around > y), (t, y, around)
+            around = np.nextafter(around, np.float32(np.inf))
+    assert np.isnan(host_twin.twin_sq_threshold(ctypes.c_float(float("nan"))))
+    assert host_twin.twin_sq_threshold(ctypes.c_float(-1.0)) == -1.0
+    assert host_twin.twin_sq_threshold(ctypes.c_float(float("inf"))) == float("inf")
