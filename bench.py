@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the batched quadrotor3d-v0 step() on B200, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          (N > 1: launched by torchrun)
+    python bench.py --impl reference ...                          (the reference CPU arm)
+
+A "step" is ONE pass of the hot path (one fused step kernel: dynamics + reward + done +
+reset-on-done) over one batch of N_ENVS = 2^20 quadrotor3d-v0 envs per GPU with random-policy
+actions (BASELINE.json metric / configs[1] scaled to the metric's N = 2^20).
+
+* value     whole-job env-steps/s, inputs resident in HBM when the timed region starts
+            (state in the handle, actions in a 64-step ring written by the Philox fill kernel).
+* e2e       the same metric through the C-ABI call with HOST buffers (rmv_step_host: pinned
+            host actions -> H2D -> kernel -> D2H of obs/reward/done every step).
+* roofline  algorithmic bytes (101 B per env-step) / CUDA-event time per launch,
+            against MEASURED_PEAKS.json hbm_gbs.
+* cpu_baseline  oracle/scalar.py (one Python object per env, the reference's execution model) on
+            all host cores, a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "reinmav-gym_b200")]
+
+ENV_ID = "quadrotor3d-v0"
+N_ENVS = 1 << 20                 # per GPU (weak scaling)
+STATE_DIM, ACTION_DIM = 10, 4
+ALG_BYTES = 4 * (2 * STATE_DIM + ACTION_DIM + 1) + 1      # 101 B per env-step
+ACT_LO, ACT_HI = 0.0, 10.0
+RING = 64                        # pre-generated action steps (64 x 16 MiB = 1 GiB > L2)
+SEED = 0
+METRIC = "env-steps/sec quadrotor3d-v0 at N=2^20 per GPU"
+UNIT = "env-steps/s"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    """One worker process = a DummyVecEnv of `envs` reference-style env objects stepped `steps` times."""
+    worker, envs, steps, warmup = args
+    import numpy as np
+    from oracle.scalar import ScalarEnv
+    objs = [ScalarEnv(ENV_ID, seed=SEED, env_id=worker * envs + i) for i in range(envs)]
+    for o in objs:
+        o.reset()
+    rng = np.random.RandomState(1000 + worker)
+    acts = rng.uniform(ACT_LO, ACT_HI, size=(steps + warmup, envs, ACTION_DIM))
+
+    def run(t0, t1):
+        for t in range(t0, t1):
+            for i, o in enumerate(objs):
+                _, _, done = o.step(acts[t, i])
+                if done:
+                    o.reset()
+
+    run(0, warmup)
+    begin = time.perf_counter()
+    run(warmup, warmup + steps)
+    return time.perf_counter() - begin
+
+
+def cpu_reference(steps, warmup, target_seconds=15.0, per_core_rate=15000.0):
+    """Times oracle/scalar.py with every host core (process-per-worker, the reference's own scaling
+    model: baselines SubprocVecEnv behind gym_reinmav/run.py:74-89)."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    envs = int(max(1, min(4096, round(target_seconds * per_core_rate / max(1, steps + warmup)))))
+    with mp.get_context("fork").Pool(cores) as pool:
+        times = pool.map(_cpu_worker, [(w, envs, steps, warmup) for w in range(cores)])
+    worst = max(times)
+    total = cores * envs * steps
+    return {"value": total / worst, "seconds": worst, "cores": cores, "envs_per_core": envs, "steps": steps,
+            "sample": "%d processes x %d env objects x %d steps (+%d warm-up), %s, actions ~ U(action_space), "
+                      "reset-on-done, float64 NumPy per env (oracle/scalar.py)" % (cores, envs, steps, warmup, ENV_ID)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    res = cpu_reference(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * res["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s, %d env objects per step over %d host cores (bounded sample of N=2^20)"
+                               % (ENV_ID, res["cores"] * res["envs_per_core"], res["cores"]),
+                   "env_id": ENV_ID, "envs_per_step": res["cores"] * res["envs_per_core"]},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python and does not import here (SURVEY.md R8/R9); this arm runs the "
+                "oracle port that reproduces its trajectories bit for bit (tests/test_oracle_golden.py)",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, n_gpus):
+        self.path = tempfile.mktemp(prefix="rmv_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", ",".join(str(i) for i in range(n_gpus))],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, smax, reasons, busy = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx, util = float(f[1]), float(f[2]), float(f[4])
+            except ValueError:
+                continue
+            sm.append(clk); smax.append(mx); busy.append(util > 0)
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        under = [c for c, b in zip(sm, busy) if b] or sm
+        if under:
+            under.sort()
+            out.update(sm_mhz=under[len(under) // 2], sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(under))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import gym_reinmav_b200 as rmv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
+        args.gpus = world
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU path"
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, A, S = args.envs, ACTION_DIM, STATE_DIM
+    batch = rmv.QuadBatch(ENV_ID, n, device=local, seed=SEED, env_id_offset=rank * n)   # global env ids: shard-invariant
+    batch.set_tuning(vec=args.vec, block=args.block)
+    batch.reset()
+    ring = max(2, min(RING, args.steps + args.warmup))
+    acts = torch.empty((ring, n, A), dtype=torch.float32, device=dev)
+    for t in range(ring):
+        rmv.fill_uniform_actions(acts[t], n, A, ACT_LO, ACT_HI, SEED, env_id_offset=rank * n, step_index=t, device=local)
+    rew = torch.empty((ring, n), dtype=torch.float32, device=dev)
+    done = torch.empty((ring, n), dtype=torch.uint8, device=dev)
+
+    def run_steps(k):
+        """k single-step launches (state streams through HBM every step), actions from the ring."""
+        left = k
+        while left > 0:
+            m = min(left, ring)
+            batch.step_many(m, acts, rew, done, out_ld=n, layout=0, fused=False)
+            left -= m
+
+    sampler = ClockSampler(world) if rank == 0 else None
+
+    # ---- value: K steps, device-resident inputs
+    run_steps(args.warmup)
+    times = []
+    for _ in range(args.repeats):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = batch.launches
+        e0.record()
+        run_steps(args.steps)
+        e1.record()
+        barrier()
+        times.append(max_over_ranks(e0.elapsed_time(e1)))
+        launches = batch.launches - launches0
+    times.sort()
+    ms_total = times[len(times) // 2]
+    ms_per_step = ms_total / args.steps
+    value = world * n * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers through rmv_step_host (H2D + kernel + D2H every step)
+    from gym_reinmav_b200.vec_env import _Pinned
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h_ring = 4
+    h_act = [_Pinned((n, A), "float32") for _ in range(h_ring)]
+    for i, h in enumerate(h_act):
+        h.array[...] = acts[i % ring].cpu().numpy()
+    h_obs, h_rew, h_done = _Pinned((n, S), "float32"), _Pinned((n,), "float32"), _Pinned((n,), "uint8")
+    for t in range(3):
+        batch.step_host(h_act[t % h_ring].array, h_rew.array, h_done.array, h_obs.array)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(e2e_steps):
+        batch.step_host(h_act[t % h_ring].array, h_rew.array, h_done.array, h_obs.array)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0) if world == 1 else 0.0))
+    e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
+    checksum = float(h_rew.array[:1024].sum())            # the step's result is read on the host
+
+    extras = {}
+    if args.extras and world == 1:
+        extras = measure_extras(torch, rmv, args, local)
+
+    clocks = sampler.stop() if sampler else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        res = cpu_reference(args.cpu_steps, 20)
+        cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]}
+
+    if rank == 0:
+        peaks, peak_src = load_peak()
+        achieved = ALG_BYTES * n / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s N=%d envs per GPU, random-policy actions U[0,10)^4, reset-on-done in-kernel"
+                                   % (ENV_ID, n),
+                       "env_id": ENV_ID, "envs_per_gpu": n, "state_dim": S, "action_dim": A,
+                       "launch": "one fused step kernel per step (vec=%d, block=%d), %d-step action ring" % (args.vec, args.block, ring),
+                       "l2": "no flush: per-step traffic %.0f MB (state %.0f MB read+written in place, re-read next step; "
+                             "actions stream from a %.2f GiB ring > 126 MB L2); extras.n23 is the same kernel with a "
+                             "working set that cannot be L2-resident" % (ALG_BYTES * n / 1e6, 4 * S * n / 1e6, ring * n * A * 4 / 2 ** 30),
+                       "timing": "CUDA events on the launch stream, median of %d runs of exactly K steps, max over ranks" % args.repeats},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * A * 4, "d2h_bytes_per_step": n * (4 * S + 4 + 1),
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "path": "rmv_step_host (C-ABI, pinned host buffers): H2D actions, step kernel with obs rows, D2H obs+reward+done, stream sync"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks, "unit": "GB/s", "frac": achieved / peaks,
+                         "traffic": load_traffic(), "kernel": "rmv::k_step<QUAD3D, vec=%d, block=%d>" % (args.vec, args.block),
+                         "algorithmic_bytes_per_launch": ALG_BYTES * n, "avg_launch_us": ms_per_step * 1e3, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "extras": extras,
+            "result_checksum": checksum,
+        }
+        print(json.dumps(line), flush=True)
+    for h in h_act + [h_obs, h_rew, h_done]:
+        h.free()
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_extras(torch, rmv, args, local):
+    """Side measurements that explain the headline (not part of the contract line's value)."""
+    dev = "cuda:%d" % local
+    out = {}
+
+    def time_steps(batch, acts, rew, done, n, k, fused=False, layout=0, act_ld=0):
+        ring = acts.shape[0]
+
+        def run(kk):
+            left = kk
+            while left > 0:
+                m = min(left, ring)
+                batch.step_many(m, acts, rew, done, out_ld=n, layout=layout, act_ld=act_ld, fused=fused)
+                left -= m
+        run(ring)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(k); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / k)
+        return best
+
+    peak, _ = load_peak()
+    cases = [("n23", ENV_ID, 1 << 23, 8, 100, False), ("fused_rollout", ENV_ID, 1 << 20, 64, 256, True),
+             ("quadrotor3d-slungload-v0", "quadrotor3d-slungload-v0", 1 << 20, 32, 300, False),
+             ("quadrotor2d-v0", "quadrotor2d-v0", 1 << 20, 32, 300, False),
+             ("quadrotor2d-slungload-v0", "quadrotor2d-slungload-v0", 1 << 20, 32, 300, False)]
+    bytes_of = {"quadrotor2d-v0": 53, "quadrotor2d-slungload-v0": 85, "quadrotor3d-v0": 101, "quadrotor3d-slungload-v0": 149}
+    bounds = {"quadrotor2d-v0": (-10, 10), "quadrotor2d-slungload-v0": (-10, 10), "quadrotor3d-v0": (0, 10),
+              "quadrotor3d-slungload-v0": (-10, 10)}
+    for name, env_id, n, ring, k, fused in cases:
+        b = rmv.QuadBatch(env_id, n, device=local, seed=SEED)
+        b.set_tuning(vec=args.vec, block=args.block)
+        b.reset()
+        A = b.action_dim
+        lo, hi = bounds[env_id]
+        acts = torch.empty((ring, n, A), dtype=torch.float32, device=dev)
+        for t in range(ring):
+            rmv.fill_uniform_actions(acts[t], n, A, lo, hi, SEED, step_index=t, device=local)
+        rew = torch.empty((ring, n), dtype=torch.float32, device=dev)
+        done = torch.empty((ring, n), dtype=torch.uint8, device=dev)
+        ms = time_steps(b, acts, rew, done, n, k, fused=fused)
+        sps = n / (ms * 1e-3)
+        out[name] = {"env_id": env_id, "n_envs": n, "us_per_step": ms * 1e3, "env_steps_per_s": sps,
+                     "algorithmic_GBps": sps * bytes_of[env_id] / 1e9, "frac_of_hbm_peak": sps * bytes_of[env_id] / 1e9 / peak,
+                     "mode": "one launch per %d steps, state in registers" % ring if fused else "one launch per step"}
+        b.close()
+        del acts, rew, done
+    return out
+
+
+def load_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
+
+
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed
+    ncu --set full capture (profiles/); None if no capture is recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh)["k_step_quadrotor3d_n2pow20"]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU")
+    ap.add_argument("--vec", type=int, default=1)
+    ap.add_argument("--block", type=int, default=128)
+    ap.add_argument("--repeats", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--cpu-steps", type=int, default=2000)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", dest="extras", action="store_false")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
