@@ -276,7 +276,11 @@ def run_gpu_arm(args):
                     "path": "rmv_step_host (C-ABI, pinned host buffers): H2D actions, step kernel with obs rows, D2H obs+reward+done, stream sync"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks, "unit": "GB/s", "frac": achieved / peaks,
-                         "traffic": load_traffic(), "kernel": "rmv::k_step<QUAD3D, vec=%d, block=%d>" % (args.vec, args.block),
+                         "traffic": (load_traffic() or {}).get("dram_bytes_per_launch"),
+                         "traffic_steady_state": ((load_traffic() or {}).get("steady_state") or {}).get("dram_bytes_per_launch"),
+                         "traffic_note": "ncu --set full per launch: cold-cache capture (L2 flushed per replay) / "
+                                         "--cache-control none capture of a back-to-back run (42 MB state L2-resident)",
+                         "kernel": "rmv::k_step<QUAD3D, vec=%d, block=%d>" % (args.vec, args.block),
                          "algorithmic_bytes_per_launch": ALG_BYTES * n, "avg_launch_us": ms_per_step * 1e3, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "extras": extras,
@@ -357,7 +361,7 @@ def load_traffic():
     ncu --set full capture (profiles/); None if no capture is recorded."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh)["k_step_quadrotor3d_n2pow20"]["dram_bytes_per_launch"]
+            return json.load(fh)["k_step_quadrotor3d_n2pow20"]
     except Exception:
         return None
 
