@@ -1,0 +1,143 @@
+"""The reference-facing Python surface on a GPU: baselines-style VecEnv, N=1 gym.Env views, registry."""
+import numpy as np
+import pytest
+
+from oracle.batch import ACTION_BOUNDS, ACTION_DIM, KIND_OF_ID, STATE_DIM, BatchOracle
+from tests.util import same_bits
+
+pytestmark = pytest.mark.gpu
+ENV_IDS = list(KIND_OF_ID)
+
+
+@pytest.fixture(scope="module")
+def rmv():
+    import torch
+    torch.cuda.init()
+    import gym_reinmav_b200
+    return gym_reinmav_b200
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_vec_env_protocol_and_monitor(rmv, env_id):
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    lo, hi = ACTION_BOUNDS[kind]
+    n, steps, seed = 3000, 250, 4
+    venv = rmv.make_vec_env(env_id, "native", num_env=n, seed=seed)
+    assert venv.num_envs == n and venv.observation_space.shape == (S,) and venv.action_space.shape == (A,)
+    assert float(venv.action_space.low[0]) == lo and float(venv.action_space.high[0]) == hi
+    o = BatchOracle(kind, n, seed=seed, dtype=np.float32)
+    obs = venv.reset()
+    assert obs.shape == (n, S) and obs.dtype == np.float32 and same_bits(obs, o.reset())
+    rng = np.random.RandomState(0)
+    ret, length = np.zeros(n, np.float32), np.zeros(n, np.int64)
+    seen = 0
+    for t in range(steps):
+        a = rng.uniform(lo, hi, size=(n, A)).astype(np.float32)
+        obs, rew, done, infos = venv.step(a)
+        obs_ref, rew_ref, done_ref = o.step(a)
+        assert done.dtype == bool and np.array_equal(done, done_ref)
+        assert same_bits(rew, rew_ref) and same_bits(obs, obs_ref)          # done envs report the RESET observation
+        ret = (ret + rew_ref).astype(np.float32)
+        length += 1
+        assert len(infos) == n
+        for i in np.flatnonzero(done_ref):
+            ep = infos[int(i)]["episode"]                                    # baselines Monitor's info['episode']
+            assert ep["l"] == length[i] and np.float32(ep["r"]) == ret[i]
+            seen += 1
+        assert infos[int(np.flatnonzero(~done_ref)[0])] == {}
+        ret[done_ref], length[done_ref] = 0, 0
+    assert seen > 20
+    stats = venv.episode_stats()
+    assert stats["episodes"] == seen and stats["env_steps"] == n * steps
+    with pytest.raises(ValueError):
+        venv.step(np.zeros((n, A + 1), np.float32))
+    venv.close()
+    venv.close()                                                             # idempotent
+
+
+def test_vec_env_tensor_path_matches_host_path(rmv):
+    import torch
+    n, seed = 4096, 8
+    a_env = rmv.QuadVecEnv("quadrotor3d-v0", n, seed=seed)
+    b_env = rmv.QuadVecEnv("quadrotor3d-v0", n, seed=seed)
+    oa = a_env.reset()
+    ob = b_env.reset_tensor()
+    assert same_bits(oa, ob.cpu().numpy())
+    rng = np.random.RandomState(1)
+    for t in range(120):
+        act = rng.uniform(0, 10, size=(n, 4)).astype(np.float32)
+        oa, ra, da, _ = a_env.step(act)
+        ob, rb, db = b_env.step_tensor(torch.as_tensor(act, device="cuda:0"))
+        assert same_bits(oa, ob.cpu().numpy()) and same_bits(ra, rb.cpu().numpy())
+        assert np.array_equal(da, db.cpu().numpy().astype(bool))
+    tiles = b_env.state_tensor()                       # [n/128, S, 128] view of the handle's own buffer
+    rows = tiles.permute(0, 2, 1).reshape(-1, 10)[:n]
+    assert same_bits(rows.cpu().numpy(), oa)
+    a_env.close()
+    b_env.close()
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_single_env_view(rmv, env_id):
+    """The gym.Env surface of the reference classes (quadrotor3d.py:42-185 and twins), N = 1."""
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    env = rmv.make(env_id)
+    assert type(env).__module__.endswith("envs.native")          # run.py:36 derives env_type from this tail
+    assert env.metadata == {"render.modes": ["human"]}
+    assert env.dt == np.float32(0.01) and env.mass == 1.0 and env.g[-1] == -np.float32(9.8)
+    assert env.observation_space.shape == (S,) and env.action_space.shape == (A,)
+    assert env.steps_beyond_done is None
+    assert env.seed(123) == [123]
+    obs = env.reset()
+    assert obs.shape == (S,) and obs.dtype == np.float64 and (np.abs(obs) <= 1).all()
+    o = BatchOracle(kind, 1, seed=123, dtype=np.float32)
+    o.episode[:] = 1                                               # the constructor already reset once
+    assert np.array_equal(obs, o.reset()[0].astype(np.float64))
+    a = env.action_space.sample()
+    obs, rew, done, info = env.step(a)
+    obs_ref, rew_ref, done_ref = o.step(a[None], auto_reset=False)
+    assert isinstance(rew, float) and isinstance(done, bool) and info == {}
+    assert np.array_equal(obs, obs_ref[0].astype(np.float64)) and rew == float(rew_ref[0]) and done == bool(done_ref[0])
+    # drive it out of bounds: first done pays +1 and does NOT reset; the next done pays 0 (steps_beyond_done)
+    far = np.zeros(S)
+    far[0] = 50.0
+    if S in (9, 16):
+        far[5 if S == 9 else 10] = 50.0
+    env.state = far
+    assert np.array_equal(env.state, far)
+    _, r1, d1, _ = env.step(np.zeros(A))
+    _, r2, d2, _ = env.step(np.zeros(A))
+    assert (d1, r1, d2, r2) == (True, 1.0, True, 0.0)
+    assert env.steps_beyond_done is not None and abs(env.state[0]) > 40
+    env.reset()
+    env.state = far
+    assert env.step(np.zeros(A))[1] == 0.0                          # reset() does not clear it (quadrotor3d.py:182-185)
+    assert env.render() is None
+    env.close()
+
+
+def test_unknown_id_and_registry(rmv):
+    assert sorted(rmv.ENTRY_POINTS) == sorted(KIND_OF_ID)
+    with pytest.raises(KeyError):
+        rmv.make("quadrotor4d-v0")
+    with pytest.raises(KeyError):
+        rmv.QuadBatch("nope", 4)
+    with pytest.raises(rmv.RmvError):
+        rmv.QuadBatch("quadrotor3d-v0", 0)
+
+
+def test_params_override_repair_b(rmv):
+    """quadrotor2d.py:95-98 repair B = velocity threshold 2.0 through rmv_params."""
+    import torch
+    b = rmv.QuadBatch("quadrotor2d-v0", 2, params={"vel_done": 2.0})
+    assert b.params["vel_done"] == 2.0 and b.params["thrust_scale"] == 10.0
+    b.set_state(np.array([[0, 0, 0, 0, 0], [0, 0, 0, 2.5, 0]], np.float32))
+    rew = torch.empty(2, device="cuda:0")
+    done = torch.empty(2, dtype=torch.uint8, device="cuda:0")
+    b.step(torch.zeros((2, 2), device="cuda:0"), rew, done, auto_reset=False)
+    assert done.cpu().tolist() == [0, 1]
+    with pytest.raises(KeyError):
+        rmv.QuadBatch("quadrotor2d-v0", 2, params={"no_such_field": 1.0})
+    b.close()
