@@ -121,6 +121,9 @@ RMV_API int rmv_set_seed(rmv_env* env, uint64_t seed);
 /* Launch tuning (benchmarks / sweeps): vec = envs per thread (0 = auto, 1, 2, 4),
  * block = threads per CTA (multiple of 32, <= 256). */
 RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block);
+/* number of chunks rmv_step_host pipelines a batch through (H2D | kernel | D2H overlap); 0 = auto
+ * (8 for n >= 65536, else 1) */
+RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks);
 
 /* ---- state access (parity tests, checkpoint/resume, zero-copy views) --------------------- */
 /* device pointers of the handle-owned buffers: state float32 [n_pad/128][S][128]; episode uint32 [n_pad]
@@ -173,11 +176,26 @@ RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act_dev, int a
 
 /* Same as rmv_step with HOST buffers (pinned memory recommended: rmv_host_alloc): copies the
  * actions host->device, runs the step kernel, copies reward/done/(obs) back and synchronises
- * `stream`.  This is what the Python VecEnv's numpy step() calls. */
+ * `stream`.  This is what the Python VecEnv's numpy step() calls.  Large batches are pipelined in
+ * chunks over internal streams (ordered after everything already queued on `stream`) so that both
+ * PCIe directions and the kernel overlap. */
 RMV_API int rmv_step_host(rmv_env* env, const float* act_host /*[n][A]*/, float* reward_host,
                   uint8_t* done_host, float* obs_host /*[n][S] or NULL*/, int auto_reset,
                   void* stream);
 RMV_API int rmv_reset_host(rmv_env* env, float* obs_host /*[n][S]*/, void* stream);
+
+/* ---- controllers (the caller on the input side of step() in every reference test) ---- */
+/* control(): the reference's geometric controller for every env, actions written to act_dev
+ * (layout as in rmv_step).  Replaces Quadrotor2D.control (quadrotor2d.py:115-138),
+ * Quadrotor2DSlungload.control (quadrotor2d_slungload.py:156-183), Quadrotor3D.control
+ * (quadrotor3d.py:126-180), Quadrotor3DSlungload.control (quadrotor3d_slungload.py:169-226).
+ * ref_pos / ref_vel: D floats each (D = 2 or 3), NULL -> the reference's defaults
+ * (ref_pos (0,0) | (0,0,2) | slung 3D (0,0,1); ref_vel 0). */
+RMV_API int rmv_control(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_dev,
+                        int act_layout, int64_t act_ld, void* stream);
+/* same with a host destination [n][A]; synchronises `stream` */
+RMV_API int rmv_control_host(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_host,
+                             void* stream);
 
 /* ---- synthetic inputs --------------------------------------------------------------------- */
 /* Random-policy actions ~ U[low, high) for n envs from Philox4x32-10 keyed by

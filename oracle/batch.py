@@ -305,6 +305,78 @@ class BatchOracle:
         # done: load position / load velocity (:136-139); reward: QUAD position (:143)
         return new, self._norm(lp2), self._norm(lv2), self._norm(pos2)
 
+    # ------------------------------------------------------------------ control()
+    REF_POS = {QUAD2D: (0.0, 0.0), QUAD2D_SLUNG: (0.0, 0.0), QUAD3D: (0.0, 0.0, 2.0), QUAD3D_SLUNG: (0.0, 0.0, 1.0)}
+
+    def control(self, ref_pos=None, ref_vel=None):
+        """The reference's geometric controllers, vectorised: ``[N, A]`` actions from the current state.
+
+        2D kinds: quadrotor2d.py:115-138 / quadrotor2d_slungload.py:156-183 (PD acceleration, attitude
+        from atan2, first-order attitude loop tau = 0.1).  3D kinds: quadrotor3d.py:126-180 /
+        quadrotor3d_slungload.py:169-226 (PD acceleration, desired attitude via ``Quaternion(matrix=)``
+        — pyquaternion's trace method on the transposed matrix — error quaternion from the
+        UN-normalised current attitude, tau = 0.3, thrust projected on the normalised body z)."""
+        s = self.state
+        rp = [self._c(v) for v in (ref_pos if ref_pos is not None else self.REF_POS[self.kind])]
+        rv = [self._c(v) for v in (ref_vel if ref_vel is not None else (0.0,) * len(rp))]
+        gr = self._c(self.p["gravity"])
+        with np.errstate(all="ignore"):
+            if self.kind in (QUAD2D, QUAD2D_SLUNG):
+                kp, kv, tau = self._c(-5.0), self._c(-4.0), self._c(0.1)
+                pos, th, vel = s[0:2], s[2], s[3:5]
+                acc = [kp * (pos[i] - rp[i]) + kv * (vel[i] - rv[i]) + (gr if i == 1 else self._c(0.0)) for i in range(2)]
+                att = np.arctan2(acc[1], acc[0]) - self._c(np.pi / 2)
+                w = (self._c(-1.0) / tau) * (th - att)
+                thrust = self._c(self.p["mass"]) * self._norm(acc)
+                return np.stack([thrust, w], axis=1)
+            kp, kv, tau = self._c(-5.0), self._c(-4.0), self._c(0.3)
+            pos, q, vel = s[0:3], s[3:7], s[7:10]
+            acc = [kp * (pos[i] - rp[i]) + kv * (vel[i] - rv[i]) - (-gr if i == 2 else self._c(0.0)) for i in range(3)]
+            na = self._norm(acc)
+            zb = [a / na for a in acc]
+            # xb = yc x zb with yc = (0,1,0); yb = zb x xb
+            xb = [zb[2], 0 * zb[0], -zb[0]]
+            nx = self._norm(xb)
+            xb = [x / nx for x in xb]
+            yb = [zb[1] * xb[2] - zb[2] * xb[1], zb[2] * xb[0] - zb[0] * xb[2], zb[0] * xb[1] - zb[1] * xb[0]]
+            nz = self._norm(zb)
+            zb = [z / nz for z in zb]
+            # rotmat columns are (xb, yb, zb); pyquaternion works on m = rotmat^T, i.e. rows (xb, yb, zb)
+            m = [xb, yb, zb]
+            qd = self._quat_from_rows(m)
+            # error = conj(q_current) * q_desired with the raw (un-normalised) state quaternion
+            w0, x0, y0, z0 = q[0], -q[1], -q[2], -q[3]
+            dw, dx, dy, dz = qd
+            ew = w0 * dw - x0 * dx - y0 * dy - z0 * dz
+            ex = x0 * dw + w0 * dx - z0 * dy + y0 * dz
+            ey = y0 * dw + z0 * dx + w0 * dy - x0 * dz
+            ez = z0 * dw - y0 * dx + x0 * dy + w0 * dz
+            gain = (self._c(2.0) / tau) * np.sign(ew)
+            _, e3 = self._thrust_axis_3d(q)
+            thrust = acc[0] * e3[0] + acc[1] * e3[1] + acc[2] * e3[2]
+            return np.stack([thrust, gain * ex, gain * ey, gain * ez], axis=1)
+
+    def _quat_from_rows(self, m):
+        """pyquaternion ``Quaternion(matrix=R)`` after its ``m = R^T``: the
+        branch on m22 / m00 vs m11 picks the numerically largest component."""
+        one = self._c(1.0)
+        m00, m01, m02 = m[0]
+        m10, m11, m12 = m[1]
+        m20, m21, m22 = m[2]
+        c1 = m22 < 0
+        c2 = m00 > m11
+        c3 = m00 < -m11
+        ta, qa = one + m00 - m11 - m22, (m12 - m21, None, m01 + m10, m20 + m02)
+        tb, qb = one - m00 + m11 - m22, (m20 - m02, m01 + m10, None, m12 + m21)
+        tc, qc = one - m00 - m11 + m22, (m01 - m10, m20 + m02, m12 + m21, None)
+        td, qd = one + m00 + m11 + m22, (None, m12 - m21, m20 - m02, m01 - m10)
+        fill = lambda qq, t: [t if c is None else c for c in qq]
+        qa, qb, qc, qd = fill(qa, ta), fill(qb, tb), fill(qc, tc), fill(qd, td)
+        t = np.where(c1, np.where(c2, ta, tb), np.where(c3, tc, td))
+        comps = [np.where(c1, np.where(c2, qa[i], qb[i]), np.where(c3, qc[i], qd[i])) for i in range(4)]
+        scale = self._c(0.5) / np.sqrt(t)
+        return [c * scale for c in comps]
+
     # ------------------------------------------------------------------ public step
     def step(self, actions, auto_reset=True):
         """One step of all envs.  ``actions`` is ``[N, A]``.

@@ -12,6 +12,7 @@
 
 #include "rmv.h"
 #include "rmv_kernels.cuh"
+#include "rmv_control.cuh"
 
 using namespace rmv;
 
@@ -85,6 +86,12 @@ struct rmv_env {
   float* h_rew = nullptr;
   uint8_t* h_done = nullptr;
   float* h_obs = nullptr;
+  // pipeline of the *_host entry points (lazy)
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t pipe_start = nullptr;
+  int host_chunks = 0;      // 0 = auto
+  int64_t host_launches = 0;
   // tuning
   int vec = 0;     // 0 = auto
   int block = 128;
@@ -149,6 +156,11 @@ static void free_all(rmv_env* e) {
   cudaFree(e->last_return); cudaFree(e->last_length); cudaFree(e->cum_return);
   cudaFree(e->cum_length); cudaFree(e->fin_count); cudaFree(e->stats_dev);
   cudaFree(e->h_act); cudaFree(e->h_rew); cudaFree(e->h_done); cudaFree(e->h_obs);
+  for (int i = 0; i < 3; ++i) {
+    if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]);
+    if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]);
+  }
+  if (e->pipe_start) cudaEventDestroy(e->pipe_start);
 }
 
 extern "C" RMV_API int rmv_create(rmv_env** out, int kind, int64_t n_envs, int64_t env_id_offset, int device,
@@ -223,6 +235,13 @@ extern "C" RMV_API int rmv_get_params(const rmv_env* env, rmv_params* out) {
 extern "C" RMV_API int rmv_set_seed(rmv_env* env, uint64_t seed) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
   env->seed = seed;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(chunks >= 0 && chunks <= 1024, "chunks must be in [0, 1024] (0 = auto)");
+  env->host_chunks = chunks;
   return RMV_OK;
 }
 
@@ -368,15 +387,18 @@ static cudaError_t launch_step_k(const rmv_env* e, const StepArgs& args, int vec
   }
 }
 
+// Launches the step (or rollout) kernel for the envs [c0, c0 + cn) of the handle (c0 a multiple of the
+// 128-env tile; the whole handle when cn == n).  act / rew / done / obs point at env c0's element.
 static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act_ld, int64_t act_step_stride,
                        float* rew, uint8_t* done, int64_t out_ld, float* obs, int auto_reset, int n_steps,
-                       cudaStream_t st) {
+                       cudaStream_t st, int64_t c0 = 0, int64_t cn = -1, bool advance_clock = true) {
+  if (cn < 0) cn = e->n;
   RMV_REQUIRE(act != nullptr, "act_dev is NULL");
   RMV_REQUIRE(act_layout == RMV_ACT_AOS || act_layout == RMV_ACT_SOA, "bad act_layout %d", act_layout);
-  if (act_layout == RMV_ACT_SOA) RMV_REQUIRE(act_ld >= e->n, "act_ld (%lld) < n_envs", (long long)act_ld);
+  if (act_layout == RMV_ACT_SOA) RMV_REQUIRE(act_ld >= cn, "act_ld (%lld) < n_envs", (long long)act_ld);
   RMV_REQUIRE(aligned(act, 4) && aligned(rew, 4) && aligned(obs, 4), "float buffers must be 4-byte aligned");
-  // widest vector width every buffer supports
-  int vec = e->vec ? e->vec : 2;
+  // widest vector width every buffer supports (auto = 1: measured fastest, profiles/r1_sweep_v1_tiled.txt)
+  int vec = e->vec ? e->vec : 1;
   auto ok_for = [&](int v) {
     if (v == 1) return true;
     const size_t fb = 4u * v;
@@ -395,12 +417,14 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
     return fail(RMV_EALIGN, "buffers are not aligned for the forced vector width %d", e->vec);
 
   StepArgs a;
-  a.state = e->state; a.episode = e->episode; a.act = act; a.reward = rew; a.done = done; a.obs = obs;
-  a.ep_return = e->ep_return; a.ep_start = e->ep_start; a.last_return = e->last_return;
-  a.last_length = e->last_length; a.cum_return = e->cum_return; a.cum_length = e->cum_length;
-  a.fin_count = e->fin_count;
-  a.n = e->n; a.act_ld = act_ld; a.out_ld = out_ld; a.act_step_stride = act_step_stride;
-  a.env_id_offset = e->env_id_offset; a.seed = e->seed; a.step_index = e->step_index;
+  auto at = [c0](auto* p) { return p ? p + c0 : p; };
+  a.state = e->state + (c0 / kTile) * (int64_t)(e->S * kTile); a.episode = e->episode + c0;
+  a.act = act; a.reward = rew; a.done = done; a.obs = obs;
+  a.ep_return = at(e->ep_return); a.ep_start = at(e->ep_start); a.last_return = at(e->last_return);
+  a.last_length = at(e->last_length); a.cum_return = at(e->cum_return); a.cum_length = at(e->cum_length);
+  a.fin_count = at(e->fin_count);
+  a.n = cn; a.act_ld = act_ld; a.out_ld = out_ld; a.act_step_stride = act_step_stride;
+  a.env_id_offset = e->env_id_offset + c0; a.seed = e->seed; a.step_index = e->step_index;
   a.n_steps = n_steps; a.act_soa = (act_layout == RMV_ACT_SOA); a.auto_reset = auto_reset ? 1 : 0;
   a.P = e->dp;
   cudaError_t err;
@@ -411,7 +435,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
     default: err = launch_step_k<QUAD3D_SLUNG>(e, a, vec, st); break;
   }
   if (err != cudaSuccess) return fail(RMV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(err));
-  e->step_index += (uint32_t)n_steps;
+  if (advance_clock) e->step_index += (uint32_t)n_steps;
   return RMV_OK;
 }
 
@@ -441,6 +465,19 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
   return RMV_OK;
 }
 
+// Host-buffer step.  Large batches are cut into chunks of whole state tiles that flow through three
+// internal streams: chunk i's host->device action copy, its step kernel and its device->host result copies
+// are ordered inside one stream, different chunks overlap — so the two PCIe directions and the kernel run
+// concurrently and the call costs ~max(H2D, D2H) instead of their sum.
+static int ensure_pipe(rmv_env* e) {
+  for (int i = 0; i < 3; ++i) {
+    if (!e->pipe[i]) RMV_CUDA(cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking));
+    if (!e->pipe_done[i]) RMV_CUDA(cudaEventCreateWithFlags(&e->pipe_done[i], cudaEventDisableTiming));
+  }
+  if (!e->pipe_start) RMV_CUDA(cudaEventCreateWithFlags(&e->pipe_start, cudaEventDisableTiming));
+  return RMV_OK;
+}
+
 extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float* reward_host, uint8_t* done_host,
                              float* obs_host, int auto_reset, void* stream) {
   RMV_REQUIRE(env != nullptr && act_host != nullptr, "NULL argument");
@@ -448,14 +485,45 @@ extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = ensure_staging(env);
   if (rc) return rc;
-  RMV_CUDA(cudaMemcpyAsync(env->h_act, act_host, (size_t)env->n * env->A * sizeof(float), cudaMemcpyHostToDevice, st));
-  rc = launch_step(env, env->h_act, RMV_ACT_AOS, 0, 0, env->h_rew, env->h_done, env->n,
-                   obs_host ? env->h_obs : nullptr, auto_reset, 1, st);
+  const int64_t n = env->n;
+  const int S = env->S, A = env->A;
+  int chunks = env->host_chunks > 0 ? env->host_chunks : (n >= (1 << 16) ? 8 : 1);
+  int64_t per = ((n + chunks - 1) / chunks + 1023) / 1024 * 1024;      // whole tiles, aligned for every vector width
+  if (per >= n) chunks = 1;
+  if (chunks == 1) {
+    RMV_CUDA(cudaMemcpyAsync(env->h_act, act_host, (size_t)n * A * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = launch_step(env, env->h_act, RMV_ACT_AOS, 0, 0, env->h_rew, env->h_done, n, obs_host ? env->h_obs : nullptr,
+                     auto_reset, 1, st);
+    if (rc) return rc;
+    if (reward_host) RMV_CUDA(cudaMemcpyAsync(reward_host, env->h_rew, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (done_host) RMV_CUDA(cudaMemcpyAsync(done_host, env->h_done, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host, env->h_obs, (size_t)n * S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RMV_CUDA(cudaStreamSynchronize(st));
+    return RMV_OK;
+  }
+  rc = ensure_pipe(env);
   if (rc) return rc;
-  if (reward_host) RMV_CUDA(cudaMemcpyAsync(reward_host, env->h_rew, (size_t)env->n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (done_host) RMV_CUDA(cudaMemcpyAsync(done_host, env->h_done, (size_t)env->n, cudaMemcpyDeviceToHost, st));
-  if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host, env->h_obs, (size_t)env->n * env->S * sizeof(float), cudaMemcpyDeviceToHost, st));
-  RMV_CUDA(cudaStreamSynchronize(st));
+  RMV_CUDA(cudaEventRecord(env->pipe_start, st));          // everything queued on the caller's stream comes first
+  for (int i = 0; i < 3; ++i) RMV_CUDA(cudaStreamWaitEvent(env->pipe[i], env->pipe_start, 0));
+  int k = 0;
+  for (int64_t c0 = 0; c0 < n; c0 += per, ++k) {
+    const int64_t cn = (n - c0 < per) ? n - c0 : per;
+    cudaStream_t ps = env->pipe[k % 3];
+    RMV_CUDA(cudaMemcpyAsync(env->h_act + c0 * A, act_host + c0 * A, (size_t)cn * A * sizeof(float), cudaMemcpyHostToDevice, ps));
+    rc = launch_step(env, env->h_act + c0 * A, RMV_ACT_AOS, 0, 0, env->h_rew + c0, env->h_done + c0, cn,
+                     obs_host ? env->h_obs + c0 * S : nullptr, auto_reset, 1, ps, c0, cn, false);
+    if (rc) return rc;
+    if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host + c0 * S, env->h_obs + c0 * S, (size_t)cn * S * sizeof(float), cudaMemcpyDeviceToHost, ps));
+    if (reward_host) RMV_CUDA(cudaMemcpyAsync(reward_host + c0, env->h_rew + c0, (size_t)cn * sizeof(float), cudaMemcpyDeviceToHost, ps));
+    if (done_host) RMV_CUDA(cudaMemcpyAsync(done_host + c0, env->h_done + c0, (size_t)cn, cudaMemcpyDeviceToHost, ps));
+  }
+  env->step_index += 1u;
+  env->host_launches += k;
+  for (int i = 0; i < 3; ++i) {
+    RMV_CUDA(cudaEventRecord(env->pipe_done[i], env->pipe[i]));
+    RMV_CUDA(cudaStreamWaitEvent(st, env->pipe_done[i], 0));   // later work on the caller's stream sees the new state
+  }
+  for (int i = 0; i < 3; ++i) RMV_CUDA(cudaStreamSynchronize(env->pipe[i]));
   return RMV_OK;
 }
 
@@ -468,6 +536,50 @@ extern "C" RMV_API int rmv_reset_host(rmv_env* env, float* obs_host, void* strea
   rc = rmv_reset(env, nullptr, obs_host ? env->h_obs : nullptr, stream);
   if (rc) return rc;
   if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host, env->h_obs, (size_t)env->n * env->S * sizeof(float), cudaMemcpyDeviceToHost, st));
+  RMV_CUDA(cudaStreamSynchronize(st));
+  return RMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// controllers
+// ------------------------------------------------------------------------------------------
+extern "C" RMV_API int rmv_control(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_dev,
+                                   int act_layout, int64_t act_ld, void* stream) {
+  RMV_REQUIRE(env != nullptr && act_dev != nullptr, "NULL argument");
+  RMV_REQUIRE(act_layout == RMV_ACT_AOS || act_layout == RMV_ACT_SOA, "bad act_layout %d", act_layout);
+  if (act_layout == RMV_ACT_SOA) RMV_REQUIRE(act_ld >= env->n, "act_ld (%lld) < n_envs", (long long)act_ld);
+  RMV_ON_DEVICE(env->device);
+  ControlArgs a;
+  a.state = env->state; a.act = act_dev; a.n = env->n; a.act_ld = act_ld; a.act_soa = (act_layout == RMV_ACT_SOA);
+  static const float kRef[RMV_NUM_KINDS][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 2.0f}, {0, 0, 1.0f}};
+  const int D = (env->kind == RMV_QUAD2D || env->kind == RMV_QUAD2D_SLUNG) ? 2 : 3;
+  for (int i = 0; i < 3; ++i) {
+    a.ref_pos[i] = (i < D) ? (ref_pos ? ref_pos[i] : kRef[env->kind][i]) : 0.0f;
+    a.ref_vel[i] = (i < D && ref_vel) ? ref_vel[i] : 0.0f;
+  }
+  a.mass = env->params.mass; a.gravity = env->params.gravity;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = blocks_for(env->n, 128);
+  switch (env->kind) {
+    case RMV_QUAD2D: k_control<QUAD2D><<<grid, 128, 0, st>>>(a); break;
+    case RMV_QUAD2D_SLUNG: k_control<QUAD2D_SLUNG><<<grid, 128, 0, st>>>(a); break;
+    case RMV_QUAD3D: k_control<QUAD3D><<<grid, 128, 0, st>>>(a); break;
+    default: k_control<QUAD3D_SLUNG><<<grid, 128, 0, st>>>(a); break;
+  }
+  RMV_CUDA(cudaGetLastError());
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_control_host(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_host,
+                                        void* stream) {
+  RMV_REQUIRE(env != nullptr && act_host != nullptr, "NULL argument");
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_staging(env);
+  if (rc) return rc;
+  rc = rmv_control(env, ref_pos, ref_vel, env->h_act, RMV_ACT_AOS, 0, stream);
+  if (rc) return rc;
+  RMV_CUDA(cudaMemcpyAsync(act_host, env->h_act, (size_t)env->n * env->A * sizeof(float), cudaMemcpyDeviceToHost, st));
   RMV_CUDA(cudaStreamSynchronize(st));
   return RMV_OK;
 }

@@ -52,6 +52,7 @@ SIGNATURES = {
     "rmv_get_params": (_i, [_vp, ctypes.POINTER(Params)]),
     "rmv_set_seed": (_i, [_vp, _u64]),
     "rmv_set_tuning": (_i, [_vp, _i, _i]),
+    "rmv_set_host_chunks": (_i, [_vp, _i]),
     "rmv_state_ptr": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "rmv_set_state": (_i, [_vp, _vp, _i, _vp]),
     "rmv_get_state": (_i, [_vp, _vp, _i, _vp]),
@@ -62,6 +63,8 @@ SIGNATURES = {
     "rmv_step_many": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp, _i64, _i, _vp]),
     "rmv_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rmv_reset_host": (_i, [_vp, _vp, _vp]),
+    "rmv_control": (_i, [_vp, _pf, _pf, _vp, _i, _i64, _vp]),
+    "rmv_control_host": (_i, [_vp, _pf, _pf, _vp, _vp]),
     "rmv_fill_uniform_actions": (_i, [_vp, _i64, _i, _i, _i64, _f, _f, _u64, _i64, _u32, _i, _vp]),
     "rmv_episode_stats": (_i, [_vp, ctypes.POINTER(ctypes.c_double), _vp]),
     "rmv_episode_ptr": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),

@@ -110,6 +110,9 @@ class QuadBatch:
     def set_tuning(self, vec=0, block=256):
         check(lib().rmv_set_tuning(self._h, int(vec), int(block)))
 
+    def set_host_chunks(self, chunks=0):
+        check(lib().rmv_set_host_chunks(self._h, int(chunks)))
+
     # ---------------------------------------------------------------- hot path (device buffers)
     def reset(self, mask=None, obs=None, stream=None):
         check(lib().rmv_reset(self._h, _ptr(mask), _ptr(obs), _stream(stream, self.device)))
@@ -134,6 +137,25 @@ class QuadBatch:
 
     def reset_host(self, obs, stream=None):
         check(lib().rmv_reset_host(self._h, _ptr(obs), _stream(stream, self.device)))
+        self.launches += 1
+
+    # ---------------------------------------------------------------- controllers
+    @staticmethod
+    def _ref(v):
+        if v is None:
+            return None
+        v = [float(x) for x in v]
+        return (ctypes.c_float * len(v))(*v)
+
+    def control(self, actions, ref_pos=None, ref_vel=None, layout=ACT_AOS, act_ld=0, stream=None):
+        """The reference's geometric controller for every env -> device action buffer."""
+        check(lib().rmv_control(self._h, self._ref(ref_pos), self._ref(ref_vel), _ptr(actions), layout, int(act_ld),
+                                _stream(stream, self.device)))
+        self.launches += 1
+
+    def control_host(self, actions, ref_pos=None, ref_vel=None, stream=None):
+        check(lib().rmv_control_host(self._h, self._ref(ref_pos), self._ref(ref_vel), _ptr(actions),
+                                     _stream(stream, self.device)))
         self.launches += 1
 
     # ---------------------------------------------------------------- state access

@@ -96,6 +96,7 @@ class NativeQuadEnv(_EnvBase):
         return 0 if (int(self._batch.get_episode_words()[0]) & _capi.EVER_DONE_BIT) else None
 
     def control(self):
-        raise NotImplementedError(
-            "control() (the reference's geometric controller, e.g. quadrotor3d.py:126-180) is not part of the "
-            "step()/reset() path yet — SURVEY.md §8(f) rank 1")
+        """The reference's geometric controller for the current state (quadrotor3d.py:126-180 and
+        twins), evaluated by the batched CUDA controller kernel; honours ``self.ref_pos`` / ``self.ref_vel``."""
+        self._batch.control_host(self._act, ref_pos=self.ref_pos, ref_vel=self.ref_vel)
+        return self._act[0].astype(np.float64)

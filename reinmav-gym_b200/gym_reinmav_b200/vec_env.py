@@ -174,6 +174,16 @@ class QuadVecEnv:
         self.batch.step(actions, t["rew"], t["done"], obs=t["obs"] if want_obs else None, auto_reset=True)
         return (t["obs"] if want_obs else None), t["rew"], t["done"]
 
+    def control_tensor(self, ref_pos=None, ref_vel=None):
+        """Actions [N, A] of the reference's geometric controller for the current states (device tensor)."""
+        import torch
+        t = self._tensors()
+        if "act" not in t:
+            t["act"] = torch.empty((self.num_envs, self.batch.action_dim), dtype=torch.float32,
+                                   device="cuda:%d" % self.device)
+        self.batch.control(t["act"], ref_pos=ref_pos, ref_vel=ref_vel)
+        return t["act"]
+
     def state_tensor(self):
         """The handle's state buffer itself, tiled [N_pad/128, S, 128] (a view; obs == state in these
         envs): env e is ``[e // 128, :, e % 128]``."""

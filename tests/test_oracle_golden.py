@@ -106,3 +106,18 @@ def test_fixtures_are_what_the_reference_produces_now(env_id, repair):
     fresh = make_golden._kat(cls, kind, rng)
     for k, v in fresh.items():
         assert np.array_equal(v, g[k]), k
+
+
+@pytest.mark.parametrize("env_id,repair", CASES)
+def test_batch_control_matches_reference_controller(env_id, repair):
+    """ctrl_* fixtures: the reference's own test loop control() -> step() (test/test_quadrotor3d.py:12-22)."""
+    g = load_golden(env_id, repair)
+    T = g["ctrl_a"].shape[0]
+    states = np.concatenate([g["ctrl_obs0"][None], g["ctrl_obs"][:-1]], axis=0)     # state before step t
+    o = BatchOracle(env_id, T, dtype=np.float64, repair=repair)
+    o.state = states.T.copy()
+    np.testing.assert_allclose(o.control(), g["ctrl_a"], rtol=0, atol=1e-10)
+    o32 = BatchOracle(env_id, T, dtype=np.float32, repair=repair)
+    o32.state = states.T.astype(np.float32)
+    a32 = o32.control()
+    assert (np.abs(a32 - g["ctrl_a"]) <= 3e-5 * np.maximum(1.0, np.abs(g["ctrl_a"]))).all()
