@@ -14,9 +14,9 @@ import os
 
 import numpy as np
 
-from .. import _capi
-from ..batch import QuadBatch
-from ..vec_env import make_spaces
+from ... import _capi
+from ...batch import QuadBatch
+from ...vec_env import make_spaces
 
 try:                                    # be a real gym.Env when gym / gymnasium is installed
     import gym as _gym
