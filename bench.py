@@ -99,7 +99,7 @@ def run_reference_arm(args):
         "note": "the reference is pure Python and does not import here (SURVEY.md R8/R9); this arm runs the "
                 "oracle port that reproduces its trajectories bit for bit (tests/test_oracle_golden.py)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -274,7 +274,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * A * 4, "d2h_bytes_per_step": n * (4 * S + 4 + 1),
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "path": "rmv_step_host (C-ABI, pinned host buffers): H2D actions, step kernel with obs rows, D2H obs+reward+done, stream sync"},
-            "gpu_launches": launches,
+            "gpu_launches": launches * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks, "unit": "GB/s", "frac": achieved / peaks,
                          "traffic": (load_traffic() or {}).get("dram_bytes_per_launch"),
                          "traffic_steady_state": ((load_traffic() or {}).get("steady_state") or {}).get("dram_bytes_per_launch"),
@@ -286,7 +286,7 @@ def run_gpu_arm(args):
             "extras": extras,
             "result_checksum": checksum,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     for h in h_act + [h_obs, h_rew, h_done]:
         h.free()
     batch.close()
@@ -366,7 +366,30 @@ def load_traffic():
         return None
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under
+    NCCL_DEBUG, warnings from C code), so everything else is sent to stderr and the JSON line is written
+    to the original descriptor at the end."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)

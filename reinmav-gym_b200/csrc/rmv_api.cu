@@ -170,7 +170,7 @@ extern "C" RMV_API int rmv_create(rmv_env** out, int kind, int64_t n_envs, int64
   RMV_REQUIRE(kind >= 0 && kind < RMV_NUM_KINDS, "unknown env kind %d", kind);
   RMV_REQUIRE(n_envs > 0, "n_envs must be positive (got %lld)", (long long)n_envs);
   RMV_REQUIRE(env_id_offset >= 0, "env_id_offset must be >= 0");
-  RMV_REQUIRE(n_envs < (int64_t)1 << 40, "n_envs too large");
+  RMV_REQUIRE(n_envs <= (int64_t)1 << 30, "n_envs must be <= 2^30 per handle (32-bit env indices inside a launch)");
   int count = 0;
   cudaError_t ce = cudaGetDeviceCount(&count);
   if (ce != cudaSuccess || count <= 0)
@@ -248,7 +248,7 @@ extern "C" RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks) {
 extern "C" RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
   RMV_REQUIRE(vec == 0 || vec == 1 || vec == 2 || vec == 4, "vec must be 0 (auto), 1, 2 or 4");
-  RMV_REQUIRE(block == 128 || block == 256, "block must be 128 or 256");
+  RMV_REQUIRE(block == 128, "the step kernel is built for 128 threads per CTA");
   env->vec = vec; env->block = block;
   return RMV_OK;
 }
@@ -358,24 +358,25 @@ extern "C" RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* o
 // ------------------------------------------------------------------------------------------
 static inline bool aligned(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-template <int KIND, int V, int BLOCK>
-static cudaError_t launch_step_kvb(const StepArgs& args, cudaStream_t st) {
+template <int KIND, int V, bool OBS, bool TRACK>
+static cudaError_t launch_step_kvf(const StepArgs& args, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;
-  const int64_t per_cta = (int64_t)BLOCK * V;
-  const size_t smem = args.obs ? (size_t)(BLOCK / 32) * 32 * SP * sizeof(float) : 0;
-  k_step<KIND, V, BLOCK><<<blocks_for(args.n, per_cta), BLOCK, smem, st>>>(args);
+  const size_t smem = OBS ? (size_t)kWarps * 32 * SP * sizeof(float) : 0;
+  k_step<KIND, V, OBS, TRACK><<<blocks_for(args.n, (int64_t)kBlock * V), kBlock, smem, st>>>(args);
   return cudaGetLastError();
 }
 
 template <int KIND, int V>
 static cudaError_t launch_step_kv(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
-  if (args.n_steps > 1 || e->force_rollout) {
+  if (args.n_steps > 1) {
     const int64_t groups = (args.n + V - 1) / V;
     k_rollout<KIND, V><<<blocks_for(groups, 128), 128, 0, st>>>(args);
     return cudaGetLastError();
   }
-  return e->block == 256 ? launch_step_kvb<KIND, V, 256>(args, st) : launch_step_kvb<KIND, V, 128>(args, st);
+  const bool track = args.ep_return != nullptr;
+  if (args.obs) return track ? launch_step_kvf<KIND, V, true, true>(args, st) : launch_step_kvf<KIND, V, true, false>(args, st);
+  return track ? launch_step_kvf<KIND, V, false, true>(args, st) : launch_step_kvf<KIND, V, false, false>(args, st);
 }
 
 template <int KIND>
@@ -385,6 +386,7 @@ static cudaError_t launch_step_k(const rmv_env* e, const StepArgs& args, int vec
     case 2: return launch_step_kv<KIND, 2>(e, args, st);
     default: return launch_step_kv<KIND, 1>(e, args, st);
   }
+  (void)e;
 }
 
 // Launches the step (or rollout) kernel for the envs [c0, c0 + cn) of the handle (c0 a multiple of the
@@ -442,6 +444,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
 extern "C" RMV_API int rmv_step(rmv_env* env, const float* act_dev, int act_layout, int64_t act_ld, float* reward_dev,
                         uint8_t* done_dev, float* obs_aos_dev, int auto_reset, void* stream) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(reward_dev != nullptr && done_dev != nullptr, "reward_dev and done_dev must not be NULL");
   RMV_ON_DEVICE(env->device);
   return launch_step(env, act_dev, act_layout, act_ld, 0, reward_dev, done_dev, env->n, obs_aos_dev, auto_reset, 1,
                      static_cast<cudaStream_t>(stream));
@@ -456,10 +459,14 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t stride = (act_layout == RMV_ACT_SOA) ? (int64_t)env->A * act_ld : env->n * env->A;
   if (fused) return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st);
+  if (!reward_dev || !done_dev) {                 // the single-step kernel always writes both: park them in scratch
+    int rc = ensure_staging(env);
+    if (rc) return rc;
+  }
   for (int t = 0; t < n_steps; ++t) {
     int rc = launch_step(env, act_dev + (int64_t)t * stride, act_layout, act_ld, 0,
-                         reward_dev ? reward_dev + (int64_t)t * out_ld : nullptr,
-                         done_dev ? done_dev + (int64_t)t * out_ld : nullptr, out_ld, nullptr, 1, 1, st);
+                         reward_dev ? reward_dev + (int64_t)t * out_ld : env->h_rew,
+                         done_dev ? done_dev + (int64_t)t * out_ld : env->h_done, out_ld, nullptr, 1, 1, st);
     if (rc) return rc;
   }
   return RMV_OK;

@@ -184,35 +184,41 @@ __device__ __forceinline__ float on_done(const StepArgs& a, int64_t e, float n_r
 // ---- the fused single-step kernel ------------------------------------------------------------
 // dynamics + done + reward + reset-on-done (+ optional episode bookkeeping, + optional
 // row-per-env observation copy) for n envs: the reference's step() and the caller's reset-on-done
-// in ONE launch.
-template <int KIND, int V, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_step(const StepArgs a) {
+// in ONE launch.  128 threads per CTA, V envs per thread; indices are 32-bit (n < 2^31 per launch,
+// enforced by the host), the only 64-bit arithmetic is the one base pointer per thread.
+//
+// Reset-on-done without serialising warps: an env that finished gets its terminal reward and its
+// `episode` word updated by its owner thread, which then just raises a bit in a per-warp ballot.  After
+// the single __syncthreads of the kernel the CTA's finished envs (1-2 per CTA under a random policy) are
+// re-drawn cooperatively, ONE (env, Philox block) PAIR PER THREAD, straight into the state tile.  The
+// inline alternative makes every warp that contains a finished env (a third of all warps) run the
+// 3 x 10 Philox rounds of a quadrotor3d reset with one lane active.
+constexpr int kBlock = 128;
+constexpr int kWarps = kBlock / 32;
+
+template <int KIND, int V, bool OBS, bool TRACK>
+__global__ void __launch_bounds__(kBlock) k_step(const StepArgs a) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   constexpr int NB = (S + 3) / 4;                  // Philox blocks per reset
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;     // odd row pitch: conflict-free transposes
-  constexpr int kMaxList = BLOCK * V;
-  __shared__ uint32_t list_env[kMaxList];          // envs of this CTA to re-draw (index relative to the CTA)
-  __shared__ uint32_t list_episode[kMaxList];
-  __shared__ uint32_t list_len;
-  extern __shared__ float tile[];                  // [warps][32][SP], only when a.obs != nullptr
+  __shared__ uint32_t redraw_mask[V][kWarps];      // bit l of [v][w]: env (w*32+l)*V+v of this CTA is re-drawn
+  extern __shared__ float tile[];                  // [warps][32][SP], only when OBS
 
-  const uint32_t tid = threadIdx.x;
-  const int64_t cta_e0 = (int64_t)blockIdx.x * (BLOCK * V);
-  const int64_t e0 = cta_e0 + (int64_t)tid * V;
-  const bool active = e0 < a.n;
-  const bool full = e0 + V <= a.n;
-  if (tid == 0) list_len = 0u;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t n = (uint32_t)a.n;
+  const uint32_t cta_e0 = blockIdx.x * (uint32_t)(kBlock * V);
+  const uint32_t e0 = cta_e0 + tid * V;
+  const bool active = e0 < n;
+  const bool full = e0 + V <= n;
 
   // thread's base pointer into the tiled state: rows of the tile are at constant offsets c*kTile
-  float* const sp = a.state + ((e0 >> 7) * (int64_t)(S * kTile) + (e0 & (kTile - 1)));
+  float* const sp = a.state + ((size_t)(e0 >> 7) * (S * kTile) + (e0 & (kTile - 1)));
   float s[V][S];
   float ep_ret[V];
-  float rew[V];
-  uint8_t dn[V];
   bool redraw[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) redraw[v] = false;
-  __syncthreads();                                 // list_len = 0 visible
+
   if (active) {
 #pragma unroll
     for (int c = 0; c < S; ++c) {
@@ -221,10 +227,12 @@ __global__ void __launch_bounds__(BLOCK) k_step(const StepArgs a) {
 #pragma unroll
       for (int v = 0; v < V; ++v) s[v][c] = t[v];
     }
-    if (a.ep_return) load_v<V, false>(a.ep_return + e0, ep_ret);
+    if (TRACK) load_v<V, false>(a.ep_return + e0, ep_ret);
     float act[V][A];
-    load_actions<KIND, V>(a, a.act, e0, full, act);
+    load_actions<KIND, V>(a, a.act, (int64_t)e0, full, act);
 
+    float rew[V];
+    uint8_t dn[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       float pos_sq, vel_sq, n_rew;
@@ -232,24 +240,41 @@ __global__ void __launch_bounds__(BLOCK) k_step(const StepArgs a) {
       const bool done = is_done(a.P, pos_sq, vel_sq);
       float r = -n_rew;
       dn[v] = done ? 1 : 0;
-      redraw[v] = false;
-      const int64_t e = e0 + v;
-      if (done && e < a.n) {
-        uint32_t count;
-        r = on_done(a, e, n_rew, a.ep_return ? ep_ret[v] : 0.0f, a.step_index + 1u, count);
-        if (a.ep_return) ep_ret[v] = -r;          // becomes 0 after the "+= r" below
-        if (a.auto_reset) {
-          const uint32_t slot = atomicAdd(&list_len, 1u);
-          list_env[slot] = tid * V + v;
-          list_episode[slot] = count;
-          redraw[v] = true;
+      const uint32_t e = e0 + v;
+      if (done && e < n) {
+        // rare lane: the ever-done flag decides the terminal reward (quadrotor3d.py:112-122)
+        const uint32_t word = a.episode[e];
+        r = reward_of(a.P, true, (word & kEverDone) != 0u, n_rew);
+        a.episode[e] = ((word & ~kEverDone) + (a.auto_reset ? 1u : 0u)) | kEverDone;
+        redraw[v] = a.auto_reset != 0;
+        if (TRACK) {
+          const float total = ep_ret[v] + r;
+          const uint32_t now = a.step_index + 1u;
+          const uint32_t len = now - a.ep_start[e];
+          a.last_return[e] = total;
+          a.last_length[e] = len;
+          a.cum_return[e] += (double)total;
+          a.cum_length[e] += len;
+          a.fin_count[e] += 1u;
+          a.ep_start[e] = now;
+          ep_ret[v] = -r;                          // becomes 0 after the "+= r" below
         }
       }
       rew[v] = r;
-      if (a.ep_return) ep_ret[v] += r;
+      if (TRACK) ep_ret[v] += r;
     }
-    store_outputs<V>(a, e0, e0, full, rew, dn);
-    // a done env's new state comes from the work list below, everything else is stored here
+    if (full) {
+      store_v<V, true>(a.reward + e0, rew);
+      store_done<V>(a.done + e0, dn);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (e0 + v < n) {
+          __stcs(a.reward + e0 + v, rew[v]);
+          __stcs(reinterpret_cast<unsigned char*>(a.done) + e0 + v, (unsigned char)dn[v]);
+        }
+    }
+    // a re-drawn env's new state is written after the barrier; everything else is stored here
     bool any_redraw = false;
 #pragma unroll
     for (int v = 0; v < V; ++v) any_redraw |= redraw[v];
@@ -269,51 +294,71 @@ __global__ void __launch_bounds__(BLOCK) k_step(const StepArgs a) {
           for (int c = 0; c < S; ++c) sp[c * kTile + v] = s[v][c];
         }
     }
-    if (a.ep_return) store_v<V, false>(a.ep_return + e0, ep_ret);
+    if (TRACK) store_v<V, false>(a.ep_return + e0, ep_ret);
   }
 
-  if (a.obs) {
+  uint32_t my_mask[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    my_mask[v] = __ballot_sync(0xffffffffu, redraw[v]);
+    if (lane == 0) redraw_mask[v][warp] = my_mask[v];
+  }
+
+  if (OBS) {
     // row-per-env observation copy [n][S]: transpose through a per-warp shared tile so that each
     // store instruction writes runs of S contiguous floats instead of 32 scattered words.
-    // Rows of re-drawn envs are written by the work-list pass instead.
-    const int lane = tid & 31, warp = tid >> 5;
+    // Rows of re-drawn envs are written by the re-draw pass instead.
     float* my = tile + warp * 32 * SP;
-    const int64_t warp_e0 = e0 - (int64_t)lane * V;
-    uint32_t skip = 0u;                            // bit r: row r of this pass belongs to a re-drawn env
+    const uint32_t warp_e0 = e0 - lane * V;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < S; ++c) my[lane * SP + c] = s[v][c];
-      skip = __ballot_sync(0xffffffffu, active && redraw[v]);
       __syncwarp();
 #pragma unroll
       for (int i = lane; i < 32 * S; i += 32) {
         const int r = i / S, c = i - r * S;
-        const int64_t e = warp_e0 + (int64_t)r * V + v;
-        if (e < a.n && !((skip >> r) & 1u)) __stcs(a.obs + e * S + c, my[r * SP + c]);
+        const uint32_t e = warp_e0 + (uint32_t)r * V + v;
+        if (e < n && !((my_mask[v] >> r) & 1u)) __stcs(a.obs + (size_t)e * S + c, my[r * SP + c]);
       }
     }
   }
 
-  // ---- re-draw the done envs of this CTA: one (env, Philox block) pair per thread -------------
+  // ---- re-draw the finished envs of this CTA: one (env, Philox block) pair per thread ------------
   __syncthreads();
-  const uint32_t pairs = list_len * NB;
-  for (uint32_t i = tid; i < pairs; i += BLOCK) {
-    const uint32_t slot = i / NB, b = i - slot * NB;
-    const int64_t e = cta_e0 + list_env[slot];
-    const uint64_t id = (uint64_t)(a.env_id_offset + e);
-    uint32_t w[4];
-    philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), list_episode[slot],
-                  ((STREAM_RESET_BASE + (uint32_t)KIND) << 8) | b, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
-    float* const row = a.state + ((e >> 7) * (int64_t)(S * kTile) + (e & (kTile - 1)));
+  uint32_t total = 0;
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) total += __popc(redraw_mask[v][w]);
+  for (uint32_t i = tid; i < total * NB; i += kBlock) {
+    uint32_t slot = i / NB;
+    const uint32_t b = i - slot * NB;
+    uint32_t rel = 0;                              // index of the slot-th flagged env inside the CTA
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        const uint32_t m = redraw_mask[v][w];
+        const uint32_t c = __popc(m);
+        if (slot < c) { rel = ((uint32_t)w * 32u + __fns(m, 0, slot + 1)) * V + v; slot = 0xffffffffu; }
+        else if (slot != 0xffffffffu) slot -= c;
+      }
+    const uint32_t e = cta_e0 + rel;
+    const uint32_t episode = a.episode[e] & ~kEverDone;      // written by the owner before the barrier
+    const uint64_t id = (uint64_t)a.env_id_offset + e;
+    uint32_t w4[4];
+    philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), episode, ((STREAM_RESET_BASE + (uint32_t)KIND) << 8) | b,
+                  (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w4);
+    float* const row = a.state + ((size_t)(e >> 7) * (S * kTile) + (e & (kTile - 1)));
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       const int c = 4 * (int)b + l;
       if (c < S) {
-        const float x = uniform_from_bits(w[l], -1.0f, 2.0f);
+        const float x = uniform_from_bits(w4[l], -1.0f, 2.0f);
         row[c * kTile] = x;
-        if (a.obs) a.obs[e * S + c] = x;
+        if (OBS) a.obs[(size_t)e * S + c] = x;
       }
     }
   }

@@ -107,7 +107,7 @@ class QuadBatch:
         self.seed = int(seed)
         check(lib().rmv_set_seed(self._h, self.seed & 0xFFFFFFFFFFFFFFFF))
 
-    def set_tuning(self, vec=0, block=256):
+    def set_tuning(self, vec=0, block=128):
         check(lib().rmv_set_tuning(self._h, int(vec), int(block)))
 
     def set_host_chunks(self, chunks=0):

@@ -62,7 +62,7 @@ def main():
     ap.add_argument("--envs", default="quadrotor3d-v0")
     ap.add_argument("--n", default="1048576")
     ap.add_argument("--vec", default="1,2,4")
-    ap.add_argument("--block", default="128,256")
+    ap.add_argument("--block", default="128")
     ap.add_argument("--layout", default="soa,aos")
     ap.add_argument("--fused", default="0")
     ap.add_argument("--steps", type=int, default=200)
