@@ -260,6 +260,8 @@ extern "C" RMV_API int rmv_state_ptr(rmv_env* env, float** state_dev, uint32_t**
   return RMV_OK;
 }
 
+static int g_use_pdl = (getenv("RMV_NO_PDL") == nullptr) ? 1 : 0;
+
 static inline unsigned blocks_for(int64_t n, int64_t block) { return (unsigned)((n + block - 1) / block); }
 
 // ------------------------------------------------------------------------------------------
@@ -363,8 +365,17 @@ static cudaError_t launch_step_kvf(const StepArgs& args, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;
   const size_t smem = OBS ? (size_t)kWarps * 32 * SP * sizeof(float) : 0;
-  k_step<KIND, V, OBS, TRACK><<<blocks_for(args.n, (int64_t)kBlock * V), kBlock, smem, st>>>(args);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks_for(args.n, (int64_t)kBlock * V));
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this launch's ramp with the previous grid's tail
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_step<KIND, V, OBS, TRACK>, args);
 }
 
 template <int KIND, int V>

@@ -204,6 +204,9 @@ __global__ void __launch_bounds__(kBlock) k_step(const StepArgs a) {
   __shared__ uint32_t redraw_mask[V][kWarps];      // bit l of [v][w]: env (w*32+l)*V+v of this CTA is re-drawn
   extern __shared__ float tile[];                  // [warps][32][SP], only when OBS
 
+  // Programmatic dependent launch: let the NEXT launch in the stream become resident while this grid
+  // drains, and do not touch global memory before the PREVIOUS grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t n = (uint32_t)a.n;
   const uint32_t cta_e0 = blockIdx.x * (uint32_t)(kBlock * V);
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(kBlock) k_step(const StepArgs a) {
   bool redraw[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) redraw[v] = false;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (active) {
 #pragma unroll
