@@ -14,6 +14,12 @@ from ._capi import LIB_PATH, RmvError  # noqa: F401
 from .batch import ENV_IDS, QuadBatch, fill_uniform_actions  # noqa: F401
 from .vec_env import QuadVecEnv, SparseInfos  # noqa: F401
 
+
+def RolloutBuffer(*args, **kwargs):
+    """On-device PPO2-shaped rollout buffers (imports torch lazily)."""
+    from .rollout import RolloutBuffer as _RB
+    return _RB(*args, **kwargs)
+
 __version__ = "0.1.0"
 
 ENTRY_POINTS = {

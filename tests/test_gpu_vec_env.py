@@ -233,3 +233,26 @@ def test_pipelined_host_step_equals_single_shot(rmv):
         assert same_bits(ref[0], other[0]) and np.array_equal(ref[2], other[2]) and ref[3] == other[3]
         for (r0, d0), (r1, d1) in zip(ref[1], other[1]):
             assert same_bits(r0, r1) and np.array_equal(d0, d1)
+
+
+def test_ppo2_shaped_rollout_buffers(rmv):
+    """BASELINE config 4 shape: quadrotor2d-v0, obs [N,5] -> actions [N,2] ~ N(0,1) (baselines' initial
+    diagonal Gaussian) -> step, T steps written straight into [T, N, ...] device buffers."""
+    import torch
+    n, T, seed = 8192, 96, 12
+    venv = rmv.QuadVecEnv("quadrotor2d-v0", n, seed=seed, monitor=False)
+    buf = rmv.RolloutBuffer(venv, T)
+    gen = torch.Generator(device="cuda:0").manual_seed(0)
+    buf.collect(lambda obs: torch.randn((n, 2), generator=gen, device="cuda:0"))
+    o = BatchOracle("quadrotor2d-v0", n, seed=seed, dtype=np.float32)
+    assert same_bits(buf.obs[0].cpu().numpy(), o.reset())
+    acts = buf.actions.cpu().numpy()
+    for t in range(T):
+        obs_ref, rew_ref, done_ref = o.step(acts[t])
+        assert same_bits(buf.obs[t + 1].cpu().numpy(), obs_ref), t
+        assert same_bits(buf.rewards[t].cpu().numpy(), rew_ref), t
+        assert np.array_equal(buf.dones[t].cpu().numpy().astype(bool), done_ref), t
+    assert int(buf.dones.sum()) > 50
+    buf.roll()
+    assert torch.equal(buf.obs[0], buf.obs[T])
+    venv.close()
