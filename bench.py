@@ -345,6 +345,31 @@ def measure_extras(torch, rmv, args, local):
                      "mode": "one launch per %d steps, state in registers" % ring if fused else "one launch per step"}
         b.close()
         del acts, rew, done
+
+    # BASELINE config 4: quadrotor2d-v0, N = 2^20, PPO2 rollout shape — obs rows [N,5] out, actions [N,2]
+    # ~ N(0,1) in (baselines' initial diagonal Gaussian), T = 128 steps into [T, N, ...] device buffers
+    import gym_reinmav_b200.rollout as rollout
+    n, T = 1 << 20, 128
+    venv = rmv.QuadVecEnv("quadrotor2d-v0", n, device=local, seed=SEED, monitor=False)
+    buf = rollout.RolloutBuffer(venv, T)
+    buf.actions.normal_()
+    policy = lambda obs, _it=iter(range(10 ** 9)): buf.actions[next(_it) % T]      # pre-drawn actions: env-side cost only
+    buf.collect(policy)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); buf.collect(policy); e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / T)
+    sps = n / (best * 1e-3)
+    bytes_with_obs = 53 + 4 * 5
+    out["ppo2_rollout_shape_quadrotor2d"] = {
+        "env_id": "quadrotor2d-v0", "n_envs": n, "n_steps": T, "us_per_step": best * 1e3, "env_steps_per_s": sps,
+        "bytes_per_env_step": bytes_with_obs, "algorithmic_GBps": sps * bytes_with_obs / 1e9,
+        "frac_of_hbm_peak": sps * bytes_with_obs / 1e9 / peak,
+        "mode": "one launch per step from Python (ctypes), obs rows written into obs[t+1] of a [T+1,N,5] buffer"}
+    venv.close()
     return out
 
 
