@@ -9,7 +9,18 @@ for p in (ROOT, os.path.join(ROOT, "reinmav-gym_b200")):
         sys.path.insert(0, p)
 
 
+def _ensure_library():
+    """librmv.so is a build artefact (git-ignored).  Build it when a fresh checkout has none, so that the
+    C-ABI tests never silently run against nothing."""
+    lib = os.path.join(ROOT, "reinmav-gym_b200", "gym_reinmav_b200", "lib", "librmv.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "reinmav-gym_b200", "csrc")],
+                              stdout=subprocess.DEVNULL)
+
+
 def pytest_configure(config):
+    _ensure_library()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
 

@@ -327,3 +327,82 @@ def test_full_size_properties_quadrotor3d_2pow20(torch, rmv):
     rows = s1.permute(0, 2, 1).reshape(n, S)             # tiles [n/128, S, 128] -> rows [n, S]
     assert (rows[last].abs() <= 1).all()
     assert torch.isfinite(s1).all()
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("n", [1, 2, 31, 127, 128, 129, 255, 257, 1025])
+def test_ragged_sizes_all_variants(torch, rmv, n):
+    """Tile / warp / vector-width boundaries: every kind, every V, obs rows on, auto-reset on."""
+    for env_id in ENV_IDS:
+        kind = KIND_OF_ID[env_id]
+        S, A = STATE_DIM[kind], ACTION_DIM[kind]
+        for vec in (1, 2, 4):
+            rng = np.random.RandomState(n + vec)
+            o = BatchOracle(kind, n, seed=n, dtype=np.float32)
+            b = rmv.QuadBatch(env_id, n, seed=n)
+            b.set_tuning(vec=vec)
+            b.reset()
+            o.reset()
+            rew, done, obs = _buffers(torch, n, S)
+            s0 = wide_states(kind, max(n, 8), rng)[:n]
+            b.set_state(s0)
+            o.state = s0.T.copy()
+            for t in range(6):
+                a = random_actions(kind, (n,), rng)
+                b.step(torch.as_tensor(a, device="cuda:0"), rew, done, obs=obs)
+                obs_ref, rew_ref, done_ref = o.step(a)
+                assert np.array_equal(done.cpu().numpy().astype(bool), done_ref), (env_id, vec, t)
+                assert same_bits(rew.cpu().numpy(), rew_ref) and same_bits(obs.cpu().numpy(), obs_ref), (env_id, vec, t)
+            assert same_bits(b.get_state(), o.obs())
+            b.close()
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_non_finite_and_extreme_inputs(torch, rmv, env_id):
+    """NaN / inf / huge actions and states: NaN norms are 'not done' (strict '>' on the norm, as the
+    reference's comparisons), infinities are done; the kernel and the float32 model agree bit for bit."""
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    n = 512
+    rng = np.random.RandomState(9)
+    s0 = wide_states(kind, n, rng)
+    a = random_actions(kind, (n,), rng)
+    specials = np.array([np.nan, np.inf, -np.inf, 1e38, -1e38, 1e-40, -0.0, 3e5, -7e9], np.float32)
+    for i in range(n):
+        if i % 3 == 0:
+            a[i, rng.randint(A)] = specials[rng.randint(len(specials))]
+        if i % 5 == 0:
+            s0[i, rng.randint(S)] = specials[rng.randint(len(specials))]
+    s0[7] = 0.0                                            # zero quaternion / zero tether vector
+    o = BatchOracle(kind, n, dtype=np.float32)
+    o.state = s0.T.copy()
+    obs_ref, rew_ref, done_ref = o.step(a, auto_reset=False)
+    b = rmv.QuadBatch(env_id, n)
+    b.set_state(s0)
+    rew, done, obs = _buffers(torch, n, S)
+    b.step(torch.as_tensor(a, device="cuda:0"), rew, done, obs=obs, auto_reset=False)
+    got, r, d = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy().astype(bool)
+    assert np.array_equal(d, done_ref)
+    both_nan = np.isnan(got) & np.isnan(obs_ref)
+    assert ((got.view(np.uint32) == obs_ref.view(np.uint32)) | both_nan).all()
+    rn = np.isnan(r) & np.isnan(rew_ref)
+    assert ((r.view(np.uint32) == rew_ref.view(np.uint32)) | rn).all()
+    assert np.isnan(got).any() and done_ref.any() and not done_ref[np.isnan(rew_ref)].any()
+    b.close()
+
+
+def test_deterministic_and_seed_sensitive(torch, rmv):
+    def run(seed):
+        b = rmv.QuadBatch("quadrotor3d-slungload-v0", 5000, seed=seed)
+        b.reset()
+        act = torch.empty((5000, 4), device="cuda:0")
+        rew = torch.empty(5000, device="cuda:0")
+        done = torch.empty(5000, dtype=torch.uint8, device="cuda:0")
+        for t in range(120):
+            rmv.fill_uniform_actions(act, 5000, 4, -10, 10, 3, step_index=t)
+            b.step(act, rew, done)
+        out = b.get_state()
+        b.close()
+        return out
+    a, b_, c = run(1), run(1), run(2)
+    assert same_bits(a, b_) and not np.array_equal(a, c)
