@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(kBlock) k_step(const StepArgs a) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   constexpr int NB = (S + 3) / 4;                  // Philox blocks per reset
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;     // odd row pitch: conflict-free transposes
-  __shared__ uint32_t redraw_mask[V][kWarps];      // bit l of [v][w]: env (w*32+l)*V+v of this CTA is re-drawn
+  __shared__ uint32_t redraw_count[V][kWarps];     // finished envs per (v, warp) ...
+  __shared__ uint8_t redraw_lane[V][kWarps][32];   // ... and their lanes, compacted by a ballot prefix
   extern __shared__ float tile[];                  // [warps][32][SP], only when OBS
 
   // Programmatic dependent launch: let the NEXT launch in the stream become resident while this grid
@@ -305,7 +306,8 @@ __global__ void __launch_bounds__(kBlock) k_step(const StepArgs a) {
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     my_mask[v] = __ballot_sync(0xffffffffu, redraw[v]);
-    if (lane == 0) redraw_mask[v][warp] = my_mask[v];
+    if (lane == 0) redraw_count[v][warp] = __popc(my_mask[v]);
+    if (redraw[v]) redraw_lane[v][warp][__popc(my_mask[v] & ((1u << lane) - 1u))] = (uint8_t)lane;
   }
 
   if (OBS) {
@@ -331,23 +333,23 @@ __global__ void __launch_bounds__(kBlock) k_step(const StepArgs a) {
 
   // ---- re-draw the finished envs of this CTA: one (env, Philox block) pair per thread ------------
   __syncthreads();
-  uint32_t total = 0;
+  uint32_t count[V * kWarps], total = 0;
 #pragma unroll
   for (int v = 0; v < V; ++v)
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) total += __popc(redraw_mask[v][w]);
+    for (int w = 0; w < kWarps; ++w) { count[v * kWarps + w] = redraw_count[v][w]; total += count[v * kWarps + w]; }
   for (uint32_t i = tid; i < total * NB; i += kBlock) {
     uint32_t slot = i / NB;
     const uint32_t b = i - slot * NB;
-    uint32_t rel = 0;                              // index of the slot-th flagged env inside the CTA
+    uint32_t rel = 0;                              // index of the slot-th finished env inside the CTA
+    bool found = false;
 #pragma unroll
     for (int v = 0; v < V; ++v)
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) {
-        const uint32_t m = redraw_mask[v][w];
-        const uint32_t c = __popc(m);
-        if (slot < c) { rel = ((uint32_t)w * 32u + __fns(m, 0, slot + 1)) * V + v; slot = 0xffffffffu; }
-        else if (slot != 0xffffffffu) slot -= c;
+        const uint32_t c = count[v * kWarps + w];
+        if (!found && slot < c) { rel = ((uint32_t)w * 32u + redraw_lane[v][w][slot]) * V + v; found = true; }
+        if (!found) slot -= c;
       }
     const uint32_t e = cta_e0 + rel;
     const uint32_t episode = a.episode[e] & ~kEverDone;      // written by the owner before the barrier

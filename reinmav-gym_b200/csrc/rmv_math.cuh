@@ -14,6 +14,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define RMV_HD __host__ __device__ __forceinline__
@@ -160,6 +161,21 @@ RMV_HD void reset_draws(uint64_t seed, uint64_t env_id, uint32_t episode, float 
 // ------------------------------------------------------------------------------------------
 // sin / cos in float32 with a pinned sequence (mirror of oracle/sincos32.py)
 // ------------------------------------------------------------------------------------------
+RMV_HD uint32_t bits_of(float x) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(x);
+#else
+  uint32_t u; memcpy(&u, &x, 4); return u;
+#endif
+}
+RMV_HD float float_of(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float x; memcpy(&x, &u, 4); return x;
+#endif
+}
+
 RMV_HD void sincos_pinned(float xin, float& s_out, float& c_out) {
   const rf x(xin);
   rf r;
@@ -192,12 +208,15 @@ RMV_HD void sincos_pinned(float xin, float& s_out, float& c_out) {
   t = t * z;
   t = t - rf(0.5f) * z;
   const rf cr = t + rf(1.0f);
-  switch (quad) {
-    case 0: s_out = sr.v; c_out = cr.v; break;
-    case 1: s_out = cr.v; c_out = -sr.v; break;
-    case 2: s_out = -sr.v; c_out = -cr.v; break;
-    default: s_out = -cr.v; c_out = sr.v; break;
-  }
+  // quadrant fix-up without branches: odd quadrants swap sin/cos, the sign bits follow the quadrant
+  //   q:      0    1    2    3
+  //   sin:   sr   cr  -sr  -cr
+  //   cos:   cr  -sr  -cr   sr
+  const bool swap = (quad & 1) != 0;
+  const uint32_t sb = swap ? bits_of(cr.v) : bits_of(sr.v);
+  const uint32_t cb = swap ? bits_of(sr.v) : bits_of(cr.v);
+  s_out = float_of(sb ^ (((uint32_t)quad & 2u) << 30));
+  c_out = float_of(cb ^ ((((uint32_t)quad + 1u) & 2u) << 30));
 }
 
 // ------------------------------------------------------------------------------------------
