@@ -121,6 +121,10 @@ RMV_API int rmv_set_seed(rmv_env* env, uint64_t seed);
 /* Launch tuning (benchmarks / sweeps): vec = envs per thread (0 = auto, 1, 2, 4),
  * block = threads per CTA (multiple of 32, <= 256). */
 RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block);
+/* step-kernel variant: use_tma != 0 selects the persistent TMA-bulk-copy / mbarrier-pipelined kernel
+ * (V = 1, row-per-env actions) where it applies, 0 the register-path kernel; ctas_per_sm caps the
+ * persistent grid (0 = as many as fit).  Results are identical. */
+RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm);
 /* number of chunks rmv_step_host pipelines a batch through (H2D | kernel | D2H overlap); 0 = auto
  * (8 for n >= 65536, else 1) */
 RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks);

@@ -13,6 +13,7 @@
 #include "rmv.h"
 #include "rmv_kernels.cuh"
 #include "rmv_control.cuh"
+#include "rmv_step_tma.cuh"
 
 using namespace rmv;
 
@@ -95,7 +96,8 @@ struct rmv_env {
   // tuning
   int vec = 0;     // 0 = auto
   int block = 128;
-  int force_rollout = 0;   // tests: run the multi-step kernel even for one step
+  int use_tma = 0;         // 1: TMA-pipelined persistent step kernel where it applies
+  int tma_ctas_per_sm = 0; // 0 = as many as fit
 };
 
 static const int kS[RMV_NUM_KINDS] = {5, 9, 10, 16};
@@ -245,6 +247,14 @@ extern "C" RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks) {
   return RMV_OK;
 }
 
+extern "C" RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 32, "ctas_per_sm must be in [0, 32]");
+  env->use_tma = use_tma ? 1 : 0;
+  env->tma_ctas_per_sm = ctas_per_sm;
+  return RMV_OK;
+}
+
 extern "C" RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
   RMV_REQUIRE(vec == 0 || vec == 1 || vec == 2 || vec == 4, "vec must be 0 (auto), 1, 2 or 4");
@@ -261,6 +271,8 @@ extern "C" RMV_API int rmv_state_ptr(rmv_env* env, float** state_dev, uint32_t**
 }
 
 static int g_use_pdl = (getenv("RMV_NO_PDL") == nullptr) ? 1 : 0;
+
+static inline bool aligned(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 static inline unsigned blocks_for(int64_t n, int64_t block) { return (unsigned)((n + block - 1) / block); }
 
@@ -358,8 +370,6 @@ extern "C" RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* o
 // ------------------------------------------------------------------------------------------
 // step
 // ------------------------------------------------------------------------------------------
-static inline bool aligned(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
-
 template <int KIND, int V, bool OBS, bool TRACK>
 static cudaError_t launch_step_kvf(const StepArgs& args, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
@@ -378,6 +388,46 @@ static cudaError_t launch_step_kvf(const StepArgs& args, cudaStream_t st) {
   return cudaLaunchKernelEx(&cfg, k_step<KIND, V, OBS, TRACK>, args);
 }
 
+// TMA-pipelined persistent variant (V = 1, row-per-env actions, 16-byte aligned action buffer)
+constexpr int kTmaStages = 3;
+template <int KIND, bool OBS, bool TRACK>
+static cudaError_t launch_step_tma(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
+  constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
+  constexpr int SP = (S % 2 == 0) ? S + 1 : S;
+  const size_t smem = (size_t)kTmaStages * (S + A) * kTile * 4 + (OBS ? (size_t)kWarps * 32 * SP * sizeof(float) : 0);
+  static int resident = 0, sms = 0;
+  if (resident == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_step_tma<KIND, OBS, TRACK, kTmaStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_step_tma<KIND, OBS, TRACK, kTmaStages>, kBlock, smem);
+    if (resident < 1) resident = 1;
+    if (sms < 1) sms = 1;
+  }
+  const unsigned tiles = blocks_for(args.n, kTile);
+  int per_sm = e->tma_ctas_per_sm > 0 && e->tma_ctas_per_sm < resident ? e->tma_ctas_per_sm : resident;
+  const unsigned persistent = (unsigned)sms * (unsigned)per_sm;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles < persistent ? tiles : persistent);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_step_tma<KIND, OBS, TRACK, kTmaStages>, args);
+}
+
+template <int KIND>
+static cudaError_t launch_step_tma_k(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
+  const bool track = args.ep_return != nullptr;
+  if (args.obs) return track ? launch_step_tma<KIND, true, true>(e, args, st) : launch_step_tma<KIND, true, false>(e, args, st);
+  return track ? launch_step_tma<KIND, false, true>(e, args, st) : launch_step_tma<KIND, false, false>(e, args, st);
+}
+
 template <int KIND, int V>
 static cudaError_t launch_step_kv(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
   if (args.n_steps > 1) {
@@ -392,6 +442,8 @@ static cudaError_t launch_step_kv(const rmv_env* e, const StepArgs& args, cudaSt
 
 template <int KIND>
 static cudaError_t launch_step_k(const rmv_env* e, const StepArgs& args, int vec, cudaStream_t st) {
+  if (e->use_tma && vec == 1 && args.n_steps == 1 && !args.act_soa && aligned(args.act, 16))
+    return launch_step_tma_k<KIND>(e, args, st);
   switch (vec) {
     case 4: return launch_step_kv<KIND, 4>(e, args, st);
     case 2: return launch_step_kv<KIND, 2>(e, args, st);

@@ -110,6 +110,10 @@ class QuadBatch:
     def set_tuning(self, vec=0, block=128):
         check(lib().rmv_set_tuning(self._h, int(vec), int(block)))
 
+    def set_kernel(self, tma=False, ctas_per_sm=0):
+        """Pick the step-kernel variant (register path / TMA-pipelined persistent); results are identical."""
+        check(lib().rmv_set_kernel(self._h, 1 if tma else 0, int(ctas_per_sm)))
+
     def set_host_chunks(self, chunks=0):
         check(lib().rmv_set_host_chunks(self._h, int(chunks)))
 

@@ -106,13 +106,14 @@ def test_single_step_bitwise(torch, rmv, env_id, vec, layout):
 
 
 # ------------------------------------------------------------------------------------------ rollouts vs T1 (bit-exact)
-def _rollout_bitwise(torch, rmv, env_id, n, steps, vec, seed, check_state_every):
+def _rollout_bitwise(torch, rmv, env_id, n, steps, vec, seed, check_state_every, tma=False, track=False):
     kind = KIND_OF_ID[env_id]
     S, A = STATE_DIM[kind], ACTION_DIM[kind]
     lo, hi = ACTION_BOUNDS[kind]
     off = 5 * n
-    b = rmv.QuadBatch(env_id, n, seed=seed, env_id_offset=off)
+    b = rmv.QuadBatch(env_id, n, seed=seed, env_id_offset=off, track_episodes=track)
     b.set_tuning(vec=vec)
+    b.set_kernel(tma=tma)
     o = BatchOracle(kind, n, seed=seed, env_id_offset=off, dtype=np.float32)
     b.reset()
     o.reset()
@@ -136,6 +137,8 @@ def _rollout_bitwise(torch, rmv, env_id, n, steps, vec, seed, check_state_every)
                 assert same_bits(obs.cpu().numpy(), o.obs()), "obs rows, step %d" % t
     words = b.get_episode_words()
     assert np.array_equal(words & 0x7FFFFFFF, o.episode) and np.array_equal((words >> 31).astype(bool), o.ever_done)
+    if track:
+        assert b.episode_stats()["episodes"] == n_done
     b.close()
     return n_done
 
@@ -160,6 +163,14 @@ def test_planar_rollouts_bitwise(torch, rmv, env_id):
 @pytest.mark.parametrize("env_id", ENV_IDS)
 def test_small_ragged_rollouts_bitwise(torch, rmv, env_id, vec):
     _rollout_bitwise(torch, rmv, env_id, 1000 + 1, 200, vec=vec, seed=3, check_state_every=50)
+
+
+@pytest.mark.parametrize("n,track", [(1000 + 1, False), (127, True), (128 * 700 + 5, True), (65536, False)])
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_tma_pipelined_kernel_bitwise(torch, rmv, env_id, n, track):
+    """The persistent TMA-bulk / mbarrier-pipelined variant of the step kernel: same bits as the float32
+    model, with more tiles than resident CTAs (pipeline wrap-around), ragged last tiles, obs rows, tracking."""
+    _rollout_bitwise(torch, rmv, env_id, n, 200, vec=1, seed=4, check_state_every=50, tma=True, track=track)
 
 
 # ------------------------------------------------------------------------------------------ vs float64 reference arithmetic

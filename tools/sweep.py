@@ -15,10 +15,11 @@ BOUNDS = {"quadrotor2d-v0": (-10, 10), "quadrotor2d-slungload-v0": (-10, 10), "q
           "quadrotor3d-slungload-v0": (-10, 10)}
 
 
-def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak):
+def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, ctas=0):
     dev = "cuda:0"
     b = rmv.QuadBatch(env_id, n, seed=0)
     b.set_tuning(vec=vec, block=block)
+    b.set_kernel(tma=bool(tma), ctas_per_sm=ctas)
     b.reset()
     A = b.action_dim
     lo, hi = BOUNDS[env_id]
@@ -68,6 +69,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--ring", type=int, default=16)
     ap.add_argument("--peak", type=float, default=6546.2)
+    ap.add_argument("--tma", default="0", help="comma list of 0/1: register-path / TMA-pipelined kernel")
+    ap.add_argument("--ctas", default="0", help="comma list: persistent CTAs per SM for the TMA kernel (0 = max)")
     args = ap.parse_args()
     print("%-26s %9s %3s %5s %4s %5s %9s %11s %9s %6s" % ("env", "n", "vec", "block", "lay", "fused", "us/step", "steps/s", "GB/s(alg)", "frac"))
     for env_id in args.envs.split(","):
@@ -77,8 +80,10 @@ def main():
                     for vec in (int(x) for x in args.vec.split(",")):
                         for block in (int(x) for x in args.block.split(",")):
                             ring = max(2, min(args.ring, int(6e9 // (n * 4 * 6))))
-                            us, sps, gbs, frac = time_cfg(env_id, n, vec, block, layout, bool(fused), args.steps, ring, args.peak)
-                            print("%-26s %9d %3d %5d %4s %5d %9.2f %11.4g %9.1f %6.3f" % (env_id, n, vec, block, layout, fused, us, sps, gbs, frac), flush=True)
+                            for tma in (int(x) for x in args.tma.split(",")):
+                                for ctas in (int(x) for x in args.ctas.split(",")) if tma else (0,):
+                                    us, sps, gbs, frac = time_cfg(env_id, n, vec, block, layout, bool(fused), args.steps, ring, args.peak, tma, ctas)
+                                    print("%-26s %9d %3d %5d %4s %5d %9.2f %11.4g %9.1f %6.3f  tma=%d ctas=%d" % (env_id, n, vec, block, layout, fused, us, sps, gbs, frac, tma, ctas), flush=True)
 
 
 if __name__ == "__main__":
