@@ -51,7 +51,11 @@ enum {
   RMV_QUAD2D_SLUNG = 1,  /* quadrotor2d-slungload-v0  envs/native/quadrotor2d_slungload.py  */
   RMV_QUAD3D = 2,        /* quadrotor3d-v0            envs/native/quadrotor3d.py            */
   RMV_QUAD3D_SLUNG = 3,  /* quadrotor3d-slungload-v0  envs/native/quadrotor3d_slungload.py  */
-  RMV_NUM_KINDS = 4
+  RMV_REINMAV = 4,       /* reinmav-v0                envs/native/reinmav_env.py: closed-loop
+                            13-state rigid body [x y z vx vy vz qw qx qy qz p q r], NO action (action_dim 0,
+                            act_dev may be NULL), reward 90 and done 1 every step, reset() keeps the state
+                            (reinmav_env.py:99-126,348-351); rmv_params is not used by this kind */
+  RMV_NUM_KINDS = 5
 };
 
 enum {
@@ -117,6 +121,11 @@ RMV_API int rmv_dims(const rmv_env* env, int* state_dim, int* action_dim, int64_
 RMV_API int rmv_get_params(const rmv_env* env, rmv_params* out);
 /* seed(): re-key the reset stream (Quadrotor3D.seed, quadrotor3d.py:77-79).  State is untouched. */
 RMV_API int rmv_set_seed(rmv_env* env, uint64_t seed);
+
+/* reinmav-v0 only: the simulation clock `self.t` (reinmav_env.py:73,119), advanced by dt = 0.01 per step;
+ * the trajectory generator and the substep grid depend on it. */
+RMV_API int rmv_get_time(const rmv_env* env, double* t);
+RMV_API int rmv_set_time(rmv_env* env, double t);
 
 /* Launch tuning (benchmarks / sweeps): vec = envs per thread (0 = auto, 1, 2, 4),
  * block = threads per CTA (multiple of 32, <= 256). */

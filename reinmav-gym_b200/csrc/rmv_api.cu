@@ -14,6 +14,7 @@
 #include "rmv_kernels.cuh"
 #include "rmv_control.cuh"
 #include "rmv_step_tma.cuh"
+#include "rmv_reinmav.cuh"
 
 using namespace rmv;
 
@@ -69,6 +70,7 @@ struct rmv_env {
   int64_t n = 0, ld = 0, env_id_offset = 0;
   uint64_t seed = 0;
   uint32_t flags = 0, step_index = 0;
+  double sim_time = 0.0;   // reinmav-v0: self.t (reinmav_env.py:73,119)
   rmv_params params{};
   DevParams dp{};
   float* state = nullptr;
@@ -100,8 +102,15 @@ struct rmv_env {
   int tma_ctas_per_sm = 0; // 0 = as many as fit
 };
 
-static const int kS[RMV_NUM_KINDS] = {5, 9, 10, 16};
-static const int kA[RMV_NUM_KINDS] = {2, 2, 4, 4};
+// developer switch for A/B measurements (tools/sweep.py); the default is the product configuration
+static int g_use_pdl = (getenv("RMV_NO_PDL") == nullptr) ? 1 : 0;
+
+static inline bool aligned(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+static inline unsigned blocks_for(int64_t n, int64_t block) { return (unsigned)((n + block - 1) / block); }
+
+static const int kS[RMV_NUM_KINDS] = {5, 9, 10, 16, 13};
+static const int kA[RMV_NUM_KINDS] = {2, 2, 4, 4, 0};
 
 static DevParams to_dev(const rmv_params& p) {
   DevParams d;
@@ -133,6 +142,7 @@ extern "C" RMV_API int rmv_default_params(int kind, rmv_params* out) {
   if (kind == RMV_QUAD2D) { p.thrust_scale = 10.0f; p.thrust_clamp = 1; }
   if (kind == RMV_QUAD2D_SLUNG) { p.tether_len = 0.5f; p.pos_done = 2.0f; }
   if (kind == RMV_QUAD3D_SLUNG) { p.tether_len = 1.5f; }
+  if (kind == RMV_REINMAV) { p.mass = 0.18f; p.gravity = 9.81f; p.load_mass = 0.0f; }   // informational (reinmav_env.py:55-57)
   *out = p;
   return RMV_OK;
 }
@@ -141,8 +151,8 @@ extern "C" RMV_API int64_t rmv_padded_ld(int64_t n_envs) { return n_envs <= 0 ? 
 
 extern "C" RMV_API int rmv_action_bounds(int kind, float* low, float* high) {
   RMV_REQUIRE(kind >= 0 && kind < RMV_NUM_KINDS, "unknown env kind %d", kind);
-  if (low) *low = (kind == RMV_QUAD3D) ? 0.0f : -10.0f;
-  if (high) *high = 10.0f;
+  if (low) *low = (kind == RMV_QUAD3D || kind == RMV_REINMAV) ? 0.0f : -10.0f;
+  if (high) *high = (kind == RMV_REINMAV) ? 0.0f : 10.0f;
   return RMV_OK;
 }
 
@@ -198,6 +208,10 @@ extern "C" RMV_API int rmv_create(rmv_env** out, int kind, int64_t n_envs, int64
     if (err == cudaSuccess) err = alloc_zero(&e->fin_count, (size_t)e->ld);
     if (err == cudaSuccess) err = alloc_zero(&e->stats_dev, 4);
   }
+  if (err == cudaSuccess && kind == RMV_REINMAV) {
+    k_reinmav_init<<<blocks_for(e->n, 256), 256>>>(e->state, e->n);
+    err = cudaGetLastError();
+  }
   if (err == cudaSuccess) err = cudaDeviceSynchronize();   // memsets done before any user stream touches the buffers
   if (err != cudaSuccess) {
     free_all(e);
@@ -247,6 +261,18 @@ extern "C" RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks) {
   return RMV_OK;
 }
 
+extern "C" RMV_API int rmv_get_time(const rmv_env* env, double* t) {
+  RMV_REQUIRE(env != nullptr && t != nullptr, "NULL argument");
+  *t = env->sim_time;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_set_time(rmv_env* env, double t) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  env->sim_time = t;
+  return RMV_OK;
+}
+
 extern "C" RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
   RMV_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 32, "ctas_per_sm must be in [0, 32]");
@@ -270,17 +296,11 @@ extern "C" RMV_API int rmv_state_ptr(rmv_env* env, float** state_dev, uint32_t**
   return RMV_OK;
 }
 
-static int g_use_pdl = (getenv("RMV_NO_PDL") == nullptr) ? 1 : 0;
-
-static inline bool aligned(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
-
-static inline unsigned blocks_for(int64_t n, int64_t block) { return (unsigned)((n + block - 1) / block); }
-
 // ------------------------------------------------------------------------------------------
 // state in / out
 // ------------------------------------------------------------------------------------------
 static int ensure_staging(rmv_env* e) {
-  if (!e->h_act) RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->h_act), (size_t)e->n * e->A * sizeof(float)));
+  if (!e->h_act) RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->h_act), (size_t)e->n * (e->A > 0 ? e->A : 1) * sizeof(float)));
   if (!e->h_rew) RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->h_rew), (size_t)e->n * sizeof(float)));
   if (!e->h_done) RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->h_done), (size_t)e->n));
   if (!e->h_obs) RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->h_obs), (size_t)e->n * e->S * sizeof(float)));
@@ -357,6 +377,14 @@ extern "C" RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* o
   RMV_REQUIRE(env != nullptr, "env is NULL");
   RMV_ON_DEVICE(env->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (env->kind == RMV_REINMAV) {
+    // ReinmavEnv.reset() returns the CURRENT state and resets nothing (reinmav_env.py:348-351)
+    if (obs_aos_dev) {
+      k_tiles_to_rows<<<blocks_for(env->n, 256), 256, 0, st>>>(env->state, obs_aos_dev, env->n, env->S);
+      RMV_CUDA(cudaGetLastError());
+    }
+    return RMV_OK;
+  }
   switch (env->kind) {
     case RMV_QUAD2D: launch_reset<QUAD2D>(env, mask_dev, obs_aos_dev, st); break;
     case RMV_QUAD2D_SLUNG: launch_reset<QUAD2D_SLUNG>(env, mask_dev, obs_aos_dev, st); break;
@@ -452,12 +480,43 @@ static cudaError_t launch_step_k(const rmv_env* e, const StepArgs& args, int vec
   (void)e;
 }
 
+// inverse of the reference's inertia matrix (reinmav_env.py:60-63), by cofactors in float64
+static void reinmav_inverse_inertia(double out[9]) {
+  const double a = 0.00025, c = 2.55e-06, e = 0.000232, g = 2.55e-06, i = 0.0003738;   // [[a,0,c],[0,e,0],[g,0,i]]
+  const double det = e * (a * i - c * g);
+  out[0] = e * i / det; out[1] = 0.0; out[2] = -c * e / det;
+  out[3] = 0.0; out[4] = (a * i - c * g) / det; out[5] = 0.0;
+  out[6] = -e * g / det; out[7] = 0.0; out[8] = a * e / det;
+}
+
 // Launches the step (or rollout) kernel for the envs [c0, c0 + cn) of the handle (c0 a multiple of the
 // 128-env tile; the whole handle when cn == n).  act / rew / done / obs point at env c0's element.
 static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act_ld, int64_t act_step_stride,
                        float* rew, uint8_t* done, int64_t out_ld, float* obs, int auto_reset, int n_steps,
                        cudaStream_t st, int64_t c0 = 0, int64_t cn = -1, bool advance_clock = true) {
   if (cn < 0) cn = e->n;
+  if (e->kind == RMV_REINMAV) {
+    // no action; n_steps consecutive steps, each np.arange(t, t + dt, 1/5000) substeps (reinmav_env.py:90-98)
+    double t = e->sim_time;
+    for (int k = 0; k < n_steps; ++k) {
+      ReinmavArgs ra;
+      ra.state = e->state + (c0 / kTile) * (int64_t)(e->S * kTile);
+      ra.reward = rew ? rew + (int64_t)k * out_ld : nullptr;
+      ra.done = done ? done + (int64_t)k * out_ld : nullptr;
+      ra.obs = obs; ra.n = cn;
+      volatile double stop = t + 1.0 / 100, next = t + 1.0 / 5000;
+      ra.n_sub = (int)ceil((stop - t) / (1.0 / 5000));     // NumPy's arange length ...
+      ra.delta = next - t;                                  // ... and fill increment
+      ra.t0 = t;
+      reinmav_inverse_inertia(ra.inv_inertia);
+      k_reinmav_step<<<blocks_for(cn, 128), 128, 0, st>>>(ra);
+      cudaError_t err = cudaGetLastError();
+      if (err != cudaSuccess) return fail(RMV_ECUDA, "reinmav step launch failed: %s", cudaGetErrorString(err));
+      t = t + 1.0 / 100;
+    }
+    if (advance_clock) { e->sim_time = t; e->step_index += (uint32_t)n_steps; }
+    return RMV_OK;
+  }
   RMV_REQUIRE(act != nullptr, "act_dev is NULL");
   RMV_REQUIRE(act_layout == RMV_ACT_AOS || act_layout == RMV_ACT_SOA, "bad act_layout %d", act_layout);
   if (act_layout == RMV_ACT_SOA) RMV_REQUIRE(act_ld >= cn, "act_ld (%lld) < n_envs", (long long)act_ld);
@@ -507,7 +566,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
 extern "C" RMV_API int rmv_step(rmv_env* env, const float* act_dev, int act_layout, int64_t act_ld, float* reward_dev,
                         uint8_t* done_dev, float* obs_aos_dev, int auto_reset, void* stream) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
-  RMV_REQUIRE(reward_dev != nullptr && done_dev != nullptr, "reward_dev and done_dev must not be NULL");
+  RMV_REQUIRE(env->kind == RMV_REINMAV || (reward_dev != nullptr && done_dev != nullptr), "reward_dev and done_dev must not be NULL");
   RMV_ON_DEVICE(env->device);
   return launch_step(env, act_dev, act_layout, act_ld, 0, reward_dev, done_dev, env->n, obs_aos_dev, auto_reset, 1,
                      static_cast<cudaStream_t>(stream));
@@ -520,6 +579,8 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
   if (reward_dev || done_dev) RMV_REQUIRE(out_ld >= env->n, "out_ld (%lld) < n_envs", (long long)out_ld);
   RMV_ON_DEVICE(env->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (env->kind == RMV_REINMAV)
+    return launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, reward_dev, done_dev, out_ld, nullptr, 0, n_steps, st);
   const int64_t stride = (act_layout == RMV_ACT_SOA) ? (int64_t)env->A * act_ld : env->n * env->A;
   if (fused) return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st);
   if (!reward_dev || !done_dev) {                 // the single-step kernel always writes both: park them in scratch
@@ -550,7 +611,7 @@ static int ensure_pipe(rmv_env* e) {
 
 extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float* reward_host, uint8_t* done_host,
                              float* obs_host, int auto_reset, void* stream) {
-  RMV_REQUIRE(env != nullptr && act_host != nullptr, "NULL argument");
+  RMV_REQUIRE(env != nullptr && (act_host != nullptr || env->A == 0), "NULL argument");
   RMV_ON_DEVICE(env->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = ensure_staging(env);
@@ -558,10 +619,11 @@ extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float*
   const int64_t n = env->n;
   const int S = env->S, A = env->A;
   int chunks = env->host_chunks > 0 ? env->host_chunks : (n >= (1 << 16) ? 8 : 1);
+  if (env->A == 0) chunks = 1;
   int64_t per = ((n + chunks - 1) / chunks + 1023) / 1024 * 1024;      // whole tiles, aligned for every vector width
   if (per >= n) chunks = 1;
   if (chunks == 1) {
-    RMV_CUDA(cudaMemcpyAsync(env->h_act, act_host, (size_t)n * A * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (A > 0) RMV_CUDA(cudaMemcpyAsync(env->h_act, act_host, (size_t)n * A * sizeof(float), cudaMemcpyHostToDevice, st));
     rc = launch_step(env, env->h_act, RMV_ACT_AOS, 0, 0, env->h_rew, env->h_done, n, obs_host ? env->h_obs : nullptr,
                      auto_reset, 1, st);
     if (rc) return rc;
@@ -616,12 +678,13 @@ extern "C" RMV_API int rmv_reset_host(rmv_env* env, float* obs_host, void* strea
 extern "C" RMV_API int rmv_control(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_dev,
                                    int act_layout, int64_t act_ld, void* stream) {
   RMV_REQUIRE(env != nullptr && act_dev != nullptr, "NULL argument");
+  RMV_REQUIRE(env->kind != RMV_REINMAV, "reinmav-v0 has no action input: its controller runs inside step()");
   RMV_REQUIRE(act_layout == RMV_ACT_AOS || act_layout == RMV_ACT_SOA, "bad act_layout %d", act_layout);
   if (act_layout == RMV_ACT_SOA) RMV_REQUIRE(act_ld >= env->n, "act_ld (%lld) < n_envs", (long long)act_ld);
   RMV_ON_DEVICE(env->device);
   ControlArgs a;
   a.state = env->state; a.act = act_dev; a.n = env->n; a.act_ld = act_ld; a.act_soa = (act_layout == RMV_ACT_SOA);
-  static const float kRef[RMV_NUM_KINDS][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 2.0f}, {0, 0, 1.0f}};
+  static const float kRef[RMV_NUM_KINDS][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 2.0f}, {0, 0, 1.0f}, {0, 0, 0}};
   const int D = (env->kind == RMV_QUAD2D || env->kind == RMV_QUAD2D_SLUNG) ? 2 : 3;
   for (int i = 0; i < 3; ++i) {
     a.ref_pos[i] = (i < D) ? (ref_pos ? ref_pos[i] : kRef[env->kind][i]) : 0.0f;

@@ -1,7 +1,8 @@
 """gym_reinmav_b200 — B200-native batched drop-in for reinmav-gym's native quadrotor envs.
 
 Registered ids (same strings as /root/reference/gym_reinmav/__init__.py:8-26):
-``quadrotor2d-v0``, ``quadrotor2d-slungload-v0``, ``quadrotor3d-v0``, ``quadrotor3d-slungload-v0``.
+``quadrotor2d-v0``, ``quadrotor2d-slungload-v0``, ``quadrotor3d-v0``, ``quadrotor3d-slungload-v0``
+and ``reinmav-v0`` (/root/reference/gym_reinmav/__init__.py:3-6).
 
     import gym_reinmav_b200 as rmv
     env = rmv.make('quadrotor3d-v0')                         # gym.Env view, N = 1
@@ -27,6 +28,7 @@ ENTRY_POINTS = {
     "quadrotor2d-slungload-v0": "gym_reinmav_b200.envs.native:Quadrotor2DSlungload",
     "quadrotor3d-v0": "gym_reinmav_b200.envs.native:Quadrotor3D",
     "quadrotor3d-slungload-v0": "gym_reinmav_b200.envs.native:Quadrotor3DSlungload",
+    "reinmav-v0": "gym_reinmav_b200.envs.native:ReinmavEnv",
 }
 
 

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RMV_LIB", os.path.join(_HERE, "lib", "librmv.so"))
 
-QUAD2D, QUAD2D_SLUNG, QUAD3D, QUAD3D_SLUNG = 0, 1, 2, 3
+QUAD2D, QUAD2D_SLUNG, QUAD3D, QUAD3D_SLUNG, REINMAV = 0, 1, 2, 3, 4
 ACT_AOS, ACT_SOA = 0, 1
 TRACK_EPISODES = 1
 EVER_DONE_BIT = 0x80000000
@@ -51,6 +51,8 @@ SIGNATURES = {
     "rmv_dims": (_i, [_vp, _pi, _pi, _pi64, _pi64]),
     "rmv_get_params": (_i, [_vp, ctypes.POINTER(Params)]),
     "rmv_set_seed": (_i, [_vp, _u64]),
+    "rmv_get_time": (_i, [_vp, ctypes.POINTER(ctypes.c_double)]),
+    "rmv_set_time": (_i, [_vp, ctypes.c_double]),
     "rmv_set_tuning": (_i, [_vp, _i, _i]),
     "rmv_set_host_chunks": (_i, [_vp, _i]),
     "rmv_set_kernel": (_i, [_vp, _i, _i]),

@@ -16,6 +16,7 @@ ENV_IDS = {
     "quadrotor2d-slungload-v0": _capi.QUAD2D_SLUNG,
     "quadrotor3d-v0": _capi.QUAD3D,
     "quadrotor3d-slungload-v0": _capi.QUAD3D_SLUNG,
+    "reinmav-v0": _capi.REINMAV,
 }
 
 
@@ -109,6 +110,17 @@ class QuadBatch:
 
     def set_tuning(self, vec=0, block=128):
         check(lib().rmv_set_tuning(self._h, int(vec), int(block)))
+
+    @property
+    def sim_time(self):
+        """reinmav-v0: the env clock ``t`` (seconds)."""
+        t = ctypes.c_double()
+        check(lib().rmv_get_time(self._h, ctypes.byref(t)))
+        return t.value
+
+    @sim_time.setter
+    def sim_time(self, t):
+        check(lib().rmv_set_time(self._h, float(t)))
 
     def set_kernel(self, tma=False, ctas_per_sm=0):
         """Pick the step-kernel variant (register path / TMA-pipelined persistent); results are identical."""

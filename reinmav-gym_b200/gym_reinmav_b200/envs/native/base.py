@@ -40,6 +40,8 @@ class NativeQuadEnv(_EnvBase):
         p = _capi.default_params(self.KIND)
         self.mass, self.dt = p.mass, p.dt
         planar = self.KIND in (_capi.QUAD2D, _capi.QUAD2D_SLUNG)
+        if self.KIND == _capi.REINMAV:
+            p.gravity = 9.81
         self.g = np.array([0.0, -p.gravity]) if planar else np.array([0.0, 0.0, -p.gravity])
         self.ref_pos = np.array(self.REF_POS, dtype=float)
         self.ref_vel = np.zeros_like(self.ref_pos)
@@ -50,7 +52,7 @@ class NativeQuadEnv(_EnvBase):
         self.viewer = None
         self._seed_value = self._fresh_seed() if seed is None else int(seed)
         self._batch = QuadBatch(self.KIND, 1, device=device, seed=self._seed_value)
-        self._act = np.zeros((1, self._batch.action_dim), dtype=np.float32)
+        self._act = np.zeros((1, max(self._batch.action_dim, 1)), dtype=np.float32)
         self._rew = np.zeros(1, dtype=np.float32)
         self._done = np.zeros(1, dtype=np.uint8)
         self._obs = np.zeros((1, self._batch.state_dim), dtype=np.float32)

@@ -33,6 +33,8 @@ _ACTION_BOX = {_capi.QUAD2D: (-10.0, 10.0), _capi.QUAD2D_SLUNG: (-10.0, 10.0),
 
 def make_spaces(kind):
     s, a = _capi.kind_dims(kind)
+    if kind == _capi.REINMAV:       # the reference leaves both spaces undefined (reinmav_env.py:65-70); no action input
+        return Box(low=-np.inf, high=np.inf, shape=(s,), dtype=np.float32), None
     lo, hi = _ACTION_BOX[kind]
     return (Box(low=-10.0, high=10.0, shape=(s,), dtype=np.float32),
             Box(low=lo, high=hi, shape=(a,), dtype=np.float32))

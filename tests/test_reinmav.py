@@ -1,0 +1,109 @@
+"""reinmav-v0: oracle pinned to the reference's ReinmavEnv (tests/golden/reinmav-v0.npz,
+made by oracle/make_golden_reinmav.py from /root/reference), CUDA path checked against both."""
+import numpy as np
+import pytest
+
+from oracle.reinmav64 import INIT_STATE, ReinmavBatch, substep_times
+from tests.util import GOLDEN
+
+
+@pytest.fixture(scope="module")
+def golden():
+    import os
+    return np.load(os.path.join(GOLDEN, "reinmav-v0.npz"))
+
+
+def test_substep_grid_matches_numpy_arange():
+    t = 0.0
+    lengths = []
+    for _ in range(400):
+        ref = np.arange(t, t + 1 / 100, 1 / 5000)
+        mine = substep_times(t)
+        assert len(mine) == len(ref) and np.array_equal(np.array(mine), ref)
+        lengths.append(len(mine))
+        t = t + 1 / 100
+    assert set(lengths) == {50, 51}                      # the float arange length flips
+
+
+def test_oracle_follows_the_reference(golden):
+    T, E, _ = golden["traj"].shape
+    b = ReinmavBatch(E, state=golden["init"])
+    for t in range(T):
+        s, r, d = b.step()
+        np.testing.assert_allclose(s, golden["traj"][t], rtol=0, atol=1e-11)
+        assert (r == 90.0).all() and d.all()
+    assert np.array_equal(golden["init"][0], INIT_STATE)
+    assert 0.15 < golden["traj"][-1, 0, 0] < 0.18         # env 0 tracks the quintic: x(1.2 s) = 0.163
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_reference_and_oracle(golden):
+    import torch
+    import gym_reinmav_b200 as rmv
+    T, E, _ = golden["traj"].shape
+    b = rmv.QuadBatch("reinmav-v0", E)
+    assert (b.state_dim, b.action_dim) == (13, 0)
+    assert np.array_equal(b.get_state(), np.tile(INIT_STATE.astype(np.float32), (E, 1)))
+    b.set_state(golden["init"].astype(np.float32))
+    o = ReinmavBatch(E, state=golden["init"])
+    rew = torch.empty(E, device="cuda:0")
+    done = torch.empty(E, dtype=torch.uint8, device="cuda:0")
+    obs = torch.empty((E, 13), device="cuda:0")
+    for t in range(T):
+        b.step(None, rew, done, obs=obs)
+        s_ref, _, _ = o.step(round_to_float32=True)
+        got = obs.cpu().numpy().astype(np.float64)
+        # float64 substeps, float32 state between steps: 1e-5 against the reference, 2e-6 against the
+        # oracle with the same storage rule
+        assert np.abs(got - golden["traj"][t]).max() <= 1e-5, t
+        assert np.abs(got - s_ref).max() <= 2e-6, t
+        assert (rew.cpu().numpy() == 90.0).all() and (done.cpu().numpy() == 1).all()
+    assert abs(b.sim_time - T * 0.01) < 1e-12
+    b.close()
+
+
+@pytest.mark.gpu
+def test_reference_test_loop_400_steps():
+    """test/test_reinmav.py:12-25: 400 steps of reinmav-v0 (4 s): x, y, z and yaw reach the reference 1.0."""
+    import gym_reinmav_b200 as rmv
+    env = rmv.make("reinmav-v0")
+    assert env.reset().shape == (13,)
+    o = ReinmavBatch(1)
+    worst = 0.0
+    for i in range(400):
+        s, r, d, info = env.step()
+        so, _, _ = o.step(round_to_float32=True)
+        worst = max(worst, float(np.abs(s - so[0]).max()))
+        assert r == 90.0 and d is True and info == {}
+    assert worst < 1e-5
+    assert np.abs(s[:3] - 1.0).max() < 0.02 and abs(env.t - 4.0) < 1e-9
+    before = env.state.copy()
+    assert np.array_equal(env.reset(), before)            # reset() returns the current state (reinmav_env.py:348-351)
+    with pytest.raises(TypeError):
+        env.control()
+    env.close()
+
+
+@pytest.mark.gpu
+def test_many_envs_and_step_many():
+    import torch
+    import gym_reinmav_b200 as rmv
+    n = 5000
+    rng = np.random.RandomState(0)
+    init = np.tile(INIT_STATE, (n, 1)) + rng.uniform(-1, 1, (n, 13)) * np.array([0.02] * 3 + [0.05] * 3 + [0.01] * 4 + [0.1] * 3)
+    init = init.astype(np.float32)
+    a, b = rmv.QuadBatch("reinmav-v0", n), rmv.QuadBatch("reinmav-v0", n)
+    a.set_state(init)
+    b.set_state(init)
+    rew = torch.empty((10, n), device="cuda:0")
+    done = torch.empty((10, n), dtype=torch.uint8, device="cuda:0")
+    a.step_many(10, None, rew, done, out_ld=n)
+    for t in range(10):
+        b.step(None, rew[0], done[0])
+    assert np.array_equal(a.get_state(), b.get_state())
+    o = ReinmavBatch(n, state=init.astype(np.float64))
+    for t in range(10):
+        s_ref, _, _ = o.step(round_to_float32=True)
+    assert np.abs(a.get_state() - s_ref).max() < 2e-6
+    a.close()
+    b.close()
