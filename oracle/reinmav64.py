@@ -15,7 +15,7 @@ import numpy as np
 ARM, MASS, GRAV = 0.0860, 0.1800, 9.8100          # :55-57
 MIN_F, MAX_F = 0.0, 3.5316                         # :58-59
 INERTIA = np.array([[0.00025, 0.0, 2.55e-06], [0.0, 0.000232, 0.0], [2.55e-06, 0.0, 0.0003738]])   # :60-62
-INV_INERTIA = np.asarray(np.matrix(INERTIA).getI())                                             # :63
+INV_INERTIA = np.linalg.inv(INERTIA)                   # np.matrix.getI() of a square matrix                                           # :63
 DT, DS = 1 / 100, 1 / 5000                         # :74, :91
 INIT_STATE = np.array([0.0] * 6 + [1.0] + [0.0] * 6)                                             # :80
 KP, KD = np.array([10.0, 10.0, 35.0]), np.array([5.0, 5.0, 22.0])                                 # :311-312

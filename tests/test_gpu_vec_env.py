@@ -119,7 +119,7 @@ def test_single_env_view(rmv, env_id):
 
 
 def test_unknown_id_and_registry(rmv):
-    assert sorted(rmv.ENTRY_POINTS) == sorted(KIND_OF_ID)
+    assert sorted(rmv.ENTRY_POINTS) == sorted(list(KIND_OF_ID) + ["reinmav-v0"])      # gym_reinmav/__init__.py:3-26
     with pytest.raises(KeyError):
         rmv.make("quadrotor4d-v0")
     with pytest.raises(KeyError):
