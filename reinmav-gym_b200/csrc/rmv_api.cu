@@ -94,7 +94,6 @@ struct rmv_env {
   cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t pipe_start = nullptr;
   int host_chunks = 0;      // 0 = auto
-  int64_t host_launches = 0;
   // tuning
   int vec = 0;     // 0 = auto
   int block = 128;
@@ -650,7 +649,6 @@ extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float*
     if (done_host) RMV_CUDA(cudaMemcpyAsync(done_host + c0, env->h_done + c0, (size_t)cn, cudaMemcpyDeviceToHost, ps));
   }
   env->step_index += 1u;
-  env->host_launches += k;
   for (int i = 0; i < 3; ++i) {
     RMV_CUDA(cudaEventRecord(env->pipe_done[i], env->pipe[i]));
     RMV_CUDA(cudaStreamWaitEvent(st, env->pipe_done[i], 0));   // later work on the caller's stream sees the new state

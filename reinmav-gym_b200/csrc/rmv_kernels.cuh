@@ -12,10 +12,10 @@
 //   actions  float32 [n][A] (AOS, what a policy emits) or [A][act_ld] (SOA); streaming loads
 //   reward   float32 [n], done uint8 [n]; streaming stores
 //
-// One thread owns V consecutive envs (V = 1, 2 or 4).  The path is HBM-bound (~1.5 flop/B): no
+// One thread owns V consecutive envs (V = 1, 2 or 4; V = 1 is the measured optimum).  ~1.5 flop/B: no
 // tensor cores, no shared-memory reuse.  Shared memory is used for two things only: transposing
-// the optional row-per-env observation copy so its stores coalesce, and the per-CTA work list
-// that lets the rare done envs (~1.3 % of env-steps) be re-drawn by whichever threads are free
+// the optional row-per-env observation copy so its stores coalesce, and the per-warp compacted lists
+// that let the rare finished envs (~1.3 % of env-steps) be re-drawn by whichever threads are free
 // instead of serialising a Philox evaluation inside every warp that contains one.
 #pragma once
 #include <cuda_runtime.h>
@@ -26,13 +26,7 @@
 namespace rmv {
 
 constexpr int kTile = 128;            // envs per state tile
-constexpr int kMaxBlock = 256;
 constexpr uint32_t kEverDone = 0x80000000u;
-
-// element offset of (env e, component c) in the tiled state buffer
-template <int S> __host__ __device__ __forceinline__ int64_t tiled_index(int64_t e, int c) {
-  return (e / kTile) * (int64_t)(S * kTile) + (int64_t)c * kTile + (e % kTile);
-}
 
 struct StepArgs {
   float* state;            // tiled [n_tiles][S][128]
@@ -197,7 +191,7 @@ constexpr int kBlock = 128;
 constexpr int kWarps = kBlock / 32;
 
 template <int KIND, int V, bool OBS, bool TRACK>
-__global__ void __launch_bounds__(kBlock) k_step(const StepArgs a) {
+__global__ void __launch_bounds__(kBlock, (V == 1 && Dims<KIND>::S <= 10 && !OBS && !TRACK) ? 16 : 1) k_step(const StepArgs a) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   constexpr int NB = (S + 3) / 4;                  // Philox blocks per reset
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;     // odd row pitch: conflict-free transposes
