@@ -346,6 +346,26 @@ def measure_extras(torch, rmv, args, local):
         b.close()
         del acts, rew, done
 
+    # reinmav-v0 (closed-loop 13-state body, 50/51 float64 substeps per step, no action)
+    n = 1 << 20
+    b = rmv.QuadBatch("reinmav-v0", n, device=local)
+    rew = torch.empty(n, dtype=torch.float32, device=dev)
+    done = torch.empty(n, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        b.step(None, rew, done)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        b.step(None, rew, done)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    out["reinmav-v0"] = {"env_id": "reinmav-v0", "n_envs": n, "us_per_step": ms * 1e3, "env_steps_per_s": n / (ms * 1e-3),
+                         "euler_substeps_per_s": 50 * n / (ms * 1e-3), "frac_of_hbm_peak": 109 * n / (ms * 1e-3) / 1e9 / peak,
+                         "mode": "one launch per step; float64 substeps in registers (compute-bound, not HBM-bound)"}
+    b.close()
+
     # BASELINE config 4: quadrotor2d-v0, N = 2^20, PPO2 rollout shape — obs rows [N,5] out, actions [N,2]
     # ~ N(0,1) in (baselines' initial diagonal Gaussian), T = 128 steps into [T, N, ...] device buffers
     import gym_reinmav_b200.rollout as rollout

@@ -222,6 +222,11 @@ RMV_API int rmv_fill_uniform_actions(float* act_dev, int64_t n_envs, int action_
 /* out[0] = number of finished episodes, out[1] = sum of their returns, out[2] = sum of their
  * lengths, out[3] = env-steps taken, all since creation.  Synchronises `stream`. */
 RMV_API int rmv_episode_stats(rmv_env* env, double out[4], void* stream);
+/* return / length of the most recently finished episode of the k envs listed in idx_host (host array of env
+ * indices), gathered on the device and copied to the host arrays; synchronises `stream`.  This is how the
+ * VecEnv fills info['episode'] for the envs whose done flag is set, without moving all n entries. */
+RMV_API int rmv_gather_episodes(rmv_env* env, const int64_t* idx_host, int64_t k, float* return_host,
+                                uint32_t* length_host, void* stream);
 /* per-env return / length of the most recently finished episode, device pointers [ld] */
 RMV_API int rmv_episode_ptr(rmv_env* env, float** last_return_dev, uint32_t** last_length_dev);
 

@@ -84,6 +84,10 @@ struct rmv_env {
   unsigned long long* cum_length = nullptr;
   uint32_t* fin_count = nullptr;
   double* stats_dev = nullptr;
+  int64_t* gather_idx = nullptr;   // scratch of rmv_gather_episodes (lazy)
+  float* gather_ret = nullptr;
+  uint32_t* gather_len = nullptr;
+  int64_t gather_cap = 0;
   // staging for the *_host entry points (lazy)
   float* h_act = nullptr;
   float* h_rew = nullptr;
@@ -166,6 +170,7 @@ static void free_all(rmv_env* e) {
   cudaFree(e->state); cudaFree(e->episode); cudaFree(e->ep_return); cudaFree(e->ep_start);
   cudaFree(e->last_return); cudaFree(e->last_length); cudaFree(e->cum_return);
   cudaFree(e->cum_length); cudaFree(e->fin_count); cudaFree(e->stats_dev);
+  cudaFree(e->gather_idx); cudaFree(e->gather_ret); cudaFree(e->gather_len);
   cudaFree(e->h_act); cudaFree(e->h_rew); cudaFree(e->h_done); cudaFree(e->h_obs);
   for (int i = 0; i < 3; ++i) {
     if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]);
@@ -744,6 +749,36 @@ extern "C" RMV_API int rmv_episode_stats(rmv_env* env, double out[4], void* stre
   RMV_CUDA(cudaMemcpyAsync(out, env->stats_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   RMV_CUDA(cudaStreamSynchronize(st));
   out[3] = (double)env->step_index * (double)env->n;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_gather_episodes(rmv_env* env, const int64_t* idx_host, int64_t k, float* return_host,
+                                           uint32_t* length_host, void* stream) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(env->flags & RMV_TRACK_EPISODES, "handle was created without RMV_TRACK_EPISODES");
+  RMV_REQUIRE(k >= 0 && k <= env->n, "k out of range");
+  if (k == 0) return RMV_OK;
+  RMV_REQUIRE(idx_host != nullptr && return_host != nullptr && length_host != nullptr, "NULL argument");
+  for (int64_t i = 0; i < k; ++i) RMV_REQUIRE(idx_host[i] >= 0 && idx_host[i] < env->n, "env index %lld out of range", (long long)idx_host[i]);
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (env->gather_cap < k) {
+    cudaFree(env->gather_idx); cudaFree(env->gather_ret); cudaFree(env->gather_len);
+    env->gather_idx = nullptr; env->gather_ret = nullptr; env->gather_len = nullptr; env->gather_cap = 0;
+    int64_t cap = 1024;
+    while (cap < k) cap *= 2;
+    RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&env->gather_idx), (size_t)cap * sizeof(int64_t)));
+    RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&env->gather_ret), (size_t)cap * sizeof(float)));
+    RMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&env->gather_len), (size_t)cap * sizeof(uint32_t)));
+    env->gather_cap = cap;
+  }
+  RMV_CUDA(cudaMemcpyAsync(env->gather_idx, idx_host, (size_t)k * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  k_gather_episodes<<<blocks_for(k, 256), 256, 0, st>>>(env->last_return, env->last_length, env->gather_idx, k,
+                                                        env->gather_ret, env->gather_len);
+  RMV_CUDA(cudaGetLastError());
+  RMV_CUDA(cudaMemcpyAsync(return_host, env->gather_ret, (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  RMV_CUDA(cudaMemcpyAsync(length_host, env->gather_len, (size_t)k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  RMV_CUDA(cudaStreamSynchronize(st));
   return RMV_OK;
 }
 

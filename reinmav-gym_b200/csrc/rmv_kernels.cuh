@@ -480,6 +480,15 @@ __global__ void k_fill_uniform(float* act, int64_t n, int A, int soa, int64_t ac
   }
 }
 
+// ---- gather of per-env episode info for a list of env indices ------------------------------------
+__global__ void k_gather_episodes(const float* last_return, const uint32_t* last_length, const int64_t* idx, int64_t k,
+                                  float* out_return, uint32_t* out_length) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  out_return[i] = last_return[idx[i]];
+  out_length[i] = last_length[idx[i]];
+}
+
 // ---- episode statistics: sums over envs ---------------------------------------------------------
 __global__ void k_episode_stats(const uint32_t* fin_count, const double* cum_return,
                                 const unsigned long long* cum_length, int64_t n, double* out3) {

@@ -70,6 +70,7 @@ SIGNATURES = {
     "rmv_control_host": (_i, [_vp, _pf, _pf, _vp, _vp]),
     "rmv_fill_uniform_actions": (_i, [_vp, _i64, _i, _i, _i64, _f, _f, _u64, _i64, _u32, _i, _vp]),
     "rmv_episode_stats": (_i, [_vp, ctypes.POINTER(ctypes.c_double), _vp]),
+    "rmv_gather_episodes": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "rmv_episode_ptr": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "rmv_host_alloc": (_i, [ctypes.POINTER(_vp), ctypes.c_size_t]),
     "rmv_host_free": (_i, [_vp]),

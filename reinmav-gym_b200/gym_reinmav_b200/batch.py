@@ -207,6 +207,15 @@ class QuadBatch:
         check(lib().rmv_episode_stats(self._h, out, _stream(stream, self.device)))
         return {"episodes": out[0], "return_sum": out[1], "length_sum": out[2], "env_steps": out[3]}
 
+    def gather_episodes(self, env_indices, stream=None):
+        """(returns float32[k], lengths uint32[k]) of the most recently finished episode of the listed envs."""
+        idx = np.ascontiguousarray(env_indices, dtype=np.int64)
+        ret = np.empty(idx.shape[0], dtype=np.float32)
+        length = np.empty(idx.shape[0], dtype=np.uint32)
+        check(lib().rmv_gather_episodes(self._h, idx.ctypes.data, idx.shape[0], ret.ctypes.data, length.ctypes.data,
+                                        _stream(stream, self.device)))
+        return ret, length
+
     def last_episode_views(self):
         rp, lp = ctypes.c_void_p(), ctypes.c_void_p()
         check(lib().rmv_episode_ptr(self._h, ctypes.byref(rp), ctypes.byref(lp)))

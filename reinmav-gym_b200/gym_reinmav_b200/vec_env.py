@@ -144,12 +144,7 @@ class QuadVecEnv:
         idx = np.flatnonzero(done)
         if idx.size == 0:
             return {}
-        import torch
-        rv, lv = self.batch.last_episode_views()
-        dev = "cuda:%d" % self.device
-        sel = torch.as_tensor(idx, device=dev)
-        r = torch.as_tensor(rv, device=dev)[sel].cpu().numpy()
-        l = torch.as_tensor(lv, device=dev).view(torch.int32)[sel].cpu().numpy()
+        r, l = self.batch.gather_episodes(idx)
         return {int(i): {"episode": {"r": float(r[k]), "l": int(l[k])}} for k, i in enumerate(idx)}
 
     # ------------------------------------------------------------------ device-resident stepping
