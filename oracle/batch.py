@@ -8,8 +8,11 @@ One code path, two arithmetic types:
   float64 NumPy on 2-/3-vectors).  Pinned to the reference's own source by
   tests/golden/*.npz (made by oracle/make_golden.py from /root/reference).
 * ``dtype=np.float32``  -> tier T1: the same formulas, same left-to-right
-  evaluation order, every operation rounded to float32, no FMA; sin/cos from
-  oracle/sincos32.py.  The CUDA path must match T1 bit for bit.
+  evaluation order, rounded to float32; the ``acc + x*y`` steps the kernel
+  issues as one FFMA go through ``_fma`` (an exact float32 fma, oracle/fma32.py;
+  in float64 mode ``_fma`` is the plain two-rounding ``x*y + acc`` of the
+  reference); sin/cos from oracle/sincos32.py.  The CUDA path must match T1
+  bit for bit.
 
 All paths below are relative to /root/reference/gym_reinmav/envs/native/.
 
@@ -22,6 +25,7 @@ stream (replaces the MT19937 stream of quadrotor3d.py:77-79,184).
 import numpy as np
 
 from . import philox
+from .fma32 import fma32
 from .sincos32 import sincos32
 
 QUAD2D, QUAD2D_SLUNG, QUAD3D, QUAD3D_SLUNG = 0, 1, 2, 3
@@ -106,25 +110,47 @@ class BatchOracle:
         m = self._c(self.p["mass"])
         return x / m if self.dtype is np.float64 else x * (self._c(1.0) / m)
 
-    def _norm(self, comps):
+    def _fma(self, x, y, acc):
+        """``x*y + acc``: two roundings in float64 (what NumPy does for the reference), ONE in float32."""
+        if self.dtype is np.float64:
+            return x * y + acc
+        return fma32(x, y, acc)
+
+    def _sumsq(self, comps):
         acc = comps[0] * comps[0]
         for c in comps[1:]:
-            acc = acc + c * c
-        return np.sqrt(acc)
+            acc = self._fma(c, c, acc)
+        return acc
+
+    def _norm(self, comps):
+        return np.sqrt(self._sumsq(comps))
+
+    def _advance(self, x, v, a, velocity_first):
+        """``x + v*dt + 0.5*a*dt*dt`` and ``v + a*dt`` (quadrotor3d.py:98-99; velocity first in
+        quadrotor2d_slungload.py:100-101)."""
+        dt, half = self._c(self.p["dt"]), self._c(0.5)
+        if velocity_first:
+            v2 = [self._fma(a[i], dt, v[i]) for i in range(len(x))]
+            x2 = [self._fma(half * a[i] * dt, dt, self._fma(v2[i], dt, x[i])) for i in range(len(x))]
+        else:
+            x2 = [self._fma(half * a[i] * dt, dt, self._fma(v[i], dt, x[i])) for i in range(len(x))]
+            v2 = [self._fma(a[i], dt, v[i]) for i in range(len(x))]
+        return x2, v2
 
     def _thrust_axis_3d(self, q):
         """pyquaternion ``Quaternion(att).rotation_matrix.dot([0,0,1])``
         (quadrotor3d.py:94-96): normalise in place unless |1-q.q| < 1e-14, then
         column 3 of (Q Qbar^T)[1:,1:].  Returns (unit quaternion, R e3)."""
         w, x, y, z = q
-        n2 = ((w * w + x * x) + y * y) + z * z
+        f = self._fma
+        n2 = f(z, z, f(y, y, f(x, x, w * w)))
         n = np.sqrt(n2)
         need = ~(np.abs(self._c(1.0) - n2) < self._c(1e-14)) & (n > 0)
         safe = np.where(need, n, self._c(1.0))
         w, x, y, z = (np.where(need, c, q0) for c, q0 in zip(self._over((w, x, y, z), safe), (w, x, y, z)))
-        rx = ((x * z + w * y) + z * x) + y * w
-        ry = ((y * z + z * y) - w * x) - x * w
-        rz = ((z * z - y * y) - x * x) + w * w
+        rx = f(y, w, f(z, x, f(w, y, x * z)))
+        ry = f(-x, w, f(-w, x, f(z, y, y * z)))
+        rz = f(w, w, f(-x, x, f(-y, y, z * z)))
         return (w, x, y, z), (rx, ry, rz)
 
     def _qdot(self, qh, om):
@@ -133,10 +159,11 @@ class BatchOracle:
         h = self._c(0.5)
         w, x, y, z = (h * c for c in qh)
         ox, oy, oz = om
-        return ((-x * ox - y * oy) - z * oz,
-                (w * ox - z * oy) + y * oz,
-                (z * ox + w * oy) - x * oz,
-                (-y * ox + x * oy) + w * oz)
+        f = self._fma
+        return (f(-z, oz, f(-y, oy, (-x) * ox)),
+                f(y, oz, f(-z, oy, w * ox)),
+                f(-x, oz, f(w, oy, z * ox)),
+                f(w, oz, f(x, oy, (-y) * ox)))
 
     def _thrust(self, a0):
         """``thrust = 10.0 * action[0]; if thrust < 0: thrust = 0`` (quadrotor2d.py:75-77);
@@ -171,11 +198,44 @@ class BatchOracle:
             margin = nt - L
         else:
             d = [lp[i].astype(np.float64) - pos[i].astype(np.float64) for i in range(len(pos))]
-            margin = self._norm(d) - np.float64(np.float32(L))
+            sq = d[0] * d[0]
+            for di in d[1:]:
+                sq = sq + di * di                      # float64, individually rounded, as the kernel's rd ops
+            margin = np.sqrt(sq) - np.float64(np.float32(L))
         self.tether_margin = margin
         if self.taut_override is not None:
             return np.asarray(self.taut_override, dtype=bool)
         return margin >= 0
+
+    def _taut_branch(self, D, velocity_first, T, tm, axis, u, pos, vel, lp, lv, g):
+        """Taut-tether dynamics + kinematic constraint (quadrotor3d_slungload.py:104-128,
+        quadrotor2d_slungload.py:96-116).  Returns the unconstrained load / quad updates are folded in:
+        (lp', lv', p', v', lp'', lv'')."""
+        p, f = self.p, self._fma
+        m, ml, L = self._c(p["mass"]), self._c(p["load_mass"]), self._c(p["tether_len"])
+        thr = [T * axis[i] for i in range(D)]
+        c = m * L * self._sumsq(lv)                         # SCALAR, broadcast-subtracted from every component (:110)
+        inner = u[0] * (thr[0] - c)
+        for i in range(1, D):
+            inner = f(u[i], thr[i] - c, inner)
+        inv = self._c(1.0) / (m + ml)
+        la = [f(inv, inner * u[i], g[i]) for i in range(D)]
+        lp_t, lv_t = self._advance(lp, lv, la, velocity_first)
+        tn = ml * self._norm([-g[i] + la[i] for i in range(D)])          # the (x + g) - g rounding of :111,115
+        inv_m = self._c(1.0) / m if self.dtype is not np.float64 else None
+        if self.dtype is np.float64:
+            acc = [f(tm, axis[i], g[i]) + (tn * u[i]) / m for i in range(D)]
+        else:
+            acc = [f(tn * u[i], inv_m, f(tm, axis[i], g[i])) for i in range(D)]
+        p_t, v_t = self._advance(pos, vel, acc, velocity_first)
+        dv = [lp_t[i] - p_t[i] for i in range(D)]
+        d = self._over(dv, self._norm(dv))
+        rel = (lv_t[0] - v_t[0]) * d[0]
+        for i in range(1, D):
+            rel = f(lv_t[i] - v_t[i], d[i], rel)
+        lp_c = [f(d[i], L, p_t[i]) for i in range(D)]
+        lv_c = [f(-rel, d[i], lv_t[i]) for i in range(D)]
+        return lp_t, lv_t, p_t, v_t, lp_c, lv_c
 
     # ------------------------------------------------------------------ the four steps
     def _step_quad3d(self, s, a):
@@ -187,12 +247,10 @@ class BatchOracle:
         pos, q, vel = s[0:3], s[3:7], s[7:10]
         qh, e3 = self._thrust_axis_3d(q)
         tm = self._per_mass(T)
-        acc = [tm * e3[i] + g[i] for i in range(3)]
-        half = self._c(0.5)
-        pos2 = [pos[i] + vel[i] * dt + half * acc[i] * dt * dt for i in range(3)]
-        vel2 = [vel[i] + acc[i] * dt for i in range(3)]
+        acc = [self._fma(tm, e3[i], g[i]) for i in range(3)]
+        pos2, vel2 = self._advance(pos, vel, acc, False)
         qd = self._qdot(qh, om)
-        q2 = [q[i] + qd[i] * dt for i in range(4)]
+        q2 = [self._fma(qd[i], dt, q[i]) for i in range(4)]
         new = pos2 + q2 + vel2
         return new, self._norm(pos2), self._norm(vel2), self._norm(pos2)
 
@@ -210,33 +268,13 @@ class BatchOracle:
         taut = self._taut(pos, lp, nt)
         qh, e3 = self._thrust_axis_3d(q)
         qd = self._qdot(qh, om)
-        q2 = [q[i] + qd[i] * dt for i in range(4)]
+        q2 = [self._fma(qd[i], dt, q[i]) for i in range(4)]
         tm = self._per_mass(T)
-        # --- taut (:104-128)
-        thr = [T * e3[i] for i in range(3)]
-        c = m * L * ((lv[0] * lv[0] + lv[1] * lv[1]) + lv[2] * lv[2])          # scalar, broadcast-subtracted (:110)
-        inner = (u[0] * (thr[0] - c) + u[1] * (thr[1] - c)) + u[2] * (thr[2] - c)
-        inv = self._c(1.0) / (m + ml)
-        la = [inv * (inner * u[i]) + g[i] for i in range(3)]
-        lp_t = [lp[i] + lv[i] * dt + half * la[i] * dt * dt for i in range(3)]   # old lv (:112)
-        lv_t = [lv[i] + la[i] * dt for i in range(3)]
-        tn = ml * self._norm([-g[i] + la[i] for i in range(3)])
-        ten = [tn * u[i] for i in range(3)]
-        acc_t = [tm * e3[i] + g[i] + self._per_mass(ten[i]) for i in range(3)]
-        p_t = [pos[i] + vel[i] * dt + half * acc_t[i] * dt * dt for i in range(3)]
-        v_t = [vel[i] + acc_t[i] * dt for i in range(3)]
-        dv = [lp_t[i] - p_t[i] for i in range(3)]
-        nd = self._norm(dv)
-        d = self._over(dv, nd)
-        lp_c = [p_t[i] + d[i] * L for i in range(3)]
-        rel = ((lv_t[0] - v_t[0]) * d[0] + (lv_t[1] - v_t[1]) * d[1]) + (lv_t[2] - v_t[2]) * d[2]
-        lv_c = [lv_t[i] - rel * d[i] for i in range(3)]
+        lp_t, lv_t, p_t, v_t, lp_c, lv_c = self._taut_branch(3, False, T, tm, e3, u, pos, vel, lp, lv, g)   # (:104-128)
         # --- slack (:131-145)
-        lp_s = [lp[i] + lv[i] * dt + half * g[i] * dt * dt for i in range(3)]
-        lv_s = [lv[i] + g[i] * dt for i in range(3)]
-        acc_s = [tm * e3[i] + g[i] for i in range(3)]
-        p_s = [pos[i] + vel[i] * dt + half * acc_s[i] * dt * dt for i in range(3)]
-        v_s = [vel[i] + acc_s[i] * dt for i in range(3)]
+        lp_s, lv_s = self._advance(lp, lv, g, False)
+        acc_s = [self._fma(tm, e3[i], g[i]) for i in range(3)]
+        p_s, v_s = self._advance(pos, vel, acc_s, False)
         sel = lambda t_, s_: [np.where(taut, t_[i], s_[i]) for i in range(len(t_))]
         pos2, vel2, lp2, lv2 = sel(p_t, p_s), sel(v_t, v_s), sel(lp_c, lp_s), sel(lv_c, lv_s)
         new = pos2 + q2 + vel2 + lp2 + lv2
@@ -252,10 +290,9 @@ class BatchOracle:
         pos, th, vel = s[0:2], s[2], s[3:5]
         ax = self._planar_axis(th)
         tm = self._per_mass(T)
-        acc = [tm * ax[i] + g[i] for i in range(2)]
-        pos2 = [pos[i] + vel[i] * dt + half * acc[i] * dt * dt for i in range(2)]
-        vel2 = [vel[i] + acc[i] * dt for i in range(2)]
-        th2 = th + om * dt
+        acc = [self._fma(tm, ax[i], g[i]) for i in range(2)]
+        pos2, vel2 = self._advance(pos, vel, acc, False)
+        th2 = self._fma(om, dt, th)
         new = pos2 + [th2] + vel2
         return new, self._norm(pos2), self._norm(vel2), self._norm(pos2)
 
@@ -273,32 +310,13 @@ class BatchOracle:
         taut = self._taut(pos, lp, nt)
         ax = self._planar_axis(th)
         tm = self._per_mass(T)
-        th2 = th + om * dt
-        # --- taut (:96-116): velocity first, then position with the NEW velocity
-        thr = [T * ax[i] for i in range(2)]
-        c = m * L * (lv[0] * lv[0] + lv[1] * lv[1])
-        inner = u[0] * (thr[0] - c) + u[1] * (thr[1] - c)
-        inv = self._c(1.0) / (m + ml)
-        la = [inv * (inner * u[i]) + g[i] for i in range(2)]
-        lv_t = [lv[i] + la[i] * dt for i in range(2)]
-        lp_t = [lp[i] + lv_t[i] * dt + half * la[i] * dt * dt for i in range(2)]
-        tn = ml * self._norm([-g[i] + la[i] for i in range(2)])
-        ten = [tn * u[i] for i in range(2)]
-        acc_t = [tm * ax[i] + g[i] + self._per_mass(ten[i]) for i in range(2)]
-        v_t = [vel[i] + acc_t[i] * dt for i in range(2)]
-        p_t = [pos[i] + v_t[i] * dt + half * acc_t[i] * dt * dt for i in range(2)]
-        dv = [lp_t[i] - p_t[i] for i in range(2)]
-        nd = self._norm(dv)
-        d = self._over(dv, nd)
-        lp_c = [p_t[i] + d[i] * L for i in range(2)]
-        rel = (lv_t[0] - v_t[0]) * d[0] + (lv_t[1] - v_t[1]) * d[1]
-        lv_c = [lv_t[i] - rel * d[i] for i in range(2)]
+        th2 = self._fma(om, dt, th)
+        # taut (:96-116): velocity first, then position with the NEW velocity
+        lp_t, lv_t, p_t, v_t, lp_c, lv_c = self._taut_branch(2, True, T, tm, ax, u, pos, vel, lp, lv, g)
         # --- slack (:119-132)
-        lv_s = [lv[i] + g[i] * dt for i in range(2)]
-        lp_s = [lp[i] + lv_s[i] * dt + half * g[i] * dt * dt for i in range(2)]
-        acc_s = [tm * ax[i] + g[i] for i in range(2)]
-        v_s = [vel[i] + acc_s[i] * dt for i in range(2)]
-        p_s = [pos[i] + v_s[i] * dt + half * acc_s[i] * dt * dt for i in range(2)]
+        lp_s, lv_s = self._advance(lp, lv, g, True)
+        acc_s = [self._fma(tm, ax[i], g[i]) for i in range(2)]
+        p_s, v_s = self._advance(pos, vel, acc_s, True)
         sel = lambda t_, s_: [np.where(taut, t_[i], s_[i]) for i in range(len(t_))]
         pos2, vel2, lp2, lv2 = sel(p_t, p_s), sel(v_t, v_s), sel(lp_c, lp_s), sel(lv_c, lv_s)
         new = pos2 + [th2] + vel2 + lp2 + lv2

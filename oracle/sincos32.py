@@ -5,13 +5,16 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  The reference evaluates
 (/root/reference/gym_reinmav/envs/native/quadrotor2d.py:88,
 quadrotor2d_slungload.py:97,108,129).  A float32 CUDA path cannot call the host
 libm, so the float32 model fixes one algorithm that both sides implement with
-individually rounded IEEE operations (no FMA): Cody-Waite reduction by pi/2 in
-three parts followed by the classic single-precision minimax polynomials
-(Cephes sinf/cosf coefficients).  Max error ~1.5 ulp for |x| <= 1e5; larger
+IEEE operations in a fixed order — products, and fused multiply-adds where the
+kernel issues an FFMA (oracle/fma32.py is an exact float32 fma): Cody-Waite
+reduction by pi/2 in three parts followed by the classic single-precision
+minimax polynomials (Cephes sinf/cosf coefficients).  Max error ~1.5 ulp for |x| <= 1e5; larger
 arguments reduce in float64.  csrc/rmv_math.cuh ``rmv_sincos`` is the same
 sequence.
 """
 import numpy as np
+
+from .fma32 import fma32
 
 F = np.float32
 TWO_OVER_PI = F(0.63661977236758134)
@@ -31,7 +34,7 @@ def sincos32(x):
     x = np.asarray(x, dtype=F)
     with np.errstate(invalid="ignore", over="ignore"):
         kf = np.rint(x * TWO_OVER_PI)
-        r = ((x - kf * P1) - kf * P2) - kf * P3
+        r = fma32(-kf, P3, fma32(-kf, P2, fma32(-kf, P1, x)))
         quad = kf.astype(np.int64) & 3 if np.all(np.isfinite(kf)) else \
             np.where(np.isfinite(kf), kf, F(0)).astype(np.int64) & 3
         big = ~(np.abs(x) <= BIG)                 # also catches NaN
@@ -44,20 +47,15 @@ def sincos32(x):
             r = np.where(big, rd.astype(F), r)
             quad = np.where(big, qd, quad)
         z = r * r
-        t = S3 * z
-        t = t + S2
+        t = fma32(S3, z, S2)
+        t = fma32(t, z, S1)
         t = t * z
-        t = t + S1
-        t = t * z
-        t = t * r
-        sr = t + r
-        t = C3 * z
-        t = t + C2
-        t = t * z
-        t = t + C1
+        sr = fma32(t, r, r)
+        t = fma32(C3, z, C2)
+        t = fma32(t, z, C1)
         t = t * z
         t = t * z
-        t = t - F(0.5) * z
+        t = fma32(F(-0.5), z, t)
         cr = t + F(1.0)
     s = np.where(quad == 0, sr, np.where(quad == 1, cr, np.where(quad == 2, -sr, -cr)))
     c = np.where(quad == 0, cr, np.where(quad == 1, -sr, np.where(quad == 2, -cr, sr)))

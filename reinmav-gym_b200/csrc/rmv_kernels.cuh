@@ -191,7 +191,8 @@ constexpr int kBlock = 128;
 constexpr int kWarps = kBlock / 32;
 
 template <int KIND, int V, bool OBS, bool TRACK>
-__global__ void __launch_bounds__(kBlock, V != 1 ? 1 : ((Dims<KIND>::S <= 10 && !OBS && !TRACK) ? 16 : 10)) k_step(const StepArgs a) {
+__global__ void __launch_bounds__(kBlock, V != 1 ? 1 : ((OBS || TRACK || Dims<KIND>::S > 10) ? 10 : (KIND == QUAD2D_SLUNG ? 12 : 16)))
+k_step(const StepArgs a) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   constexpr int NB = (S + 3) / 4;                  // Philox blocks per reset
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;     // odd row pitch: conflict-free transposes

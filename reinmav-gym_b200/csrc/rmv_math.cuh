@@ -2,11 +2,14 @@
 //
 // One env = one set of registers; no memory access in this file.  Every floating-point
 // operation goes through rf / rd below, which map to the individually rounded IEEE
-// intrinsics (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn, ...).  Those are never
-// contracted into FMAs or re-associated, so the evaluation order written here IS the
+// intrinsics (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn, __fmaf_rn ...).  Those are never
+// contracted or re-associated by the compiler, so the evaluation order written here IS the
 // arithmetic: it is the reference's own left-to-right NumPy expression order
-// (gym_reinmav/envs/native/*.py, cited per function) rounded to float32.  tests/ check the
-// kernel against an independent NumPy float32 evaluation of the same expressions bit for bit.
+// (gym_reinmav/envs/native/*.py, cited per function) in float32, with `x*y + acc` steps of that
+// order fused into one FFMA where written as fma(x, y, acc) (one rounding instead of two: fewer
+// instructions AND closer to the float64 reference).  tests/ check the kernel against an
+// independent NumPy float32 evaluation of the same sequence (exact fma emulation,
+// oracle/fma32.py) bit for bit.
 //
 // The file also compiles as plain C++ (tests/host_twin builds it with g++ -ffp-contract=off)
 // so the arithmetic can be checked in a container without a GPU.  That build is test
@@ -47,6 +50,15 @@ RMV_HD rf rsqrt_exact(rf a) { return rf(sqrtf(a.v)); }
 #endif
 RMV_HD rf operator-(rf a) { return rf(-a.v); }
 RMV_HD rf sqrt(rf a) { return rsqrt_exact(a); }
+// a*b + c with ONE rounding (FFMA).  Used exactly where the float32 model (oracle/batch.py `_fma`)
+// uses its exact fma; everything else stays individually rounded.
+RMV_HD rf fma(rf a, rf b, rf c) {
+#if defined(__CUDA_ARCH__)
+  return rf(__fmaf_rn(a.v, b.v, c.v));
+#else
+  return rf(fmaf(a.v, b.v, c.v));
+#endif
+}
 
 struct rd {
   double v;
@@ -182,7 +194,7 @@ RMV_HD void sincos_pinned(float xin, float& s_out, float& c_out) {
   int quad;
   if (fabsf(xin) <= 1.0e5f) {
     const rf kf(rintf((x * rf(0.63661977236758134f)).v));
-    r = ((x - kf * rf(1.5703125f)) - kf * rf(4.837512969970703125e-4f)) - kf * rf(7.54978995489188216e-8f);
+    r = fma(-kf, rf(7.54978995489188216e-8f), fma(-kf, rf(4.837512969970703125e-4f), fma(-kf, rf(1.5703125f), x)));
     quad = ((int)kf.v) & 3;
   } else {  // huge, inf or NaN: reduce in float64 (rare, exact-sequence as well)
     const rd xd((double)xin);
@@ -193,20 +205,15 @@ RMV_HD void sincos_pinned(float xin, float& s_out, float& c_out) {
     quad = (qd.v == qd.v && fabs(qd.v) < 8.0) ? (int)qd.v : 0;
   }
   const rf z = r * r;
-  rf t = rf(-1.9515295891e-4f) * z;
-  t = t + rf(8.3321608736e-3f);
+  rf t = fma(rf(-1.9515295891e-4f), z, rf(8.3321608736e-3f));
+  t = fma(t, z, rf(-1.6666654611e-1f));
   t = t * z;
-  t = t + rf(-1.6666654611e-1f);
-  t = t * z;
-  t = t * r;
-  const rf sr = t + r;
-  t = rf(2.443315711809948e-5f) * z;
-  t = t + rf(-1.388731625493765e-3f);
-  t = t * z;
-  t = t + rf(4.166664568298827e-2f);
+  const rf sr = fma(t, r, r);
+  t = fma(rf(2.443315711809948e-5f), z, rf(-1.388731625493765e-3f));
+  t = fma(t, z, rf(4.166664568298827e-2f));
   t = t * z;
   t = t * z;
-  t = t - rf(0.5f) * z;
+  t = fma(rf(-0.5f), z, t);
   const rf cr = t + rf(1.0f);
   // quadrant fix-up without branches: odd quadrants swap sin/cos, the sign bits follow the quadrant
   //   q:      0    1    2    3
@@ -225,7 +232,7 @@ RMV_HD void sincos_pinned(float xin, float& s_out, float& c_out) {
 template <int D> RMV_HD rf sumsq(const rf (&c)[D]) {
   rf acc = c[0] * c[0];
 #pragma unroll
-  for (int i = 1; i < D; ++i) acc = acc + c[i] * c[i];
+  for (int i = 1; i < D; ++i) acc = fma(c[i], c[i], acc);
   return acc;
 }
 template <int D> RMV_HD rf norm(const rf (&c)[D]) { return sqrt(sumsq<D>(c)); }
@@ -237,12 +244,13 @@ RMV_HD void advance(rf (&x)[D], rf (&v)[D], const rf (&a)[D], rf dt) {
   const rf half(0.5f);
 #pragma unroll
   for (int i = 0; i < D; ++i) {
+    // x + v*dt + ((0.5*a)*dt)*dt, left to right, each "+ product" step fused
     if (VEL_FIRST) {
-      v[i] = v[i] + a[i] * dt;
-      x[i] = x[i] + v[i] * dt + half * a[i] * dt * dt;
+      v[i] = fma(a[i], dt, v[i]);
+      x[i] = fma(half * a[i] * dt, dt, fma(v[i], dt, x[i]));
     } else {
-      x[i] = x[i] + v[i] * dt + half * a[i] * dt * dt;
-      v[i] = v[i] + a[i] * dt;
+      x[i] = fma(half * a[i] * dt, dt, fma(v[i], dt, x[i]));
+      v[i] = fma(a[i], dt, v[i]);
     }
   }
 }
@@ -253,7 +261,7 @@ RMV_HD void advance(rf (&x)[D], rf (&v)[D], const rf (&a)[D], rf dt) {
 // out: e3 = R(q^) e_z, qdot = (0.5 q^) (x) (0, om)
 RMV_HD void attitude_3d(const rf (&q)[4], const rf (&om)[3], rf (&e3)[3], rf (&qdot)[4]) {
   rf w = q[0], x = q[1], y = q[2], z = q[3];
-  const rf n2 = ((w * w + x * x) + y * y) + z * z;
+  const rf n2 = fma(z, z, fma(y, y, fma(x, x, w * w)));
   const rf n = sqrt(n2);
   // pyquaternion skips the division when |1 - q.q| < 1e-14; in float32 that means q.q == 1, where
   // multiplying by 1/sqrt(1) = 1 is exact, so only the n > 0 guard is left.  float32 normalises
@@ -262,15 +270,16 @@ RMV_HD void attitude_3d(const rf (&q)[4], const rf (&om)[3], rf (&e3)[3], rf (&q
     const rf inv = rf(1.0f) / n;
     w = w * inv; x = x * inv; y = y * inv; z = z * inv;
   }
-  e3[0] = ((x * z + w * y) + z * x) + y * w;
-  e3[1] = ((y * z + z * y) - w * x) - x * w;
-  e3[2] = ((z * z - y * y) - x * x) + w * w;
+  // column 3 of (Q Qbar^T)[1:,1:], four-term sums left to right
+  e3[0] = fma(y, w, fma(z, x, fma(w, y, x * z)));
+  e3[1] = fma(-x, w, fma(-w, x, fma(z, y, y * z)));
+  e3[2] = fma(w, w, fma(-x, x, fma(-y, y, z * z)));
   const rf h(0.5f);
   const rf hw = h * w, hx = h * x, hy = h * y, hz = h * z;
-  qdot[0] = ((-hx) * om[0] - hy * om[1]) - hz * om[2];
-  qdot[1] = (hw * om[0] - hz * om[1]) + hy * om[2];
-  qdot[2] = (hz * om[0] + hw * om[1]) - hx * om[2];
-  qdot[3] = ((-hy) * om[0] + hx * om[1]) + hw * om[2];
+  qdot[0] = fma(-hz, om[2], fma(-hy, om[1], (-hx) * om[0]));
+  qdot[1] = fma(hy, om[2], fma(-hz, om[1], hw * om[0]));
+  qdot[2] = fma(-hx, om[2], fma(hw, om[1], hz * om[0]));
+  qdot[3] = fma(hw, om[2], fma(hx, om[1], (-hy) * om[0]));
 }
 
 // [cos(att + pi/2), sin(att + pi/2)] = [-sin att, cos att]  (quadrotor2d.py:88)
@@ -293,7 +302,7 @@ RMV_HD void quad_free(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[D
   const rf tm = T * rf(P.inv_mass);   // T/m with m = 1: exact; general m: reciprocal-multiply
   rf acc[D];
 #pragma unroll
-  for (int i = 0; i < D; ++i) acc[i] = tm * axis[i] + rf(i == D - 1 ? P.neg_gravity : 0.0f);
+  for (int i = 0; i < D; ++i) acc[i] = fma(tm, axis[i], rf(i == D - 1 ? P.neg_gravity : 0.0f));
   advance<D, false>(pos, vel, acc, rf(P.dt));
 }
 
@@ -325,25 +334,23 @@ RMV_HD void quad_slung(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[
     rf u[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) u[i] = tv[i] * inv_nt;
-    rf lv2 = lv[0] * lv[0];
-#pragma unroll
-    for (int i = 1; i < D; ++i) lv2 = lv2 + lv[i] * lv[i];
+    const rf lv2 = sumsq<D>(lv);
     const rf c = m * L * lv2;  // SCALAR, broadcast-subtracted from every component (:110)
     rf inner = u[0] * (T * axis[0] - c);
 #pragma unroll
-    for (int i = 1; i < D; ++i) inner = inner + u[i] * (T * axis[i] - c);
+    for (int i = 1; i < D; ++i) inner = fma(u[i], T * axis[i] - c, inner);
     const rf inv(P.inv_total_mass);
     rf la[D], back[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      la[i] = inv * (inner * u[i]) + g[i];
+      la[i] = fma(inv, inner * u[i], g[i]);
       back[i] = (-g[i]) + la[i];  // the (x + g) - g rounding of :111,115
     }
     advance<D, VEL_FIRST>(lp, lv, la, dt);
     const rf tn = ml * norm<D>(back);
     rf acc[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) acc[i] = tm * axis[i] + g[i] + (tn * u[i]) * rf(P.inv_mass);
+    for (int i = 0; i < D; ++i) acc[i] = fma(tn * u[i], rf(P.inv_mass), fma(tm, axis[i], g[i]));
     advance<D, VEL_FIRST>(pos, vel, acc, dt);
     // kinematic constraint (:126-128)
     rf dv[D];
@@ -355,17 +362,17 @@ RMV_HD void quad_slung(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[
     for (int i = 0; i < D; ++i) dir[i] = dv[i] * inv_nd;
     rf rel = (lv[0] - vel[0]) * dir[0];
 #pragma unroll
-    for (int i = 1; i < D; ++i) rel = rel + (lv[i] - vel[i]) * dir[i];
+    for (int i = 1; i < D; ++i) rel = fma(lv[i] - vel[i], dir[i], rel);
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      lp[i] = pos[i] + dir[i] * L;
-      lv[i] = lv[i] - rel * dir[i];
+      lp[i] = fma(dir[i], L, pos[i]);
+      lv[i] = fma(-rel, dir[i], lv[i]);
     }
   } else {
     advance<D, VEL_FIRST>(lp, lv, g, dt);
     rf acc[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) acc[i] = tm * axis[i] + g[i];
+    for (int i = 0; i < D; ++i) acc[i] = fma(tm, axis[i], g[i]);
     advance<D, VEL_FIRST>(pos, vel, acc, dt);
   }
 }
@@ -388,7 +395,7 @@ template <> struct EnvStep<QUAD3D> {  // quadrotor3d.py:81-113
     quad_free<3>(P, commanded_thrust(P, a[0]), e3, pos, vel);
     const rf dt(P.dt);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s[3 + i] = (q[i] + qdot[i] * dt).v;
+    for (int i = 0; i < 4; ++i) s[3 + i] = fma(qdot[i], dt, q[i]).v;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { s[i] = pos[i].v; s[7 + i] = vel[i].v; }
     const rf p2 = sumsq<3>(pos);
@@ -409,7 +416,7 @@ template <> struct EnvStep<QUAD3D_SLUNG> {  // quadrotor3d_slungload.py:87-156
     quad_slung<3, false>(P, commanded_thrust(P, a[0]), e3, pos, vel, lp, lv);
     const rf dt(P.dt);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s[3 + i] = (q[i] + qdot[i] * dt).v;
+    for (int i = 0; i < 4; ++i) s[3 + i] = fma(qdot[i], dt, q[i]).v;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { s[i] = pos[i].v; s[7 + i] = vel[i].v; s[10 + i] = lp[i].v; s[13 + i] = lv[i].v; }
     const rf l2 = sumsq<3>(lp);
@@ -427,7 +434,7 @@ template <> struct EnvStep<QUAD2D> {  // quadrotor2d.py:74-102
     rf axis[2];
     attitude_2d(th, axis);
     quad_free<2>(P, commanded_thrust(P, a[0]), axis, pos, vel);
-    s[2] = (th + rf(a[1]) * rf(P.dt)).v;
+    s[2] = fma(rf(a[1]), rf(P.dt), th).v;
     s[0] = pos[0].v; s[1] = pos[1].v; s[3] = vel[0].v; s[4] = vel[1].v;
     const rf p2 = sumsq<2>(pos);
     n_pos = p2.v;
@@ -444,7 +451,7 @@ template <> struct EnvStep<QUAD2D_SLUNG> {  // quadrotor2d_slungload.py:79-143
     rf axis[2];
     attitude_2d(th, axis);
     quad_slung<2, true>(P, commanded_thrust(P, a[0]), axis, pos, vel, lp, lv);
-    s[2] = (th + rf(a[1]) * rf(P.dt)).v;
+    s[2] = fma(rf(a[1]), rf(P.dt), th).v;
     s[0] = pos[0].v; s[1] = pos[1].v; s[3] = vel[0].v; s[4] = vel[1].v;
     s[5] = lp[0].v; s[6] = lp[1].v; s[7] = lv[0].v; s[8] = lv[1].v;
     n_pos = sumsq<2>(lp).v;  // done: load position / load velocity (:136-139)

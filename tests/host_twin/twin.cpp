@@ -67,6 +67,10 @@ extern "C" void twin_sincos(long n, const float* x, float* s, float* c) {
   for (long i = 0; i < n; ++i) sincos_pinned(x[i], s[i], c[i]);
 }
 
+extern "C" void twin_fma(long n, const float* a, const float* b, const float* c, float* out) {
+  for (long i = 0; i < n; ++i) out[i] = fma(rf(a[i]), rf(b[i]), rf(c[i])).v;
+}
+
 extern "C" void twin_philox(const unsigned* ctr, const unsigned* key, unsigned* out) {
   philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
 }
