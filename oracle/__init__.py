@@ -16,7 +16,8 @@ Tiers (see DESIGN.md "Oracle"):
 * T0s     ``oracle/scalar.py`` — one-object-per-env float64 port with the
   reference's execution model; the CPU arm of ``bench.py``.
 * T1      ``oracle/f32.py`` — float32 restatement with the kernel's operation
-  order (no FMA); the CUDA path must equal it bit for bit.
+  order (explicit fused multiply-adds emulated exactly, oracle/fma32.py); the CUDA path must
+  equal it bit for bit.
 * Philox  ``oracle/philox.py`` — Philox4x32-10, pinned to the Random123 KATs.
 
 Parity status: the reference's own tests assert nothing, so the

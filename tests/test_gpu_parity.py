@@ -2,7 +2,7 @@
 
 Bars (BASELINE.json north_star):
   * done masks bit-exact, state / reward bit-exact against the float32 model T1
-    (same formulas, same operation order, no FMA) — every kind, every launch variant;
+    (same formulas, same operation order, exact fma where the kernel fuses) — every kind, every launch variant;
   * against the float64 reference arithmetic T0 (pinned to the reference source by
     tests/golden): |x_gpu - x_ref| <= TOL * max(1, |x_ref|), TOL = 1e-5, over 1000 free-running
     steps with identical (seed, action) sequences, done masks identical;
