@@ -281,7 +281,10 @@ def run_gpu_arm(args):
                          "traffic_note": "ncu --set full per launch: cold-cache capture (L2 flushed per replay) / "
                                          "--cache-control none capture of a back-to-back run (42 MB state L2-resident)",
                          "kernel": "rmv::k_step<QUAD3D, vec=%d, block=%d>" % (args.vec, args.block),
-                         "algorithmic_bytes_per_launch": ALG_BYTES * n, "avg_launch_us": ms_per_step * 1e3, "peak_source": peak_src},
+                         "algorithmic_bytes_per_launch": ALG_BYTES * n, "avg_launch_us": ms_per_step * 1e3, "peak_source": peak_src,
+                         "note": "frac > 1 at N=2^20 because the 42 MB state stays L2-resident between steps "
+                                 "(traffic_steady_state << algorithmic bytes); the HBM-bound point of the same kernel is "
+                                 "extras.n23 (847 MB per step)"},
             "cpu_baseline": cpu,
             "extras": extras,
             "result_checksum": checksum,

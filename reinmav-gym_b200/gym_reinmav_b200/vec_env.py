@@ -90,7 +90,11 @@ class QuadVecEnv:
     spec = None
 
     def __init__(self, env_id, num_envs, device=0, seed=0, env_id_offset=0, params=None, monitor=True,
-                 return_obs=True):
+                 return_obs=True, copy_outputs=True):
+        """``copy_outputs=False`` returns views of the pinned staging buffers (valid until the next
+        ``step``/``reset``) instead of fresh arrays — at N = 2^20 the three NumPy copies cost more than the
+        PCIe transfers.  ``action_buffer`` is the pinned input buffer: filling it in place and passing it to
+        ``step`` skips the input copy as well."""
         self.env_id = env_id
         self.batch = QuadBatch(env_id, num_envs, device=device, seed=seed, env_id_offset=env_id_offset,
                                params=params, track_episodes=monitor)
@@ -98,6 +102,7 @@ class QuadVecEnv:
         self.device = device
         self.monitor = monitor
         self.return_obs = return_obs
+        self.copy_outputs = copy_outputs
         self.observation_space, self.action_space = make_spaces(self.batch.kind)
         n, S, A = self.num_envs, self.batch.state_dim, self.batch.action_dim
         self._act = _Pinned((n, A), np.float32)
@@ -114,15 +119,24 @@ class QuadVecEnv:
             self.batch.set_seed(seed)
         return [seed]
 
+    @property
+    def action_buffer(self):
+        """The pinned [N, A] float32 input buffer ``step`` uploads from."""
+        return self._act.array
+
+    def _out(self, a):
+        return a.copy() if self.copy_outputs else a
+
     def reset(self):
         self.batch.reset_host(self._obs.array)
-        return self._obs.array.copy()
+        return self._out(self._obs.array)
 
     def step_async(self, actions):
-        a = np.asarray(actions, dtype=np.float32)
-        if a.shape != self._act.array.shape:
-            raise ValueError("actions must have shape %s, got %s" % (self._act.array.shape, a.shape))
-        self._act.array[...] = a
+        if actions is not self._act.array:
+            a = np.asarray(actions, dtype=np.float32)
+            if a.shape != self._act.array.shape:
+                raise ValueError("actions must have shape %s, got %s" % (self._act.array.shape, a.shape))
+            self._act.array[...] = a
         self._pending = True
 
     def step_wait(self):
@@ -133,8 +147,8 @@ class QuadVecEnv:
                              self._obs.array if self.return_obs else None, auto_reset=True)
         done = self._done.array.astype(bool)
         infos = SparseInfos(self.num_envs, self._finished(done) if self.monitor else {})
-        obs = self._obs.array.copy() if self.return_obs else None
-        return obs, self._rew.array.copy(), done, infos
+        obs = self._out(self._obs.array) if self.return_obs else None
+        return obs, self._out(self._rew.array), done, infos
 
     def step(self, actions):
         self.step_async(actions)

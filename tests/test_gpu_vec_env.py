@@ -256,3 +256,20 @@ def test_ppo2_shaped_rollout_buffers(rmv):
     buf.roll()
     assert torch.equal(buf.obs[0], buf.obs[T])
     venv.close()
+
+
+def test_vec_env_zero_copy_mode(rmv):
+    n = 2048
+    venv = rmv.QuadVecEnv("quadrotor3d-v0", n, seed=1, copy_outputs=False, monitor=False)
+    ref = rmv.QuadVecEnv("quadrotor3d-v0", n, seed=1, monitor=False)
+    o1, o2 = venv.reset(), ref.reset()
+    assert same_bits(o1, o2) and o1 is venv._obs.array
+    rng = np.random.RandomState(0)
+    for t in range(20):
+        a = rng.uniform(0, 10, size=(n, 4)).astype(np.float32)
+        venv.action_buffer[...] = a                         # fill the pinned input buffer in place
+        o1, r1, d1, _ = venv.step(venv.action_buffer)
+        o2, r2, d2, _ = ref.step(a)
+        assert same_bits(o1, o2) and same_bits(r1, r2) and np.array_equal(d1, d2)
+    venv.close()
+    ref.close()
