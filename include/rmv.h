@@ -128,7 +128,7 @@ RMV_API int rmv_get_time(const rmv_env* env, double* t);
 RMV_API int rmv_set_time(rmv_env* env, double t);
 
 /* Launch tuning (benchmarks / sweeps): vec = envs per thread (0 = auto, 1, 2, 4),
- * block = threads per CTA (multiple of 32, <= 256). */
+ * block = threads per CTA of the one-env-per-thread step kernel (0 = auto, 128, 256, 512; vec > 1 always uses 128). */
 RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block);
 /* step-kernel variant: use_tma != 0 selects the persistent TMA-bulk-copy / mbarrier-pipelined kernel
  * (V = 1, row-per-env actions) where it applies, 0 the register-path kernel; ctas_per_sm caps the

@@ -100,7 +100,7 @@ struct rmv_env {
   int host_chunks = 0;      // 0 = auto
   // tuning
   int vec = 0;     // 0 = auto
-  int block = 128;
+  int block = 0;   // 0 = auto (default_block)
   int use_tma = 0;         // 1: TMA-pipelined persistent step kernel where it applies
   int tma_ctas_per_sm = 0; // 0 = as many as fit
 };
@@ -288,7 +288,7 @@ extern "C" RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm
 extern "C" RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
   RMV_REQUIRE(vec == 0 || vec == 1 || vec == 2 || vec == 4, "vec must be 0 (auto), 1, 2 or 4");
-  RMV_REQUIRE(block == 128, "the step kernel is built for 128 threads per CTA");
+  RMV_REQUIRE(block == 0 || block == 128 || block == 256 || block == 512, "block must be 0 (auto), 128, 256 or 512 threads per CTA");
   env->vec = vec; env->block = block;
   return RMV_OK;
 }
@@ -402,14 +402,32 @@ extern "C" RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* o
 // ------------------------------------------------------------------------------------------
 // step
 // ------------------------------------------------------------------------------------------
-template <int KIND, int V, bool OBS, bool TRACK>
+// threads per CTA of the one-env-per-thread step kernel when rmv_set_tuning left it on auto (measured:
+// profiles/)
+static int g_prefetch_override = getenv("RMV_PREFETCH") ? atoi(getenv("RMV_PREFETCH")) : -1;   // developer switch
+static int g_block_override = getenv("RMV_BLOCK") ? atoi(getenv("RMV_BLOCK")) : 0;   // developer switch (tools/sweep.py, parity runs)
+static int default_block(int kind) {
+  if (g_block_override == 128 || g_block_override == 256 || g_block_override == 512) return g_block_override;
+  (void)kind;
+  return 128;
+}
+
+template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF>
 static cudaError_t launch_step_kvf(const StepArgs& args, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;
-  const size_t smem = OBS ? (size_t)kWarps * 32 * SP * sizeof(float) : 0;
+  const size_t smem = OBS ? (size_t)BLOCK * SP * sizeof(float) : 0;     // [warps][32][SP] transpose tiles
+  if (OBS && smem > 48 * 1024) {
+    static bool raised = false;      // per instantiation
+    if (!raised) {
+      cudaError_t e = cudaFuncSetAttribute(k_step<KIND, V, OBS, TRACK, BLOCK, PREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      raised = true;
+    }
+  }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(blocks_for(args.n, (int64_t)kBlock * V));
-  cfg.blockDim = dim3(kBlock);
+  cfg.gridDim = dim3(blocks_for(args.n, (int64_t)BLOCK * V));
+  cfg.blockDim = dim3(BLOCK);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -417,7 +435,7 @@ static cudaError_t launch_step_kvf(const StepArgs& args, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_use_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k_step<KIND, V, OBS, TRACK>, args);
+  return cudaLaunchKernelEx(&cfg, k_step<KIND, V, OBS, TRACK, BLOCK, PREF>, args);
 }
 
 // TMA-pipelined persistent variant (V = 1, row-per-env actions, 16-byte aligned action buffer)
@@ -460,6 +478,13 @@ static cudaError_t launch_step_tma_k(const rmv_env* e, const StepArgs& args, cud
   return track ? launch_step_tma<KIND, false, true>(e, args, st) : launch_step_tma<KIND, false, false>(e, args, st);
 }
 
+template <int KIND, int V, int BLOCK, bool PREF>
+static cudaError_t launch_step_kvb(const StepArgs& args, cudaStream_t st) {
+  const bool track = args.ep_return != nullptr;
+  if (args.obs) return track ? launch_step_kvf<KIND, V, true, true, BLOCK, PREF>(args, st) : launch_step_kvf<KIND, V, true, false, BLOCK, PREF>(args, st);
+  return track ? launch_step_kvf<KIND, V, false, true, BLOCK, PREF>(args, st) : launch_step_kvf<KIND, V, false, false, BLOCK, PREF>(args, st);
+}
+
 template <int KIND, int V>
 static cudaError_t launch_step_kv(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
   if (args.n_steps > 1) {
@@ -467,9 +492,18 @@ static cudaError_t launch_step_kv(const rmv_env* e, const StepArgs& args, cudaSt
     k_rollout<KIND, V><<<blocks_for(groups, 128), 128, 0, st>>>(args);
     return cudaGetLastError();
   }
-  const bool track = args.ep_return != nullptr;
-  if (args.obs) return track ? launch_step_kvf<KIND, V, true, true>(args, st) : launch_step_kvf<KIND, V, true, false>(args, st);
-  return track ? launch_step_kvf<KIND, V, false, true>(args, st) : launch_step_kvf<KIND, V, false, false>(args, st);
+  if constexpr (V == 1) {            // CTA size is a tuning knob of the one-env-per-thread kernel only
+    const int block = e->block ? e->block : default_block(KIND);
+    const bool pref = g_prefetch_override >= 0 ? g_prefetch_override != 0 : true;
+    if (pref) {
+      if (block == 512) return launch_step_kvb<KIND, 1, 512, true>(args, st);
+      if (block == 256) return launch_step_kvb<KIND, 1, 256, true>(args, st);
+      return launch_step_kvb<KIND, 1, 128, true>(args, st);
+    }
+    if (block == 512) return launch_step_kvb<KIND, 1, 512, false>(args, st);
+    if (block == 256) return launch_step_kvb<KIND, 1, 256, false>(args, st);
+  }
+  return launch_step_kvb<KIND, V, 128, false>(args, st);
 }
 
 template <int KIND>
@@ -481,7 +515,6 @@ static cudaError_t launch_step_k(const rmv_env* e, const StepArgs& args, int vec
     case 2: return launch_step_kv<KIND, 2>(e, args, st);
     default: return launch_step_kv<KIND, 1>(e, args, st);
   }
-  (void)e;
 }
 
 // inverse of the reference's inertia matrix (reinmav_env.py:60-63), by cofactors in float64
@@ -553,6 +586,10 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
   a.fin_count = at(e->fin_count);
   a.n = cn; a.act_ld = act_ld; a.out_ld = out_ld; a.act_step_stride = act_step_stride;
   a.env_id_offset = e->env_id_offset + c0; a.seed = e->seed; a.step_index = e->step_index;
+  for (uint32_t r = 0; r < 10; ++r) {
+    a.ks[2 * r] = (uint32_t)e->seed + r * PHILOX_W0;
+    a.ks[2 * r + 1] = (uint32_t)(e->seed >> 32) + r * PHILOX_W1;
+  }
   a.n_steps = n_steps; a.act_soa = (act_layout == RMV_ACT_SOA); a.auto_reset = auto_reset ? 1 : 0;
   a.P = e->dp;
   cudaError_t err;

@@ -45,6 +45,7 @@ struct StepArgs {
   uint32_t* fin_count;
   int64_t n, act_ld, out_ld, act_step_stride, env_id_offset;
   uint64_t seed;
+  uint32_t ks[20];         // Philox key schedule of `seed`: ks[2r] = lo + r*W0, ks[2r+1] = hi + r*W1
   uint32_t step_index;
   int n_steps, act_soa, auto_reset;
   DevParams P;
@@ -178,46 +179,71 @@ __device__ __forceinline__ float on_done(const StepArgs& a, int64_t e, float n_r
 // ---- the fused single-step kernel ------------------------------------------------------------
 // dynamics + done + reward + reset-on-done (+ optional episode bookkeeping, + optional
 // row-per-env observation copy) for n envs: the reference's step() and the caller's reset-on-done
-// in ONE launch.  128 threads per CTA, V envs per thread; indices are 32-bit (n < 2^31 per launch,
-// enforced by the host), the only 64-bit arithmetic is the one base pointer per thread.
+// in ONE launch.  BLOCK threads per CTA (128, 256 or 512), V envs per thread; indices are 32-bit
+// (n < 2^31 per launch, enforced by the host), the only 64-bit arithmetic is the one base pointer
+// per thread.
 //
 // Reset-on-done without serialising warps: an env that finished gets its terminal reward and its
-// `episode` word updated by its owner thread, which then just raises a bit in a per-warp ballot.  After
-// the single __syncthreads of the kernel the CTA's finished envs (1-2 per CTA under a random policy) are
-// re-drawn cooperatively, ONE (env, Philox block) PAIR PER THREAD, straight into the state tile.  The
-// inline alternative makes every warp that contains a finished env (a third of all warps) run the
-// 3 x 10 Philox rounds of a quadrotor3d reset with one lane active.
-constexpr int kBlock = 128;
+// `episode` word updated by its owner thread, which then appends the env to a CTA-wide list in shared
+// memory (one shared-memory atomic per finished env; warps without one pay nothing).  After the
+// second __syncthreads of the kernel the CTA's finished envs are re-drawn cooperatively, ONE (env,
+// Philox block) PAIR PER THREAD, densely packed into the first warp(s), straight into the state tile.
+// The inline alternative makes every warp that contains a finished env (a third of all warps under a
+// random policy) run the 3 x 10 Philox rounds of a quadrotor3d reset with one lane active; the larger
+// the CTA, the fewer warps execute the Philox code at all (one warp per CTA while pairs <= 32).
+constexpr int kBlock = 128;           // CTA size of the TMA variant and of V > 1
 constexpr int kWarps = kBlock / 32;
 
-template <int KIND, int V, bool OBS, bool TRACK>
-__global__ void __launch_bounds__(kBlock, V != 1 ? 1 : ((OBS || TRACK || Dims<KIND>::S > 10) ? 10 : (KIND == QUAD2D_SLUNG ? 12 : 16)))
-k_step(const StepArgs a) {
-  constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
-  constexpr int NB = (S + 3) / 4;                  // Philox blocks per reset
-  constexpr int SP = (S % 2 == 0) ? S + 1 : S;     // odd row pitch: conflict-free transposes
-  __shared__ uint32_t redraw_count[V][kWarps];     // finished envs per (v, warp) ...
-  __shared__ uint8_t redraw_lane[V][kWarps][32];   // ... and their lanes, compacted by a ballot prefix
-  extern __shared__ float tile[];                  // [warps][32][SP], only when OBS
+// Philox4x32-10 with the key schedule (k + r*W) taken from the kernel-parameter constant bank: per
+// round two wide multiplies and two three-input XORs.  Same function as philox4x32_10.
+__device__ __forceinline__ void philox4x32_10_ks(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 const uint32_t (&ks)[20], uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+    const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ ks[2 * r];
+    const uint32_t n2 = hi0 ^ c3 ^ ks[2 * r + 1];
+    c1 = lo1; c3 = lo0; c0 = n0; c2 = n2;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// U[-1,1) from the top 24 bits: -1 + u24 * 2^-23 in ONE fma.  Every intermediate of
+// uniform_from_bits(bits, -1, 2) is exact (multiples of 2^-23 of magnitude <= 1), so this is the same value.
+__device__ __forceinline__ float uniform_pm1(uint32_t bits) {
+  return __fmaf_rn((float)(bits >> 8), 1.1920928955078125e-07f, -1.0f);
+}
 
-  // Programmatic dependent launch: let the NEXT launch in the stream become resident while this grid
-  // drains, and do not touch global memory before the PREVIOUS grid has completed and flushed.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+constexpr int step_min_ctas(int kind, int v, bool obs, bool track, int block) {
+  // resident-thread target per SM: 2048 (<= 32 registers) for the small-state kinds, 1536 for
+  // quadrotor2d-slungload, 1280 when the obs copy / tracking / the 16-component state need registers
+  if (v != 1) return 1;
+  const int threads = (obs || track || kind == QUAD3D_SLUNG) ? 1280 : (kind == QUAD2D_SLUNG ? 1536 : 2048);
+  return threads / block > 0 ? threads / block : 1;
+}
+
+// One CTA's worth of envs up to (not including) the re-draw pass.  FULL: every env of the CTA exists
+// (all CTAs but the last of a ragged batch), so no per-thread bounds checks.
+template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF, bool FULL>
+__device__ __forceinline__ void step_envs(const StepArgs& a, uint32_t cta_e0, uint32_t* redraw_total,
+                                          uint16_t* redraw_list, uint32_t* redraw_episode, float* tile) {
+  constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
+  constexpr int SP = (S % 2 == 0) ? S + 1 : S;     // odd row pitch: conflict-free transposes
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t n = (uint32_t)a.n;
-  const uint32_t cta_e0 = blockIdx.x * (uint32_t)(kBlock * V);
   const uint32_t e0 = cta_e0 + tid * V;
-  const bool active = e0 < n;
-  const bool full = e0 + V <= n;
+  const bool active = FULL || e0 < n;
+  const bool full = FULL || e0 + V <= n;
 
   // thread's base pointer into the tiled state: rows of the tile are at constant offsets c*kTile
   float* const sp = a.state + ((size_t)(e0 >> 7) * (S * kTile) + (e0 & (kTile - 1)));
   float s[V][S];
+  float act[V][A];
   float ep_ret[V];
+  uint32_t word[V];                                // PREF: the env's `episode` word, fetched with the state
   bool redraw[V];
 #pragma unroll
-  for (int v = 0; v < V; ++v) redraw[v] = false;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int v = 0; v < V; ++v) { redraw[v] = false; word[v] = 0u; }
 
   if (active) {
 #pragma unroll
@@ -227,10 +253,16 @@ k_step(const StepArgs a) {
 #pragma unroll
       for (int v = 0; v < V; ++v) s[v][c] = t[v];
     }
+    if (PREF) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) word[v] = a.episode[e0 + v];   // padded to whole tiles: in bounds
+    }
     if (TRACK) load_v<V, false>(a.ep_return + e0, ep_ret);
-    float act[V][A];
     load_actions<KIND, V>(a, a.act, (int64_t)e0, full, act);
+  }
+  __syncthreads();                                 // *redraw_total = 0 is visible; the loads are in flight
 
+  if (active) {
     float rew[V];
     uint8_t dn[V];
 #pragma unroll
@@ -241,12 +273,18 @@ k_step(const StepArgs a) {
       float r = -n_rew;
       dn[v] = done ? 1 : 0;
       const uint32_t e = e0 + v;
-      if (done && e < n) {
+      if (done && (FULL || e < n)) {
         // rare lane: the ever-done flag decides the terminal reward (quadrotor3d.py:112-122)
-        const uint32_t word = a.episode[e];
-        r = reward_of(a.P, true, (word & kEverDone) != 0u, n_rew);
-        a.episode[e] = ((word & ~kEverDone) + (a.auto_reset ? 1u : 0u)) | kEverDone;
-        redraw[v] = a.auto_reset != 0;
+        const uint32_t w = PREF ? word[v] : a.episode[e];
+        r = reward_of(a.P, true, (w & kEverDone) != 0u, n_rew);
+        const uint32_t count = (w & ~kEverDone) + (a.auto_reset ? 1u : 0u);
+        a.episode[e] = count | kEverDone;
+        if (a.auto_reset) {
+          redraw[v] = true;
+          const uint32_t slot = atomicAdd(redraw_total, 1u);
+          redraw_list[slot] = (uint16_t)(tid * V + v);
+          redraw_episode[slot] = count;            // the Philox episode index of the re-draw
+        }
         if (TRACK) {
           const float total = ep_ret[v] + r;
           const uint32_t now = a.step_index + 1u;
@@ -297,14 +335,6 @@ k_step(const StepArgs a) {
     if (TRACK) store_v<V, false>(a.ep_return + e0, ep_ret);
   }
 
-  uint32_t my_mask[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    my_mask[v] = __ballot_sync(0xffffffffu, redraw[v]);
-    if (lane == 0) redraw_count[v][warp] = __popc(my_mask[v]);
-    if (redraw[v]) redraw_lane[v][warp][__popc(my_mask[v] & ((1u << lane) - 1u))] = (uint8_t)lane;
-  }
-
   if (OBS) {
     // row-per-env observation copy [n][S]: transpose through a per-warp shared tile so that each
     // store instruction writes runs of S contiguous floats instead of 32 scattered words.
@@ -313,6 +343,7 @@ k_step(const StepArgs a) {
     const uint32_t warp_e0 = e0 - lane * V;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
+      const uint32_t my_mask = __ballot_sync(0xffffffffu, redraw[v]);
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < S; ++c) my[lane * SP + c] = s[v][c];
@@ -321,45 +352,55 @@ k_step(const StepArgs a) {
       for (int i = lane; i < 32 * S; i += 32) {
         const int r = i / S, c = i - r * S;
         const uint32_t e = warp_e0 + (uint32_t)r * V + v;
-        if (e < n && !((my_mask[v] >> r) & 1u)) __stcs(a.obs + (size_t)e * S + c, my[r * SP + c]);
+        if ((FULL || e < n) && !((my_mask >> r) & 1u)) __stcs(a.obs + (size_t)e * S + c, my[r * SP + c]);
       }
     }
   }
+}
+
+template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF>
+__global__ void __launch_bounds__(BLOCK, step_min_ctas(KIND, V, OBS, TRACK, BLOCK))
+k_step(const StepArgs a) {
+  constexpr int S = Dims<KIND>::S;
+  constexpr int NB = (S + 3) / 4;                  // Philox blocks per reset
+  static_assert(BLOCK * V <= 65536, "redraw_list holds 16-bit indices");
+  __shared__ uint32_t redraw_total;                // finished envs of this CTA ...
+  __shared__ uint16_t redraw_list[BLOCK * V];      // ... their indices inside the CTA, in arrival order ...
+  __shared__ uint32_t redraw_episode[BLOCK * V];   // ... and their new reset counts
+  extern __shared__ float tile[];                  // [warps][32][SP], only when OBS
+
+  // Programmatic dependent launch: let the NEXT launch in the stream become resident while this grid
+  // drains, and do not touch global memory before the PREVIOUS grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) redraw_total = 0u;
+  const uint32_t cta_e0 = blockIdx.x * (uint32_t)(BLOCK * V);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (cta_e0 + (uint32_t)(BLOCK * V) <= (uint32_t)a.n)     // uniform
+    step_envs<KIND, V, OBS, TRACK, BLOCK, PREF, true>(a, cta_e0, &redraw_total, redraw_list, redraw_episode, tile);
+  else
+    step_envs<KIND, V, OBS, TRACK, BLOCK, PREF, false>(a, cta_e0, &redraw_total, redraw_list, redraw_episode, tile);
 
   // ---- re-draw the finished envs of this CTA: one (env, Philox block) pair per thread ------------
   __syncthreads();
-  uint32_t count[V * kWarps], total = 0;
-#pragma unroll
-  for (int v = 0; v < V; ++v)
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) { count[v * kWarps + w] = redraw_count[v][w]; total += count[v * kWarps + w]; }
-  for (uint32_t i = tid; i < total * NB; i += kBlock) {
-    uint32_t slot = i / NB;
-    const uint32_t b = i - slot * NB;
-    uint32_t rel = 0;                              // index of the slot-th finished env inside the CTA
-    bool found = false;
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) {
-        const uint32_t c = count[v * kWarps + w];
-        if (!found && slot < c) { rel = ((uint32_t)w * 32u + redraw_lane[v][w][slot]) * V + v; found = true; }
-        if (!found) slot -= c;
-      }
-    const uint32_t e = cta_e0 + rel;
-    const uint32_t episode = a.episode[e] & ~kEverDone;      // written by the owner before the barrier
+  const uint32_t pairs = redraw_total * NB;
+  for (uint32_t i = tid; i < pairs; i += BLOCK) {
+    const uint32_t slot = i / NB, b = i - slot * NB;
+    const uint32_t e = cta_e0 + redraw_list[slot];
+    const uint32_t episode = redraw_episode[slot];
     const uint64_t id = (uint64_t)a.env_id_offset + e;
     uint32_t w4[4];
-    philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), episode, ((STREAM_RESET_BASE + (uint32_t)KIND) << 8) | b,
-                  (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w4);
-    float* const row = a.state + ((size_t)(e >> 7) * (S * kTile) + (e & (kTile - 1)));
+    philox4x32_10_ks((uint32_t)id, (uint32_t)(id >> 32), episode, ((STREAM_RESET_BASE + (uint32_t)KIND) << 8) | b,
+                     a.ks, w4);
+    float* const row = a.state + ((size_t)(e >> 7) * (S * kTile) + (e & (kTile - 1))) + 4 * b * kTile;
+    float* const orow = OBS ? a.obs + (size_t)e * S + 4 * b : nullptr;
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-      const int c = 4 * (int)b + l;
-      if (c < S) {
-        const float x = uniform_from_bits(w4[l], -1.0f, 2.0f);
-        row[c * kTile] = x;
-        if (OBS) a.obs[(size_t)e * S + c] = x;
+      if (S % 4 == 0 || 4 * b + l < S) {
+        const float x = uniform_pm1(w4[l]);
+        row[l * kTile] = x;
+        if (OBS) orow[l] = x;
       }
     }
   }

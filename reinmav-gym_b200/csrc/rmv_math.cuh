@@ -50,6 +50,14 @@ RMV_HD rf rsqrt_exact(rf a) { return rf(sqrtf(a.v)); }
 #endif
 RMV_HD rf operator-(rf a) { return rf(-a.v); }
 RMV_HD rf sqrt(rf a) { return rsqrt_exact(a); }
+// 1/a correctly rounded: the same value as the IEEE quotient 1.0f/a for every input; __frcp_rn is the shorter sequence
+RMV_HD rf rcp(rf a) {
+#if defined(__CUDA_ARCH__)
+  return rf(__frcp_rn(a.v));
+#else
+  return rf(1.0f / a.v);
+#endif
+}
 // a*b + c with ONE rounding (FFMA).  Used exactly where the float32 model (oracle/batch.py `_fma`)
 // uses its exact fma; everything else stays individually rounded.
 RMV_HD rf fma(rf a, rf b, rf c) {
@@ -267,7 +275,7 @@ RMV_HD void attitude_3d(const rf (&q)[4], const rf (&om)[3], rf (&e3)[3], rf (&q
   // multiplying by 1/sqrt(1) = 1 is exact, so only the n > 0 guard is left.  float32 normalises
   // with ONE IEEE reciprocal and four products (x/n -> x*(1/n)): <= 1 ulp from the quotient.
   if (n.v > 0.0f) {
-    const rf inv = rf(1.0f) / n;
+    const rf inv = rcp(n);
     w = w * inv; x = x * inv; y = y * inv; z = z * inv;
   }
   // column 3 of (Q Qbar^T)[1:,1:], four-term sums left to right
@@ -330,7 +338,7 @@ RMV_HD void quad_slung(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[
   const bool taut = sqrt(acc2).v >= (double)P.tether_len;
   const rf tm = T * rf(P.inv_mass);
   if (taut) {
-    const rf inv_nt = rf(1.0f) / norm<D>(tv);
+    const rf inv_nt = rcp(norm<D>(tv));
     rf u[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) u[i] = tv[i] * inv_nt;
@@ -356,7 +364,7 @@ RMV_HD void quad_slung(const DevParams& P, rf T, const rf (&axis)[D], rf (&pos)[
     rf dv[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) dv[i] = lp[i] - pos[i];
-    const rf inv_nd = rf(1.0f) / norm<D>(dv);
+    const rf inv_nd = rcp(norm<D>(dv));
     rf dir[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) dir[i] = dv[i] * inv_nd;

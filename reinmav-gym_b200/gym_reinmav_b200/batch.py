@@ -108,7 +108,7 @@ class QuadBatch:
         self.seed = int(seed)
         check(lib().rmv_set_seed(self._h, self.seed & 0xFFFFFFFFFFFFFFFF))
 
-    def set_tuning(self, vec=0, block=128):
+    def set_tuning(self, vec=0, block=0):
         check(lib().rmv_set_tuning(self._h, int(vec), int(block)))
 
     @property
