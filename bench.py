@@ -265,7 +265,7 @@ def run_gpu_arm(args):
             "config": {"workload": "%s N=%d envs per GPU, random-policy actions U[0,10)^4, reset-on-done in-kernel"
                                    % (ENV_ID, n),
                        "env_id": ENV_ID, "envs_per_gpu": n, "state_dim": S, "action_dim": A,
-                       "launch": "one fused step kernel per step (vec=%d, block=%d), %d-step action ring" % (args.vec, args.block, ring),
+                       "launch": "one fused step kernel per step (vec=%d, block=%s), %d-step action ring" % (args.vec, args.block or "auto", ring),
                        "l2": "no flush: per-step traffic %.0f MB (state %.0f MB read+written in place, re-read next step; "
                              "actions stream from a %.2f GiB ring > 126 MB L2); extras.n23 is the same kernel with a "
                              "working set that cannot be L2-resident" % (ALG_BYTES * n / 1e6, 4 * S * n / 1e6, ring * n * A * 4 / 2 ** 30),
@@ -280,7 +280,7 @@ def run_gpu_arm(args):
                          "traffic_steady_state": ((load_traffic() or {}).get("steady_state") or {}).get("dram_bytes_per_launch"),
                          "traffic_note": "ncu --set full per launch: cold-cache capture (L2 flushed per replay) / "
                                          "--cache-control none capture of a back-to-back run (42 MB state L2-resident)",
-                         "kernel": "rmv::k_step<QUAD3D, vec=%d, block=%d>" % (args.vec, args.block),
+                         "kernel": "rmv::k_step<QUAD3D, vec=%d, block=%s>" % (args.vec, args.block or "auto(128)"),
                          "algorithmic_bytes_per_launch": ALG_BYTES * n, "avg_launch_us": ms_per_step * 1e3, "peak_source": peak_src,
                          "note": "frac > 1 at N=2^20 because the 42 MB state stays L2-resident between steps "
                                  "(traffic_steady_state << algorithmic bytes); the HBM-bound point of the same kernel is "
@@ -349,6 +349,56 @@ def measure_extras(torch, rmv, args, local):
         b.close()
         del acts, rew, done
 
+    # The headline kernel with a COLD L2: 256 MiB are written between launches (> 126 MB L2), each launch is timed
+    # by its own pair of events.  Every state/action byte then comes from HBM; the isolated launch also pays its
+    # own ramp and launch latency (no overlap with a predecessor).
+    n = 1 << 20
+    b = rmv.QuadBatch(ENV_ID, n, device=local, seed=SEED)
+    b.set_tuning(vec=args.vec, block=args.block)
+    b.reset()
+    acts = torch.empty((8, n, ACTION_DIM), dtype=torch.float32, device=dev)
+    for t in range(8):
+        rmv.fill_uniform_actions(acts[t], n, ACTION_DIM, ACT_LO, ACT_HI, SEED, step_index=t, device=local)
+    rew = torch.empty((8, n), dtype=torch.float32, device=dev)
+    done = torch.empty((8, n), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for t in range(8):
+        b.step(acts[t], rew[t], done[t])
+    evs = []
+    for t in range(40):
+        flush.fill_(t & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); b.step(acts[t % 8], rew[t % 8], done[t % 8]); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(z) for a, z in evs)
+    ms = ts[len(ts) // 2]
+    out["n20_l2_flushed"] = {"env_id": ENV_ID, "n_envs": n, "us_per_step": ms * 1e3, "env_steps_per_s": n / (ms * 1e-3),
+                             "algorithmic_GBps": n * 101 / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": n * 101 / (ms * 1e-3) / 1e9 / peak,
+                             "mode": "one launch per step, 256 MiB written between launches (L2 flushed), one event pair per "
+                                     "launch, median of 40; ~60 MB of the 106 MB are DRAM traffic inside the launch "
+                                     "(results stay dirty in L2), so this is a latency/ramp-bound isolated launch"}
+    b.close()
+    del acts, rew, done, flush
+
+    # BASELINE configs[1], [2]: N = 65536 (launch-latency-bound: one launch moves 6.6 / 9.8 MB)
+    for name, env_id in (("n65536_quadrotor3d", ENV_ID), ("n65536_quadrotor3d_slungload", "quadrotor3d-slungload-v0")):
+        n = 1 << 16
+        b = rmv.QuadBatch(env_id, n, device=local, seed=SEED)
+        b.reset()
+        lo, hi = bounds[env_id]
+        acts = torch.empty((64, n, 4), dtype=torch.float32, device=dev)
+        for t in range(64):
+            rmv.fill_uniform_actions(acts[t], n, 4, lo, hi, SEED, step_index=t, device=local)
+        rew = torch.empty((64, n), dtype=torch.float32, device=dev)
+        done = torch.empty((64, n), dtype=torch.uint8, device=dev)
+        ms = time_steps(b, acts, rew, done, n, 2000)
+        out[name] = {"env_id": env_id, "n_envs": n, "us_per_step": ms * 1e3, "env_steps_per_s": n / (ms * 1e-3),
+                     "algorithmic_GBps": n * bytes_of[env_id] / (ms * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": n * bytes_of[env_id] / (ms * 1e-3) / 1e9 / peak, "mode": "one launch per step (launch-bound)"}
+        b.close()
+        del acts, rew, done
+
     # reinmav-v0 (closed-loop 13-state body, 50/51 float64 substeps per step, no action)
     n = 1 << 20
     b = rmv.QuadBatch("reinmav-v0", n, device=local)
@@ -376,7 +426,7 @@ def measure_extras(torch, rmv, args, local):
     venv = rmv.QuadVecEnv("quadrotor2d-v0", n, device=local, seed=SEED, monitor=False)
     buf = rollout.RolloutBuffer(venv, T)
     buf.actions.normal_()
-    policy = lambda obs, _it=iter(range(10 ** 9)): buf.actions[next(_it) % T]      # pre-drawn actions: env-side cost only
+    policy = lambda obs, _it=iter(range(10 ** 9)): buf.action_views[next(_it) % T]      # pre-drawn actions: env-side cost only
     buf.collect(policy)
     torch.cuda.synchronize()
     best = 1e30
@@ -445,7 +495,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU")
     ap.add_argument("--vec", type=int, default=1)
-    ap.add_argument("--block", type=int, default=128)
+    ap.add_argument("--block", type=int, default=0, help="threads per CTA of the step kernel (0 = the library's choice)")
     ap.add_argument("--repeats", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-steps", type=int, default=2000)

@@ -134,6 +134,10 @@ RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block);
  * (V = 1, row-per-env actions) where it applies, 0 the register-path kernel; ctas_per_sm caps the
  * persistent grid (0 = as many as fit).  Results are identical. */
 RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm);
+/* one-env-per-thread step kernel: fetch every env's `episode` word together with its state (1) instead of only
+ * on the lanes that finish (0); -1 = auto (by kind and working-set size).  Trades 4 B per env-step of read
+ * traffic for one dependent memory round trip fewer in every CTA that holds a finished env.  Results are identical. */
+RMV_API int rmv_set_prefetch(rmv_env* env, int mode);
 /* number of chunks rmv_step_host pipelines a batch through (H2D | kernel | D2H overlap); 0 = auto
  * (8 for n >= 65536, else 1) */
 RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks);

@@ -101,6 +101,7 @@ struct rmv_env {
   // tuning
   int vec = 0;     // 0 = auto
   int block = 0;   // 0 = auto (default_block)
+  int prefetch = -1;       // -1 auto, 0 / 1: episode-word prefetch of the one-env-per-thread step kernel
   int use_tma = 0;         // 1: TMA-pipelined persistent step kernel where it applies
   int tma_ctas_per_sm = 0; // 0 = as many as fit
 };
@@ -285,6 +286,13 @@ extern "C" RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm
   return RMV_OK;
 }
 
+extern "C" RMV_API int rmv_set_prefetch(rmv_env* env, int mode) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(mode >= -1 && mode <= 1, "mode must be -1 (auto), 0 or 1");
+  env->prefetch = mode;
+  return RMV_OK;
+}
+
 extern "C" RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
   RMV_REQUIRE(vec == 0 || vec == 1 || vec == 2 || vec == 4, "vec must be 0 (auto), 1, 2 or 4");
@@ -402,14 +410,26 @@ extern "C" RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* o
 // ------------------------------------------------------------------------------------------
 // step
 // ------------------------------------------------------------------------------------------
-// threads per CTA of the one-env-per-thread step kernel when rmv_set_tuning left it on auto (measured:
-// profiles/)
-static int g_prefetch_override = getenv("RMV_PREFETCH") ? atoi(getenv("RMV_PREFETCH")) : -1;   // developer switch
-static int g_block_override = getenv("RMV_BLOCK") ? atoi(getenv("RMV_BLOCK")) : 0;   // developer switch (tools/sweep.py, parity runs)
-static int default_block(int kind) {
+// Launch shape of the one-env-per-thread step kernel when rmv_set_tuning left it on auto.  Measured on B200
+// (profiles/r1b_sweep_block_prefetch.txt): what matters is whether one step's working set stays in the 126 MB
+// L2 between launches ("small": L2-bandwidth / issue bound) or streams from HBM ("big": latency bound for the
+// small-state kinds, where fetching the `episode` word together with the state takes a dependent memory round
+// trip out of every CTA that contains a finished env).
+static int g_prefetch_override = getenv("RMV_PREFETCH") ? atoi(getenv("RMV_PREFETCH")) : -1;   // developer switches
+static int g_block_override = getenv("RMV_BLOCK") ? atoi(getenv("RMV_BLOCK")) : 0;            // (tools/sweep.py, parity runs)
+static bool working_set_is_big(int kind, int64_t n) {
+  static const int64_t bytes[4] = {53, 85, 101, 149};
+  return n * bytes[kind] > ((int64_t)96 << 20);
+}
+static int default_block(int kind, int64_t n) {
   if (g_block_override == 128 || g_block_override == 256 || g_block_override == 512) return g_block_override;
-  (void)kind;
-  return 128;
+  return (kind == QUAD2D && !working_set_is_big(kind, n)) ? 256 : 128;
+}
+static bool default_prefetch(int kind, int64_t n) {
+  if (g_prefetch_override >= 0) return g_prefetch_override != 0;
+  if (kind == QUAD2D) return true;
+  if (kind == QUAD3D) return false;
+  return working_set_is_big(kind, n);
 }
 
 template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF>
@@ -493,8 +513,8 @@ static cudaError_t launch_step_kv(const rmv_env* e, const StepArgs& args, cudaSt
     return cudaGetLastError();
   }
   if constexpr (V == 1) {            // CTA size is a tuning knob of the one-env-per-thread kernel only
-    const int block = e->block ? e->block : default_block(KIND);
-    const bool pref = g_prefetch_override >= 0 ? g_prefetch_override != 0 : true;
+    const int block = e->block ? e->block : default_block(KIND, args.n);
+    const bool pref = e->prefetch >= 0 ? e->prefetch != 0 : default_prefetch(KIND, args.n);
     if (pref) {
       if (block == 512) return launch_step_kvb<KIND, 1, 512, true>(args, st);
       if (block == 256) return launch_step_kvb<KIND, 1, 256, true>(args, st);

@@ -444,7 +444,18 @@ __global__ void __launch_bounds__(128) k_rollout(const StepArgs a) {
         uint32_t count;
         r = on_done(a, e, n_rew, a.ep_return ? ep_ret[v] : 0.0f, a.step_index + (uint32_t)step + 1u, count);
         if (a.ep_return) ep_ret[v] = -r;
-        if (a.auto_reset) reset_draws<KIND>(a.seed, (uint64_t)(a.env_id_offset + e), count, s[v]);
+        if (a.auto_reset) {
+          const uint64_t id = (uint64_t)(a.env_id_offset + e);
+#pragma unroll
+          for (int b = 0; b < (S + 3) / 4; ++b) {
+            uint32_t w4[4];
+            philox4x32_10_ks((uint32_t)id, (uint32_t)(id >> 32), count, ((STREAM_RESET_BASE + (uint32_t)KIND) << 8) | (uint32_t)b,
+                             a.ks, w4);
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+              if (4 * b + l < S) s[v][4 * b + l] = uniform_pm1(w4[l]);
+          }
+        }
       }
       rew[v] = r;
       if (a.ep_return) ep_ret[v] += r;

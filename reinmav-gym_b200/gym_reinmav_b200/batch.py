@@ -126,6 +126,10 @@ class QuadBatch:
         """Pick the step-kernel variant (register path / TMA-pipelined persistent); results are identical."""
         check(lib().rmv_set_kernel(self._h, 1 if tma else 0, int(ctas_per_sm)))
 
+    def set_prefetch(self, mode=-1):
+        """Episode-word prefetch of the step kernel: -1 auto, 0 off, 1 on; results are identical."""
+        check(lib().rmv_set_prefetch(self._h, int(mode)))
+
     def set_host_chunks(self, chunks=0):
         check(lib().rmv_set_host_chunks(self._h, int(chunks)))
 

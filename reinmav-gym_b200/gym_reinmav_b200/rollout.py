@@ -19,6 +19,15 @@ class RolloutBuffer:
         self.rewards = torch.empty((self.T, n), dtype=torch.float32, device=dev)
         self.dones = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
         self._have_first = False
+        # per-step views and raw addresses, built once: the collect() loop then costs one policy call and one
+        # C-ABI call per step (at N = 2^20 a quadrotor2d step kernel takes ~10 us; seven tensor-indexing
+        # operations per step cost more than that on the host)
+        self.obs_views = [self.obs[t] for t in range(self.T + 1)]
+        self.action_views = [self.actions[t] for t in range(self.T)]
+        self._obs_p = [v.data_ptr() for v in self.obs_views]
+        self._act_p = [v.data_ptr() for v in self.action_views]
+        self._rew_p = [self.rewards[t].data_ptr() for t in range(self.T)]
+        self._done_p = [self.dones[t].data_ptr() for t in range(self.T)]
 
     def start(self):
         """reset() all envs; the first observation lands in ``obs[0]``."""
@@ -32,11 +41,13 @@ class RolloutBuffer:
         if not self._have_first:
             self.start()
         b = self.venv.batch
+        stream = torch.cuda.current_stream(self.venv.device).cuda_stream
+        obs_t, act_t, obs_p, act_p, rew_p, done_p = self.obs_views, self.action_views, self._obs_p, self._act_p, self._rew_p, self._done_p
         for t in range(self.T):
-            a = policy(self.obs[t])
-            if a.data_ptr() != self.actions[t].data_ptr():
-                self.actions[t].copy_(a)
-            b.step(self.actions[t], self.rewards[t], self.dones[t], obs=self.obs[t + 1], auto_reset=True)
+            a = policy(obs_t[t])
+            if a.data_ptr() != act_p[t]:
+                act_t[t].copy_(a)
+            b.step(act_p[t], rew_p[t], done_p[t], obs=obs_p[t + 1], auto_reset=True, stream=stream)
         return self
 
     def roll(self):

@@ -106,13 +106,15 @@ def test_single_step_bitwise(torch, rmv, env_id, vec, layout):
 
 
 # ------------------------------------------------------------------------------------------ rollouts vs T1 (bit-exact)
-def _rollout_bitwise(torch, rmv, env_id, n, steps, vec, seed, check_state_every, tma=False, track=False):
+def _rollout_bitwise(torch, rmv, env_id, n, steps, vec, seed, check_state_every, tma=False, track=False, block=0,
+                     prefetch=-1):
     kind = KIND_OF_ID[env_id]
     S, A = STATE_DIM[kind], ACTION_DIM[kind]
     lo, hi = ACTION_BOUNDS[kind]
     off = 5 * n
     b = rmv.QuadBatch(env_id, n, seed=seed, env_id_offset=off, track_episodes=track)
-    b.set_tuning(vec=vec)
+    b.set_tuning(vec=vec, block=block)
+    b.set_prefetch(prefetch)
     b.set_kernel(tma=tma)
     o = BatchOracle(kind, n, seed=seed, env_id_offset=off, dtype=np.float32)
     b.reset()
@@ -163,6 +165,16 @@ def test_planar_rollouts_bitwise(torch, rmv, env_id):
 @pytest.mark.parametrize("env_id", ENV_IDS)
 def test_small_ragged_rollouts_bitwise(torch, rmv, env_id, vec):
     _rollout_bitwise(torch, rmv, env_id, 1000 + 1, 200, vec=vec, seed=3, check_state_every=50)
+
+
+@pytest.mark.parametrize("prefetch", [0, 1])
+@pytest.mark.parametrize("block", [128, 256, 512])
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_every_cta_size_and_prefetch_mode_bitwise(torch, rmv, env_id, block, prefetch):
+    """The launch-shape knobs of the step kernel (threads per CTA, episode-word prefetch) never change a bit:
+    ragged batch (last CTA partial for every size), obs rows, episode tracking on the prefetch=1 runs."""
+    _rollout_bitwise(torch, rmv, env_id, 128 * 37 + 77, 120, vec=1, seed=5, check_state_every=40, block=block,
+                     prefetch=prefetch, track=bool(prefetch))
 
 
 @pytest.mark.parametrize("n,track", [(1000 + 1, False), (127, True), (128 * 700 + 5, True), (65536, False)])

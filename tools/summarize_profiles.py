@@ -1,0 +1,105 @@
+"""Turns the scratch captures of tools/profile_round.sh (gpurun_out/<dir>) into the tracked summaries under
+profiles/ : per-kernel key metrics, executed-SASS opcode histograms, the launch list and traffic.json."""
+import csv, io, json, os, shutil, sys, collections
+
+src, tag = sys.argv[1], sys.argv[2]            # e.g. gpurun_out/prof_r1b r1b
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+out = os.path.join(ROOT, "profiles")
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_warps", "launch__occupancy_limit_shared_mem", "sm__cycles_elapsed.avg",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
+
+
+def raw_rows(path):
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    return [dict(zip(hdr, r)) for r in rows[2:]], dict(zip(hdr, units))
+
+
+traffic = {}
+for name in ("q3d_n20_cold", "q3d_n20_warm", "q3d_n23", "q2d_n20_warm", "q2d_n23"):
+    p = os.path.join(src, name + ".raw.csv")
+    if not os.path.exists(p):
+        continue
+    rows, units = raw_rows(p)
+    with open(os.path.join(out, "%s_ncu_%s.txt" % (tag, name)), "w") as fh:
+        fh.write("# ncu --set full --clock-control none%s, key metrics per captured launch (tools/profile_round.sh)\n"
+                 % ("" if name.endswith("cold") else " --cache-control none"))
+        for d in rows:
+            fh.write("== %s\n" % d.get("Kernel Name", ""))
+            for k in KEYS:
+                if k in d:
+                    fh.write("   %-86s %s %s\n" % (k, d[k], units.get(k, "")))
+        det = os.path.join(src, name + ".details.txt")
+        if os.path.exists(det):
+            fh.write("\n# ---- ncu --page details ----\n")
+            fh.write(open(det).read())
+    d = rows[0]
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    rd = float(d["dram__bytes_read.sum"]) * scale[units["dram__bytes_read.sum"]]
+    wr = float(d["dram__bytes_write.sum"]) * scale[units["dram__bytes_write.sum"]]
+    traffic[name] = {"dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "dram_bytes_per_launch": int(rd + wr),
+                     "gpu_time_us_under_ncu": float(d["gpu__time_duration.sum"]) * (1e-3 if units["gpu__time_duration.sum"] == "ns" else 1.0),
+                     "kernel": d.get("Kernel Name", "")}
+    # executed SASS histogram per warp
+    p = os.path.join(src, name + ".sass.csv")
+    if os.path.exists(p):
+        lines = open(p).read().splitlines()
+        start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
+        rd_ = csv.DictReader(io.StringIO("\n".join(lines[start:])))
+        hist, total = collections.Counter(), 0
+        for r in rd_:
+            try:
+                n = int(r["Instructions Executed"])
+            except (KeyError, ValueError):
+                continue
+            op = r["Source"].split()[0] if not r["Source"].startswith("@") else r["Source"].split()[1]
+            hist[op] += n
+            total += n
+        warps = int(d["launch__grid_size"]) * int(d["launch__block_size"]) // 32
+        with open(os.path.join(out, "%s_sass_opcount_%s.txt" % (tag, name)), "w") as fh:
+            fh.write("# executed SASS per warp (= per env-step at one env per thread), %s, %d warps\n" % (d.get("Kernel Name", ""), warps))
+            fh.write("total per warp %.1f\n" % (total / warps))
+            for op, n in hist.most_common(45):
+                fh.write("   %-22s %6.1f\n" % (op, n / warps))
+
+if os.path.exists(os.path.join(src, "launches_bench.csv")):
+    shutil.copy(os.path.join(src, "launches_bench.csv"), os.path.join(out, "%s_launches_bench.csv" % tag))
+san = [f for f in sorted(os.listdir(src)) if f.startswith("sanitizer_")]
+if san:
+    with open(os.path.join(out, "%s_sanitizers.txt" % tag), "w") as fh:
+        for f in san:
+            fh.write("##### compute-sanitizer --tool %s python tools/sanitize_probe.py\n" % f[len("sanitizer_"):-4])
+            fh.write(open(os.path.join(src, f)).read() + "\n")
+
+tj = os.path.join(out, "traffic.json")
+old = json.load(open(tj)) if os.path.exists(tj) else {}
+if "q3d_n20_cold" in traffic:
+    alg = 101 << 20
+    old["k_step_quadrotor3d_n2pow20"] = {
+        "dram_bytes_per_launch": traffic["q3d_n20_cold"]["dram_bytes_per_launch"],
+        "dram_bytes_read": traffic["q3d_n20_cold"]["dram_bytes_read"],
+        "dram_bytes_write": traffic["q3d_n20_cold"]["dram_bytes_write"],
+        "how": "ncu --set full --clock-control none, default cache control (L2 flushed before each replay): every state/action "
+               "byte is read from DRAM, most of the 47 MB written stay dirty in L2 past the end of the launch",
+        "steady_state": dict(traffic.get("q3d_n20_warm", {}), how="ncu --cache-control none, launch 31 of a back-to-back sequence: "
+                             "the 42 MB state is L2-resident between steps, DRAM sees the action stream and reward/done"),
+        "algorithmic_bytes_per_launch": alg,
+        "source": "profiles/%s_ncu_q3d_n20_cold.txt, profiles/%s_ncu_q3d_n20_warm.txt" % (tag, tag)}
+for k, v in traffic.items():
+    old.setdefault("captures_" + tag, {})[k] = v
+json.dump(old, open(tj, "w"), indent=2)
+print(json.dumps(traffic, indent=1))

@@ -63,12 +63,12 @@ def main():
     ap.add_argument("--envs", default="quadrotor3d-v0")
     ap.add_argument("--n", default="1048576")
     ap.add_argument("--vec", default="1,2,4")
-    ap.add_argument("--block", default="128")
+    ap.add_argument("--block", default="0", help="comma list of threads per CTA (0 = the library default for the kind and size)")
     ap.add_argument("--layout", default="soa,aos")
     ap.add_argument("--fused", default="0")
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--ring", type=int, default=16)
-    ap.add_argument("--peak", type=float, default=6546.2)
+    ap.add_argument("--peak", type=float, default=6458.4)
     ap.add_argument("--tma", default="0", help="comma list of 0/1: register-path / TMA-pipelined kernel")
     ap.add_argument("--ctas", default="0", help="comma list: persistent CTAs per SM for the TMA kernel (0 = max)")
     args = ap.parse_args()
