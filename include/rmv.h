@@ -138,6 +138,13 @@ RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm);
  * on the lanes that finish (0); -1 = auto (by kind and working-set size).  Trades 4 B per env-step of read
  * traffic for one dependent memory round trip fewer in every CTA that holds a finished env.  Results are identical. */
 RMV_API int rmv_set_prefetch(rmv_env* env, int mode);
+/* Opt-in: keep the handle's state resident in L2 between steps with an access-policy window on the state buffer
+ * (persisting on hit, streaming on miss).  mode 1 sets the DEVICE-WIDE cudaLimitPersistingL2CacheSize to the state size
+ * (that much L2 is taken from everything else on the GPU) and fails with RMV_EINVAL if the state does not fit the
+ * device's carve-out; 0 / -1 (auto = off) release it.  Pays when the state fits the carve-out but state + per-step
+ * streams do not fit L2 (+10-13 % measured); launches that also write observation rows do not use the window.
+ * Results are identical. */
+RMV_API int rmv_set_l2_persist(rmv_env* env, int mode);
 /* number of chunks rmv_step_host pipelines a batch through (H2D | kernel | D2H overlap); 0 = auto
  * (8 for n >= 65536, else 1) */
 RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks);

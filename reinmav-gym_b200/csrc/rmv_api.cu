@@ -102,9 +102,15 @@ struct rmv_env {
   int vec = 0;     // 0 = auto
   int block = 0;   // 0 = auto (default_block)
   int prefetch = -1;       // -1 auto, 0 / 1: episode-word prefetch of the one-env-per-thread step kernel
+  int l2_persist = -1;     // -1 auto (= off), 0 / 1: keep the state resident in L2 between steps (access-policy window)
+  int l2_ready = 0;        // window active
+  cudaAccessPolicyWindow l2_window{};
   int use_tma = 0;         // 1: TMA-pipelined persistent step kernel where it applies
   int tma_ctas_per_sm = 0; // 0 = as many as fit
 };
+
+static int enable_l2_window(rmv_env* e);
+static void disable_l2_window(rmv_env* e);
 
 // developer switch for A/B measurements (tools/sweep.py); the default is the product configuration
 static int g_use_pdl = (getenv("RMV_NO_PDL") == nullptr) ? 1 : 0;
@@ -232,6 +238,7 @@ extern "C" RMV_API int rmv_destroy(rmv_env* env) {
   {
     RMV_ON_DEVICE(env->device);
     cudaDeviceSynchronize();
+    disable_l2_window(env);
     free_all(env);
   }
   delete env;
@@ -283,6 +290,16 @@ extern "C" RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm
   RMV_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 32, "ctas_per_sm must be in [0, 32]");
   env->use_tma = use_tma ? 1 : 0;
   env->tma_ctas_per_sm = ctas_per_sm;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_set_l2_persist(rmv_env* env, int mode) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(mode >= -1 && mode <= 1, "mode must be -1 (auto = off), 0 or 1");
+  RMV_ON_DEVICE(env->device);
+  env->l2_persist = mode;
+  if (mode == 1) return env->l2_ready ? RMV_OK : enable_l2_window(env);
+  disable_l2_window(env);
   return RMV_OK;
 }
 
@@ -410,6 +427,50 @@ extern "C" RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* o
 // ------------------------------------------------------------------------------------------
 // step
 // ------------------------------------------------------------------------------------------
+// L2 residency of the state between steps (opt-in, rmv_set_l2_persist).  The state is the one buffer every step
+// re-reads (and re-writes in place); actions, rewards and done flags stream through once.  Left to LRU, the streams
+// push the state out of the 126 MB L2 once state + streams of one step exceed it (quadrotor3d-slungload at N = 2^20:
+// 67 MB state + 89 MB streams), and every byte then moves through HBM.  An access-policy window on the state
+// (persisting on hit, streaming on miss) pins it.  Measured on B200 (profiles/r1b_sweep_l2_persist.txt): +10-13 % in
+// exactly that band (state fits the carve-out, state + streams do not fit L2); no effect when everything fits anyway;
+// 2.3x SLOWER with a hit ratio < 1 (state larger than the carve-out: the persisting subset thrashes), which is why that
+// case is refused; slower with observation rows (the carve-out is taken from the streams' share).  The carve-out is a
+// device-wide limit that also shrinks the L2 available to everything else on the GPU (the policy network) — hence opt-in.
+static int enable_l2_window(rmv_env* e) {
+  int max_persist = 0, max_window = 0;
+  RMV_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device));
+  RMV_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, e->device));
+  const size_t state_bytes = (size_t)e->S * e->ld * sizeof(float);
+  if (max_persist <= 0 || max_window <= 0)
+    return fail(RMV_EINVAL, "this device has no persisting L2 carve-out");
+  // a window slightly larger than the carve-out is fine (the few lines that miss just stream); a partial window thrashes
+  const size_t carve = state_bytes < (size_t)max_persist ? state_bytes : (size_t)max_persist;
+  if (state_bytes > (size_t)max_window || (double)carve < 0.9 * (double)state_bytes)
+    return fail(RMV_EINVAL, "state (%zu bytes) exceeds the persisting L2 carve-out (%d bytes) / window (%d bytes): a partial "
+                            "window thrashes (measured 2.3x slower), refused", state_bytes, max_persist, max_window);
+  RMV_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+  e->l2_window = cudaAccessPolicyWindow{};
+  e->l2_window.base_ptr = e->state;
+  e->l2_window.num_bytes = state_bytes;
+  e->l2_window.hitRatio = (float)((double)carve / (double)state_bytes);
+  e->l2_window.hitProp = cudaAccessPropertyPersisting;
+  e->l2_window.missProp = cudaAccessPropertyStreaming;
+  e->l2_ready = 1;
+  return RMV_OK;
+}
+static void disable_l2_window(rmv_env* e) {
+  if (!e->l2_ready) return;
+  e->l2_ready = 0;
+  e->l2_window = cudaAccessPolicyWindow{};
+  cudaCtxResetPersistingL2Cache();                             // un-pin the state's lines
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+  cudaGetLastError();
+}
+// the window is attached to launches without observation rows only (measured: rows + carve-out is a net loss)
+static const cudaAccessPolicyWindow* l2_window_of(const rmv_env* e, const StepArgs& args) {
+  return (e->l2_ready && args.obs == nullptr) ? &e->l2_window : nullptr;
+}
+
 // Launch shape of the one-env-per-thread step kernel when rmv_set_tuning left it on auto.  Measured on B200
 // (profiles/r1b_sweep_block_prefetch.txt): what matters is whether one step's working set stays in the 126 MB
 // L2 between launches ("small": L2-bandwidth / issue bound) or streams from HBM ("big": latency bound for the
@@ -433,7 +494,7 @@ static bool default_prefetch(int kind, int64_t n) {
 }
 
 template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF>
-static cudaError_t launch_step_kvf(const StepArgs& args, cudaStream_t st) {
+static cudaError_t launch_step_kvf(const StepArgs& args, const cudaAccessPolicyWindow* win, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;
   const size_t smem = OBS ? (size_t)BLOCK * SP * sizeof(float) : 0;     // [warps][32][SP] transpose tiles
@@ -450,11 +511,20 @@ static cudaError_t launch_step_kvf(const StepArgs& args, cudaStream_t st) {
   cfg.blockDim = dim3(BLOCK);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this launch's ramp with the previous grid's tail
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this launch's ramp with the previous grid's tail
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (win) {
+    attr[na].id = cudaLaunchAttributeAccessPolicyWindow;               // state stays L2-resident between steps
+    attr[na].val.accessPolicyWindow = *win;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, k_step<KIND, V, OBS, TRACK, BLOCK, PREF>, args);
 }
 
@@ -499,35 +569,36 @@ static cudaError_t launch_step_tma_k(const rmv_env* e, const StepArgs& args, cud
 }
 
 template <int KIND, int V, int BLOCK, bool PREF>
-static cudaError_t launch_step_kvb(const StepArgs& args, cudaStream_t st) {
+static cudaError_t launch_step_kvb(const StepArgs& args, const cudaAccessPolicyWindow* win, cudaStream_t st) {
   const bool track = args.ep_return != nullptr;
-  if (args.obs) return track ? launch_step_kvf<KIND, V, true, true, BLOCK, PREF>(args, st) : launch_step_kvf<KIND, V, true, false, BLOCK, PREF>(args, st);
-  return track ? launch_step_kvf<KIND, V, false, true, BLOCK, PREF>(args, st) : launch_step_kvf<KIND, V, false, false, BLOCK, PREF>(args, st);
+  if (args.obs) return track ? launch_step_kvf<KIND, V, true, true, BLOCK, PREF>(args, win, st) : launch_step_kvf<KIND, V, true, false, BLOCK, PREF>(args, win, st);
+  return track ? launch_step_kvf<KIND, V, false, true, BLOCK, PREF>(args, win, st) : launch_step_kvf<KIND, V, false, false, BLOCK, PREF>(args, win, st);
 }
 
 template <int KIND, int V>
-static cudaError_t launch_step_kv(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
+static cudaError_t launch_step_kv(rmv_env* e, const StepArgs& args, cudaStream_t st) {
   if (args.n_steps > 1) {
     const int64_t groups = (args.n + V - 1) / V;
     k_rollout<KIND, V><<<blocks_for(groups, 128), 128, 0, st>>>(args);
     return cudaGetLastError();
   }
+  const cudaAccessPolicyWindow* win = l2_window_of(e, args);
   if constexpr (V == 1) {            // CTA size is a tuning knob of the one-env-per-thread kernel only
     const int block = e->block ? e->block : default_block(KIND, args.n);
     const bool pref = e->prefetch >= 0 ? e->prefetch != 0 : default_prefetch(KIND, args.n);
     if (pref) {
-      if (block == 512) return launch_step_kvb<KIND, 1, 512, true>(args, st);
-      if (block == 256) return launch_step_kvb<KIND, 1, 256, true>(args, st);
-      return launch_step_kvb<KIND, 1, 128, true>(args, st);
+      if (block == 512) return launch_step_kvb<KIND, 1, 512, true>(args, win, st);
+      if (block == 256) return launch_step_kvb<KIND, 1, 256, true>(args, win, st);
+      return launch_step_kvb<KIND, 1, 128, true>(args, win, st);
     }
-    if (block == 512) return launch_step_kvb<KIND, 1, 512, false>(args, st);
-    if (block == 256) return launch_step_kvb<KIND, 1, 256, false>(args, st);
+    if (block == 512) return launch_step_kvb<KIND, 1, 512, false>(args, win, st);
+    if (block == 256) return launch_step_kvb<KIND, 1, 256, false>(args, win, st);
   }
-  return launch_step_kvb<KIND, V, 128, false>(args, st);
+  return launch_step_kvb<KIND, V, 128, false>(args, win, st);
 }
 
 template <int KIND>
-static cudaError_t launch_step_k(const rmv_env* e, const StepArgs& args, int vec, cudaStream_t st) {
+static cudaError_t launch_step_k(rmv_env* e, const StepArgs& args, int vec, cudaStream_t st) {
   if (e->use_tma && vec == 1 && args.n_steps == 1 && !args.act_soa && aligned(args.act, 16))
     return launch_step_tma_k<KIND>(e, args, st);
   switch (vec) {

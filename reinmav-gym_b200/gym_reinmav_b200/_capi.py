@@ -57,6 +57,7 @@ SIGNATURES = {
     "rmv_set_host_chunks": (_i, [_vp, _i]),
     "rmv_set_kernel": (_i, [_vp, _i, _i]),
     "rmv_set_prefetch": (_i, [_vp, _i]),
+    "rmv_set_l2_persist": (_i, [_vp, _i]),
     "rmv_state_ptr": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "rmv_set_state": (_i, [_vp, _vp, _i, _vp]),
     "rmv_get_state": (_i, [_vp, _vp, _i, _vp]),

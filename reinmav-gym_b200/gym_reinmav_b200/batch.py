@@ -130,6 +130,10 @@ class QuadBatch:
         """Episode-word prefetch of the step kernel: -1 auto, 0 off, 1 on; results are identical."""
         check(lib().rmv_set_prefetch(self._h, int(mode)))
 
+    def set_l2_persist(self, mode=-1):
+        """L2 access-policy window on the state (state stays L2-resident between steps): -1 auto, 0 off, 1 on."""
+        check(lib().rmv_set_l2_persist(self._h, int(mode)))
+
     def set_host_chunks(self, chunks=0):
         check(lib().rmv_set_host_chunks(self._h, int(chunks)))
 

@@ -177,6 +177,33 @@ def test_every_cta_size_and_prefetch_mode_bitwise(torch, rmv, env_id, block, pre
                      prefetch=prefetch, track=bool(prefetch))
 
 
+def test_l2_persist_window_bitwise_and_refusal(torch, rmv):
+    """Opt-in L2 access-policy window on the state: same bits; a state larger than the device's persisting
+    carve-out is refused (a partial window thrashes) instead of silently running slower."""
+    env_id, n, seed = "quadrotor3d-slungload-v0", 128 * 301 + 9, 6
+    kind = KIND_OF_ID[env_id]
+    lo, hi = ACTION_BOUNDS[kind]
+    states = []
+    for mode in (0, 1):
+        b = rmv.QuadBatch(env_id, n, seed=seed)
+        b.set_l2_persist(mode)
+        b.reset()
+        rew, done, _ = _buffers(torch, n, STATE_DIM[kind])
+        act = torch.empty((n, 4), dtype=torch.float32, device="cuda:0")
+        for t in range(60):
+            rmv.fill_uniform_actions(act, n, 4, lo, hi, seed, step_index=t)
+            b.step(act, rew, done)
+        states.append((b.get_state(), rew.cpu().numpy(), b.get_episode_words()))
+        b.set_l2_persist(0)
+        b.close()
+    for x, y in zip(*states):
+        assert same_bits(x, y)
+    big = rmv.QuadBatch(env_id, 1 << 22, seed=seed)            # 268 MB of state: larger than any carve-out of a 126 MB L2
+    with pytest.raises(Exception, match="carve-out"):
+        big.set_l2_persist(1)
+    big.close()
+
+
 @pytest.mark.parametrize("n,track", [(1000 + 1, False), (127, True), (128 * 700 + 5, True), (65536, False)])
 @pytest.mark.parametrize("env_id", ENV_IDS)
 def test_tma_pipelined_kernel_bitwise(torch, rmv, env_id, n, track):

@@ -3,6 +3,7 @@ prefetch modes, obs rows + episode tracking on, ragged batch, the TMA variant, t
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "reinmav-gym_b200")]
+import numpy as np
 import torch
 import gym_reinmav_b200 as rmv
 from tools.sweep import BOUNDS
@@ -14,6 +15,8 @@ for env_id, (lo, hi) in BOUNDS.items():
         b.set_tuning(vec=1, block=block); b.set_prefetch(pref); b.set_kernel(tma=bool(tma))
         b.reset()
         A, S = b.action_dim, b.state_dim
+        # wide states: about a third of the envs finish on the very first step, so the re-draw pass runs in every CTA
+        b.set_state((np.random.RandomState(7).uniform(-1, 1, (n, S)) * np.array([1, 1, 1, 4], np.float32)[np.arange(S) % 4]).astype(np.float32))
         act = torch.empty((8, n, A), dtype=torch.float32, device=dev)
         for t in range(8):
             rmv.fill_uniform_actions(act[t], n, A, 3 * lo, 3 * hi, 1, step_index=t)      # wide actions: many resets

@@ -15,11 +15,16 @@ BOUNDS = {"quadrotor2d-v0": (-10, 10), "quadrotor2d-slungload-v0": (-10, 10), "q
           "quadrotor3d-slungload-v0": (-10, 10)}
 
 
-def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, ctas=0):
+def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, ctas=0, obs=0, track=0, l2=0):
     dev = "cuda:0"
-    b = rmv.QuadBatch(env_id, n, seed=0)
+    b = rmv.QuadBatch(env_id, n, seed=0, track_episodes=bool(track))
     b.set_tuning(vec=vec, block=block)
     b.set_kernel(tma=bool(tma), ctas_per_sm=ctas)
+    if l2:
+        try:
+            b.set_l2_persist(1)
+        except Exception as exc:        # state larger than the carve-out: refused by the library
+            print("# l2 window refused: %s" % exc)
     b.reset()
     A = b.action_dim
     lo, hi = BOUNDS[env_id]
@@ -35,12 +40,23 @@ def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, cta
     done = torch.empty((ring, n), dtype=torch.uint8, device=dev)
     lay = 1 if layout == "soa" else 0
 
-    def run(k):
-        left = k
-        while left > 0:
-            m = min(left, ring)
-            b.step_many(m, acts, rew, done, out_ld=n, layout=lay, act_ld=n, fused=fused)
-            left -= m
+    if obs:
+        # obs rows [N][S] written by the kernel every step (the VecEnv / rollout-buffer variant); one C-ABI call per step
+        obs_ring = torch.empty((2, n, b.state_dim), dtype=torch.float32, device=dev)
+        ap, rp, dp = [acts[t].data_ptr() for t in range(ring)], [rew[t].data_ptr() for t in range(ring)], [done[t].data_ptr() for t in range(ring)]
+        op = [obs_ring[t].data_ptr() for t in range(2)]
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def run(k):
+            for t in range(k):
+                b.step(ap[t % ring], rp[t % ring], dp[t % ring], obs=op[t & 1], layout=lay, act_ld=n, stream=stream)
+    else:
+        def run(k):
+            left = k
+            while left > 0:
+                m = min(left, ring)
+                b.step_many(m, acts, rew, done, out_ld=n, layout=lay, act_ld=n, fused=fused)
+                left -= m
 
     run(ring)
     torch.cuda.synchronize()
@@ -52,9 +68,10 @@ def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, cta
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / steps)
+    b_state_dim = b.state_dim
     b.close()
     sps = n / (best * 1e-3)
-    gbs = sps * BYTES[env_id] / 1e9
+    gbs = sps * (BYTES[env_id] + (4 * b_state_dim if obs else 0) + (8 if track else 0)) / 1e9
     return best * 1e3, sps, gbs, gbs / peak
 
 
@@ -71,6 +88,9 @@ def main():
     ap.add_argument("--peak", type=float, default=6458.4)
     ap.add_argument("--tma", default="0", help="comma list of 0/1: register-path / TMA-pipelined kernel")
     ap.add_argument("--ctas", default="0", help="comma list: persistent CTAs per SM for the TMA kernel (0 = max)")
+    ap.add_argument("--obs", type=int, default=0, help="1: the kernel also writes row-per-env observations [N][S] every step")
+    ap.add_argument("--track", type=int, default=0, help="1: episode tracking (Monitor) on")
+    ap.add_argument("--l2", type=int, default=0, help="1: opt-in L2 access-policy window on the state (rmv_set_l2_persist)")
     args = ap.parse_args()
     print("%-26s %9s %3s %5s %4s %5s %9s %11s %9s %6s" % ("env", "n", "vec", "block", "lay", "fused", "us/step", "steps/s", "GB/s(alg)", "frac"))
     for env_id in args.envs.split(","):
@@ -82,8 +102,8 @@ def main():
                             ring = max(2, min(args.ring, int(6e9 // (n * 4 * 6))))
                             for tma in (int(x) for x in args.tma.split(",")):
                                 for ctas in (int(x) for x in args.ctas.split(",")) if tma else (0,):
-                                    us, sps, gbs, frac = time_cfg(env_id, n, vec, block, layout, bool(fused), args.steps, ring, args.peak, tma, ctas)
-                                    print("%-26s %9d %3d %5d %4s %5d %9.2f %11.4g %9.1f %6.3f  tma=%d ctas=%d" % (env_id, n, vec, block, layout, fused, us, sps, gbs, frac, tma, ctas), flush=True)
+                                    us, sps, gbs, frac = time_cfg(env_id, n, vec, block, layout, bool(fused), args.steps, ring, args.peak, tma, ctas, args.obs, args.track, args.l2)
+                                    print("%-26s %9d %3d %5d %4s %5d %9.2f %11.4g %9.1f %6.3f  tma=%d ctas=%d obs=%d track=%d l2=%d" % (env_id, n, vec, block, layout, fused, us, sps, gbs, frac, tma, ctas, args.obs, args.track, args.l2), flush=True)
 
 
 if __name__ == "__main__":
