@@ -109,6 +109,7 @@ struct rmv_env {
   int tma_ctas_per_sm = 0; // 0 = as many as fit
 };
 
+static int g_ctas_cap = getenv("RMV_CTAS_PER_SM") ? atoi(getenv("RMV_CTAS_PER_SM")) : 0;
 static int enable_l2_window(rmv_env* e);
 static void disable_l2_window(rmv_env* e);
 
@@ -497,8 +498,12 @@ template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF>
 static cudaError_t launch_step_kvf(const StepArgs& args, const cudaAccessPolicyWindow* win, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;
-  const size_t smem = OBS ? (size_t)BLOCK * SP * sizeof(float) : 0;     // [warps][32][SP] transpose tiles
-  if (OBS && smem > 48 * 1024) {
+  size_t smem = OBS ? (size_t)BLOCK * SP * sizeof(float) : 0;           // [warps][32][SP] transpose tiles
+  if (g_ctas_cap > 0) {               // developer experiment: cap resident CTAs per SM by padding dynamic shared memory
+    const size_t per = (size_t)(227 * 1024) / (size_t)g_ctas_cap - 2048;
+    if (per > smem) smem = per & ~(size_t)127;
+  }
+  if (smem > 48 * 1024) {
     static bool raised = false;      // per instantiation
     if (!raised) {
       cudaError_t e = cudaFuncSetAttribute(k_step<KIND, V, OBS, TRACK, BLOCK, PREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -217,6 +217,7 @@ __device__ __forceinline__ float uniform_pm1(uint32_t bits) {
 constexpr int step_min_ctas(int kind, int v, bool obs, bool track, int block) {
   // resident-thread target per SM: 2048 (<= 32 registers) for the small-state kinds, 1536 for
   // quadrotor2d-slungload, 1280 when the obs copy / tracking / the 16-component state need registers
+  if (v == 2) return (obs || track) ? 1 : 1024 / block;     // 64 registers: as many envs in flight per SM as V = 1 at 32
   if (v != 1) return 1;
   const int threads = (obs || track || kind == QUAD3D_SLUNG) ? 1280 : (kind == QUAD2D_SLUNG ? 1536 : 2048);
   return threads / block > 0 ? threads / block : 1;
