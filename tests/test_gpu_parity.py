@@ -177,6 +177,83 @@ def test_every_cta_size_and_prefetch_mode_bitwise(torch, rmv, env_id, block, pre
                      prefetch=prefetch, track=bool(prefetch))
 
 
+@pytest.mark.parametrize("vec", [1, 2])
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_fused_rollout_equals_single_steps(torch, rmv, env_id, vec):
+    """rmv_step_many(fused=1) — T steps in one launch, state in registers, reset inside the loop — against T
+    single-step launches: same state, rewards, done flags, episode words and episode statistics, bit for bit.
+    Wide initial states make a third of the envs finish at once, the batch is ragged, tracking is on."""
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    lo, hi = ACTION_BOUNDS[kind]
+    n, T, seed = 128 * 41 + 18, 48, 8          # even: the two-env-per-thread variant needs out_ld % 2 == 0
+    rng = np.random.RandomState(3)
+    start = rng.uniform(-3, 3, (n, S)).astype(np.float32)
+    dev = "cuda:0"
+    acts = torch.empty((T, n, A), dtype=torch.float32, device=dev)
+    for t in range(T):
+        rmv.fill_uniform_actions(acts[t], n, A, lo, hi, seed, step_index=t)
+    out = []
+    for fused in (False, True):
+        b = rmv.QuadBatch(env_id, n, seed=seed, track_episodes=True)
+        b.set_tuning(vec=vec)
+        b.reset()
+        b.set_state(start)
+        rew = torch.empty((T, n), dtype=torch.float32, device=dev)
+        done = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        b.step_many(T, acts, rew, done, out_ld=n, layout=0, fused=fused)
+        out.append((b.get_state(), rew.cpu().numpy(), done.cpu().numpy(), b.get_episode_words(), b.episode_stats()))
+        b.close()
+    (s0, r0, d0, w0, st0), (s1, r1, d1, w1, st1) = out
+    assert d0[0].mean() > 0.1                     # the mass-finish case really happened
+    assert np.array_equal(d0, d1) and same_bits(r0, r1) and same_bits(s0, s1) and np.array_equal(w0, w1)
+    assert st0["episodes"] == st1["episodes"] > 0 and st0["length_sum"] == st1["length_sum"]
+    assert abs(st0["return_sum"] - st1["return_sum"]) <= 1e-9 * max(1.0, abs(st0["return_sum"]))   # atomic double sums
+
+
+def test_step_is_cuda_graph_capturable(torch, rmv):
+    """rmv_step only enqueues kernels on the caller's stream (no host sync, no allocation), so a training loop can
+    capture it in a CUDA graph together with its policy: 8 captured steps replayed 3 times == 24 plain steps.
+    (Untracked handle: with RMV_TRACK_EPISODES the step counter is a launch argument and would go stale in replays.)"""
+    env_id, n, seed, K = "quadrotor3d-v0", 128 * 50 + 3, 11, 8
+    dev = "cuda:0"
+    acts = torch.empty((K, n, 4), dtype=torch.float32, device=dev)
+    for t in range(K):
+        rmv.fill_uniform_actions(acts[t], n, 4, 0.0, 10.0, seed, step_index=t)
+    rew = torch.empty((K, n), dtype=torch.float32, device=dev)
+    done = torch.empty((K, n), dtype=torch.uint8, device=dev)
+    obs = torch.empty((n, 10), dtype=torch.float32, device=dev)
+
+    def steps(b):
+        for t in range(K):
+            b.step(acts[t], rew[t], done[t], obs=obs if t == K - 1 else None)
+
+    ref = rmv.QuadBatch(env_id, n, seed=seed)
+    ref.reset()
+    for _ in range(3):
+        steps(ref)
+    torch.cuda.synchronize()
+    want = (ref.get_state(), rew.cpu().numpy().copy(), done.cpu().numpy().copy(), obs.cpu().numpy().copy(), ref.get_episode_words())
+    ref.close()
+
+    b = rmv.QuadBatch(env_id, n, seed=seed)
+    b.reset()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            steps(b)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    got = (b.get_state(), rew.cpu().numpy(), done.cpu().numpy(), obs.cpu().numpy(), b.get_episode_words())
+    b.close()
+    for x, y in zip(want, got):
+        assert same_bits(x, y)
+
+
 def test_l2_persist_window_bitwise_and_refusal(torch, rmv):
     """Opt-in L2 access-policy window on the state: same bits; a state larger than the device's persisting
     carve-out is refused (a partial window thrashes) instead of silently running slower."""
