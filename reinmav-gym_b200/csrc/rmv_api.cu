@@ -639,6 +639,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
       ra.obs = obs; ra.n = cn;
       volatile double stop = t + 1.0 / 100, next = t + 1.0 / 5000;
       ra.n_sub = (int)ceil((stop - t) / (1.0 / 5000));     // NumPy's arange length ...
+      if (ra.n_sub > kReinmavMaxSub) return fail(RMV_EINVAL, "reinmav substep count %d exceeds %d", ra.n_sub, kReinmavMaxSub);
       ra.delta = next - t;                                  // ... and fill increment
       ra.t0 = t;
       reinmav_inverse_inertia(ra.inv_inertia);
