@@ -447,29 +447,40 @@ def measure_extras(torch, rmv, args, local):
     b.close()
 
     # BASELINE config 4: quadrotor2d-v0, N = 2^20, PPO2 rollout shape — obs rows [N,5] out, actions [N,2]
-    # ~ N(0,1) in (baselines' initial diagonal Gaussian), T = 128 steps into [T, N, ...] device buffers
+    # ~ N(0,1) in (baselines' initial diagonal Gaussian), T = 128 steps into [T, N, ...] device buffers.
+    # "travelling": the rollout buffer carries the state (rmv_step_rows: read obs[t], write obs[t+1]);
+    # "in_place": tiled state in the handle + a row copy per step (rmv_step with obs rows).  Also for quadrotor3d.
     import gym_reinmav_b200.rollout as rollout
-    n, T = 1 << 20, 128
-    venv = rmv.QuadVecEnv("quadrotor2d-v0", n, device=local, seed=SEED, monitor=False)
-    buf = rollout.RolloutBuffer(venv, T)
-    buf.actions.normal_()
-    policy = lambda obs, _it=iter(range(10 ** 9)): buf.action_views[next(_it) % T]      # pre-drawn actions: env-side cost only
-    buf.collect(policy)
-    torch.cuda.synchronize()
-    best = 1e30
-    for _ in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); buf.collect(policy); e1.record()
-        torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1) / T)
-    sps = n / (best * 1e-3)
-    bytes_with_obs = 53 + 4 * 5
-    out["ppo2_rollout_shape_quadrotor2d"] = {
-        "env_id": "quadrotor2d-v0", "n_envs": n, "n_steps": T, "us_per_step": best * 1e3, "env_steps_per_s": sps,
-        "bytes_per_env_step": bytes_with_obs, "algorithmic_GBps": sps * bytes_with_obs / 1e9,
-        "frac_of_hbm_peak": sps * bytes_with_obs / 1e9 / peak,
-        "mode": "one launch per step from Python (ctypes), obs rows written into obs[t+1] of a [T+1,N,5] buffer"}
-    venv.close()
+    for env_id, key in (("quadrotor2d-v0", "ppo2_rollout_shape_quadrotor2d"), (ENV_ID, "ppo2_rollout_shape_quadrotor3d")):
+        n, T = 1 << 20, 128
+        Sd = {"quadrotor2d-v0": 5, ENV_ID: 10}[env_id]
+        for travelling in (False, True):
+            venv = rmv.QuadVecEnv(env_id, n, device=local, seed=SEED, monitor=False)
+            buf = rollout.RolloutBuffer(venv, T, travelling=travelling)
+            buf.actions.normal_()
+            if env_id == ENV_ID:
+                buf.actions.mul_(2.5).add_(5.0)          # around the middle of quadrotor3d's [0, 10) action box
+            policy = lambda obs, _it=iter(range(10 ** 9)): buf.action_views[next(_it) % T]      # pre-drawn actions: env-side cost only
+            buf.collect(policy)
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); buf.collect(policy); e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) / T)
+            sps = n / (best * 1e-3)
+            nbytes = bytes_of[env_id] + (0 if travelling else 4 * Sd)
+            out[key + ("_travelling_state" if travelling else "")] = {
+                "env_id": env_id, "n_envs": n, "n_steps": T, "us_per_step": best * 1e3, "env_steps_per_s": sps,
+                "bytes_per_env_step": nbytes, "algorithmic_GBps": sps * nbytes / 1e9,
+                "frac_of_hbm_peak": sps * nbytes / 1e9 / peak,
+                "mode": ("one launch per step from Python (ctypes); state read from obs[t], written to obs[t+1] of a [T+1,N,%d] buffer "
+                         "(rmv_step_rows)" if travelling else
+                         "one launch per step from Python (ctypes); tiled state in place + obs rows written into obs[t+1] of a "
+                         "[T+1,N,%d] buffer (rmv_step)") % Sd}
+            venv.close()
+            del buf
     return out
 
 

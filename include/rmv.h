@@ -188,6 +188,17 @@ RMV_API int rmv_step(rmv_env* env, const float* act_dev, int act_layout, int64_t
              float* reward_dev, uint8_t* done_dev, float* obs_aos_dev, int auto_reset,
              void* stream);
 
+/* step() on ROW-MAJOR state ("travelling state"): the state of env i is read from rows_in_dev[i][0..S) and the new
+ * state (for a re-drawn env: its reset state) is written to rows_out_dev[i][0..S); the handle's own tiled state is
+ * neither read nor written, its episode words / tracking buffers are used and updated as in rmv_step.  Made for
+ * on-device rollout buffers (run.py:63-68 -> ppo2 Runner): obs == state in the reference (quadrotor3d.py:104), so
+ * step t reads obs[t] and writes obs[t+1] — 4(2S+A+1)+1 bytes per env instead of the 4(3S+A+1)+1 of rmv_step with
+ * observation rows, and the rows read are the ones the previous step just wrote.  rows_in_dev == rows_out_dev is
+ * allowed (in place).  Same results as rmv_step bit for bit.  To continue with rmv_step afterwards, load the last
+ * rows into the handle with rmv_set_state(env, rows, 1, stream). */
+RMV_API int rmv_step_rows(rmv_env* env, const float* rows_in_dev, const float* act_dev, int act_layout, int64_t act_ld,
+                          float* reward_dev, uint8_t* done_dev, float* rows_out_dev, int auto_reset, void* stream);
+
 /* T consecutive steps with auto-reset from a pre-generated action block (random-policy or
  * replayed rollouts).  act_dev is [T][A][act_ld] (SOA) or [T][n][A] (AOS); reward_dev / done_dev
  * are [T][out_ld] or NULL.

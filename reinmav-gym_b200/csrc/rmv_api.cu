@@ -533,6 +533,30 @@ static cudaError_t launch_step_kvf(const StepArgs& args, const cudaAccessPolicyW
   return cudaLaunchKernelEx(&cfg, k_step<KIND, V, OBS, TRACK, BLOCK, PREF>, args);
 }
 
+template <int KIND, bool TRACK, int BLOCK>
+static cudaError_t launch_step_rows_kb(const StepArgs& args, cudaStream_t st) {
+  constexpr int S = Dims<KIND>::S;
+  constexpr int SP = (S % 2 == 0) ? S + 1 : S;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks_for(args.n, BLOCK));
+  cfg.blockDim = dim3(BLOCK);
+  cfg.dynamicSmemBytes = (size_t)BLOCK * SP * sizeof(float);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_step_rows<KIND, TRACK, BLOCK>, args);
+}
+template <int KIND>
+static cudaError_t launch_step_rows_k(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
+  const bool track = args.ep_return != nullptr;
+  const int block = e->block ? e->block : (KIND == QUAD2D ? 256 : 128);
+  if (block == 256) return track ? launch_step_rows_kb<KIND, true, 256>(args, st) : launch_step_rows_kb<KIND, false, 256>(args, st);
+  return track ? launch_step_rows_kb<KIND, true, 128>(args, st) : launch_step_rows_kb<KIND, false, 128>(args, st);
+}
+
 // TMA-pipelined persistent variant (V = 1, row-per-env actions, 16-byte aligned action buffer)
 constexpr int kTmaStages = 3;
 template <int KIND, bool OBS, bool TRACK>
@@ -708,6 +732,44 @@ extern "C" RMV_API int rmv_step(rmv_env* env, const float* act_dev, int act_layo
   RMV_ON_DEVICE(env->device);
   return launch_step(env, act_dev, act_layout, act_ld, 0, reward_dev, done_dev, env->n, obs_aos_dev, auto_reset, 1,
                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" RMV_API int rmv_step_rows(rmv_env* env, const float* rows_in_dev, const float* act_dev, int act_layout, int64_t act_ld,
+                                     float* reward_dev, uint8_t* done_dev, float* rows_out_dev, int auto_reset, void* stream) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(env->kind != RMV_REINMAV, "reinmav-v0 has no row-state step");
+  RMV_REQUIRE(rows_in_dev != nullptr && rows_out_dev != nullptr && act_dev != nullptr && reward_dev != nullptr && done_dev != nullptr,
+              "NULL argument");
+  RMV_REQUIRE(act_layout == RMV_ACT_AOS || act_layout == RMV_ACT_SOA, "bad act_layout %d", act_layout);
+  if (act_layout == RMV_ACT_SOA) RMV_REQUIRE(act_ld >= env->n, "act_ld (%lld) < n_envs", (long long)act_ld);
+  RMV_REQUIRE(aligned(rows_in_dev, 4) && aligned(rows_out_dev, 4) && aligned(reward_dev, 4), "float buffers must be 4-byte aligned");
+  RMV_REQUIRE(act_layout == RMV_ACT_SOA || aligned(act_dev, env->A * 4), "row-per-env actions must be aligned to one row (%d bytes)", env->A * 4);
+  RMV_ON_DEVICE(env->device);
+  rmv_env* e = env;
+  StepArgs a{};
+  a.state = e->state; a.episode = e->episode;
+  a.act = act_dev; a.reward = reward_dev; a.done = done_dev; a.obs = rows_out_dev; a.rows_in = rows_in_dev;
+  a.ep_return = e->ep_return; a.ep_start = e->ep_start; a.last_return = e->last_return; a.last_length = e->last_length;
+  a.cum_return = e->cum_return; a.cum_length = e->cum_length; a.fin_count = e->fin_count;
+  a.n = e->n; a.act_ld = act_ld; a.out_ld = e->n; a.act_step_stride = 0;
+  a.env_id_offset = e->env_id_offset; a.seed = e->seed; a.step_index = e->step_index;
+  for (uint32_t r = 0; r < 10; ++r) {
+    a.ks[2 * r] = (uint32_t)e->seed + r * PHILOX_W0;
+    a.ks[2 * r + 1] = (uint32_t)(e->seed >> 32) + r * PHILOX_W1;
+  }
+  a.n_steps = 1; a.act_soa = (act_layout == RMV_ACT_SOA); a.auto_reset = auto_reset ? 1 : 0;
+  a.P = e->dp;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t err;
+  switch (e->kind) {
+    case RMV_QUAD2D: err = launch_step_rows_k<QUAD2D>(e, a, st); break;
+    case RMV_QUAD2D_SLUNG: err = launch_step_rows_k<QUAD2D_SLUNG>(e, a, st); break;
+    case RMV_QUAD3D: err = launch_step_rows_k<QUAD3D>(e, a, st); break;
+    default: err = launch_step_rows_k<QUAD3D_SLUNG>(e, a, st); break;
+  }
+  if (err != cudaSuccess) return fail(RMV_ECUDA, "row-state step kernel launch failed: %s", cudaGetErrorString(err));
+  e->step_index += 1u;
+  return RMV_OK;
 }
 
 extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act_dev, int act_layout, int64_t act_ld,

@@ -34,7 +34,8 @@ struct StepArgs {
   const float* act;        // see act_soa
   float* reward;           // [T][out_ld] or nullptr
   uint8_t* done;           // [T][out_ld] or nullptr
-  float* obs;              // [n][S] or nullptr (single-step kernel only)
+  float* obs;              // [n][S] or nullptr (single-step kernel only); k_step_rows: the rows the new state goes to
+  const float* rows_in;    // k_step_rows only: [n][S] rows the state comes from (may alias obs)
   // optional episode tracking (RMV_TRACK_EPISODES), all [n_pad]
   float* ep_return;        // running return of the current episode
   uint32_t* ep_start;      // step index at which the current episode began
@@ -404,6 +405,129 @@ k_step(const StepArgs a) {
         if (OBS) orow[l] = x;
       }
     }
+  }
+}
+
+// ---- single step on row-major state ("travelling state") ------------------------------------------
+// The state comes from rows_in [n][S] and goes to obs [n][S]; the handle's tiled state is not touched.  This is
+// the shape of an on-device rollout (gym_reinmav/run.py:63-68 -> ppo2 Runner): step t reads the observation rows
+// obs[t] — which ARE the state (obs == state in the reference, quadrotor3d.py:104) — and writes obs[t+1], so a
+// step moves 4(2S + A + 1) + 1 bytes per env instead of the 4(3S + A + 1) + 1 of "tiled state in place + a row
+// copy", and the rows it reads are the ones the previous step just wrote (still in L2).  rows_in == obs is the
+// in-place form.  Same arithmetic, same reset pass, same results as k_step.
+//
+// A warp owns 32 consecutive rows = 32*S contiguous floats: loaded with S coalesced 128-byte requests into a
+// shared tile [32][S|1] (odd pitch), read back one row per thread; stored the same way in reverse.
+template <int KIND, bool TRACK, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, step_min_ctas(KIND, 1, true, TRACK, BLOCK))
+k_step_rows(const StepArgs a) {
+  constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
+  constexpr int NB = (S + 3) / 4;
+  constexpr int SP = (S % 2 == 0) ? S + 1 : S;
+  __shared__ uint32_t redraw_total;
+  __shared__ uint16_t redraw_list[BLOCK];
+  __shared__ uint32_t redraw_episode[BLOCK];
+  extern __shared__ float tile[];                  // [warps][32][SP]
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) redraw_total = 0u;
+  const uint32_t n = (uint32_t)a.n;
+  const uint32_t cta_e0 = blockIdx.x * (uint32_t)BLOCK;
+  const uint32_t e = cta_e0 + tid, warp_e0 = e - lane;
+  const bool active = e < n;
+  float* const my = tile + warp * 32 * SP;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // rows in: coalesced, transposed through the warp's tile
+  {
+    const float* const src = a.rows_in + (size_t)warp_e0 * S;
+    const uint32_t rows_here = warp_e0 < n ? (n - warp_e0 < 32u ? n - warp_e0 : 32u) : 0u;
+#pragma unroll
+    for (int i = (int)lane; i < 32 * S; i += 32) {
+      const int r = i / S, c = i - r * S;
+      my[r * SP + c] = ((uint32_t)r < rows_here) ? src[i] : 0.0f;
+    }
+  }
+  float act[1][A];
+  float ep_ret = 0.0f;
+  if (active) {
+    load_actions<KIND, 1>(a, a.act, (int64_t)e, true, act);
+    if (TRACK) ep_ret = a.ep_return[e];
+  } else {
+#pragma unroll
+    for (int c = 0; c < A; ++c) act[0][c] = 0.0f;
+  }
+  __syncwarp();
+  float s[S];
+#pragma unroll
+  for (int c = 0; c < S; ++c) s[c] = my[lane * SP + c];
+  __syncthreads();                                 // redraw_total = 0 is visible
+
+  bool redraw = false;
+  if (active) {
+    float pos_sq, vel_sq, n_rew;
+    EnvStep<KIND>::run(a.P, s, act[0], pos_sq, vel_sq, n_rew);
+    const bool done = is_done(a.P, pos_sq, vel_sq);
+    float r = -n_rew;
+    if (done) {
+      // rare lane: the ever-done flag decides the terminal reward (quadrotor3d.py:112-122)
+      const uint32_t w = a.episode[e];
+      r = reward_of(a.P, true, (w & kEverDone) != 0u, n_rew);
+      const uint32_t count = (w & ~kEverDone) + (a.auto_reset ? 1u : 0u);
+      a.episode[e] = count | kEverDone;
+      if (a.auto_reset) {
+        redraw = true;
+        const uint32_t slot = atomicAdd(&redraw_total, 1u);
+        redraw_list[slot] = (uint16_t)tid;
+        redraw_episode[slot] = count;
+      }
+      if (TRACK) {
+        const float total = ep_ret + r;
+        const uint32_t now = a.step_index + 1u;
+        const uint32_t len = now - a.ep_start[e];
+        a.last_return[e] = total;
+        a.last_length[e] = len;
+        a.cum_return[e] += (double)total;
+        a.cum_length[e] += len;
+        a.fin_count[e] += 1u;
+        a.ep_start[e] = now;
+        ep_ret = -r;
+      }
+    }
+    __stcs(a.reward + e, r);
+    __stcs(reinterpret_cast<unsigned char*>(a.done) + e, (unsigned char)(done ? 1 : 0));
+    if (TRACK) a.ep_return[e] = ep_ret + r;
+  }
+
+  // rows out (plain stores: the next step reads them); rows of re-drawn envs are written by the re-draw pass
+  {
+    const uint32_t skip = __ballot_sync(0xffffffffu, redraw);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < S; ++c) my[lane * SP + c] = s[c];
+    __syncwarp();
+    float* const dst = a.obs + (size_t)warp_e0 * S;
+#pragma unroll
+    for (int i = (int)lane; i < 32 * S; i += 32) {
+      const int r = i / S, c = i - r * S;
+      if (warp_e0 + (uint32_t)r < n && !((skip >> r) & 1u)) dst[i] = my[r * SP + c];
+    }
+  }
+
+  __syncthreads();
+  const uint32_t pairs = redraw_total * NB;
+  for (uint32_t i = tid; i < pairs; i += BLOCK) {
+    const uint32_t slot = i / NB, b = i - slot * NB;
+    const uint32_t er = cta_e0 + redraw_list[slot];
+    const uint64_t id = (uint64_t)a.env_id_offset + er;
+    uint32_t w4[4];
+    philox4x32_10_ks((uint32_t)id, (uint32_t)(id >> 32), redraw_episode[slot], ((STREAM_RESET_BASE + (uint32_t)KIND) << 8) | b,
+                     a.ks, w4);
+    float* const orow = a.obs + (size_t)er * S + 4 * b;
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if (S % 4 == 0 || 4 * b + l < S) orow[l] = uniform_pm1(w4[l]);
   }
 }
 

@@ -65,6 +65,7 @@ SIGNATURES = {
     "rmv_get_episode": (_i, [_vp, _vp, _i, _vp]),
     "rmv_reset": (_i, [_vp, _vp, _vp, _vp]),
     "rmv_step": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp]),
+    "rmv_step_rows": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp]),
     "rmv_step_many": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp, _i64, _i, _vp]),
     "rmv_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rmv_reset_host": (_i, [_vp, _vp, _vp]),

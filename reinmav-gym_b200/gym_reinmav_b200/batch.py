@@ -147,6 +147,17 @@ class QuadBatch:
                              1 if auto_reset else 0, _stream(stream, self.device)))
         self.launches += 1
 
+    def step_rows(self, rows_in, actions, reward, done, rows_out, auto_reset=True, layout=ACT_AOS, act_ld=0, stream=None):
+        """Step on row-major state: read [N, S] rows_in, write [N, S] rows_out (may alias); the handle's own tiled
+        state is not touched (``set_state_device(rows_out)`` re-synchronises it)."""
+        check(lib().rmv_step_rows(self._h, _ptr(rows_in), _ptr(actions), layout, int(act_ld), _ptr(reward), _ptr(done),
+                                  _ptr(rows_out), 1 if auto_reset else 0, _stream(stream, self.device)))
+        self.launches += 1
+
+    def set_state_device(self, rows, stream=None):
+        """Load [N, S] device rows into the handle's tiled state."""
+        check(lib().rmv_set_state(self._h, _ptr(rows), 1, _stream(stream, self.device)))
+
     def step_many(self, n_steps, actions, reward=None, done=None, out_ld=0, layout=ACT_SOA, act_ld=0, fused=False,
                   stream=None):
         check(lib().rmv_step_many(self._h, int(n_steps), _ptr(actions), layout, int(act_ld), _ptr(reward), _ptr(done),

@@ -5,13 +5,23 @@ fills ``mb_obs, mb_actions, mb_rewards, mb_dones`` of shape ``[nsteps, nenv, ...
 ``actions = model.step(obs); obs, rewards, dones, infos = env.step(actions)``.  Here the buffers live in
 HBM and the step kernel writes straight into them: step t reads ``actions[t]``, writes ``rewards[t]``,
 ``dones[t]`` and the observation rows ``obs[t + 1]`` — no staging copy, no host hop.
+
+``travelling=True`` (opt-in): obs == state in the reference (quadrotor3d.py:104), so the rollout buffer itself
+can carry the state — step t READS its state from ``obs[t]`` and writes the new one to ``obs[t + 1]``
+(``rmv_step_rows``); the handle's tiled state is not streamed at all during the rollout and is re-synchronised
+from ``obs[T]`` once at the end.  Per env-step that is 4(2S+A+1)+1 bytes instead of 4(3S+A+1)+1, and the rows
+read are the ones the previous step just wrote — but both directions now go through the shared-memory transpose:
+measured at N = 2^20 it is 15 % faster for quadrotor3d (18.7 vs 22.1 us per step), 5-7 % for the planar kinds,
+8 % SLOWER for quadrotor3d-slungload and slower with episode tracking (profiles/r1b_sweep_rows.txt), hence not
+the default.  Same results bit for bit (tests/test_gpu_vec_env.py).
 """
 import torch
 
 
 class RolloutBuffer:
-    def __init__(self, venv, n_steps):
+    def __init__(self, venv, n_steps, travelling=False):
         self.venv, self.T = venv, int(n_steps)
+        self.travelling = bool(travelling) and venv.batch.action_dim > 0
         n, S, A = venv.num_envs, venv.batch.state_dim, venv.batch.action_dim
         dev = "cuda:%d" % venv.device
         self.obs = torch.empty((self.T + 1, n, S), dtype=torch.float32, device=dev)      # obs[t] is what the policy sees at step t
@@ -43,6 +53,14 @@ class RolloutBuffer:
         b = self.venv.batch
         stream = torch.cuda.current_stream(self.venv.device).cuda_stream
         obs_t, act_t, obs_p, act_p, rew_p, done_p = self.obs_views, self.action_views, self._obs_p, self._act_p, self._rew_p, self._done_p
+        if self.travelling:
+            for t in range(self.T):
+                a = policy(obs_t[t])
+                if a.data_ptr() != act_p[t]:
+                    act_t[t].copy_(a)
+                b.step_rows(obs_p[t], act_p[t], rew_p[t], done_p[t], obs_p[t + 1], auto_reset=True, stream=stream)
+            b.set_state_device(obs_p[self.T], stream=stream)       # the handle's own state follows the rollout
+            return self
         for t in range(self.T):
             a = policy(obs_t[t])
             if a.data_ptr() != act_p[t]:

@@ -255,7 +255,62 @@ def test_ppo2_shaped_rollout_buffers(rmv):
     assert int(buf.dones.sum()) > 50
     buf.roll()
     assert torch.equal(buf.obs[0], buf.obs[T])
+    assert same_bits(venv.batch.get_state(), buf.obs[T].cpu().numpy())
     venv.close()
+
+
+@pytest.mark.parametrize("env_id", ["quadrotor2d-v0", "quadrotor2d-slungload-v0", "quadrotor3d-v0", "quadrotor3d-slungload-v0"])
+def test_travelling_state_rollout_equals_in_place_rollout(rmv, env_id):
+    """rmv_step_rows (state read from obs[t], written to obs[t+1]; the handle's tiled state untouched) against
+    rmv_step with observation rows: same obs, rewards, dones, episode words, per-env episode statistics and final
+    handle state, bit for bit; ragged batch, tracking on, two consecutive rollouts; plus the in-place form
+    (rows_in == rows_out)."""
+    import torch
+    n, T, seed = 128 * 29 + 57, 80, 21
+    outs = []
+    for travelling in (False, True):
+        venv = rmv.QuadVecEnv(env_id, n, seed=seed, monitor=True)
+        buf = rmv.RolloutBuffer(venv, T, travelling=travelling)
+        assert buf.travelling == travelling
+        A = venv.batch.action_dim
+        lo, hi = float(venv.action_space.low[0]), float(venv.action_space.high[0])
+        for rollout in range(2):
+            for t in range(T):
+                rmv.fill_uniform_actions(buf.actions[t], n, A, 2 * lo, 2 * hi, seed, step_index=rollout * T + t)
+            buf.collect(lambda obs, _it=iter(range(T)): buf.action_views[next(_it)])
+            if rollout == 0:
+                first = (buf.obs.cpu().numpy().copy(), buf.rewards.cpu().numpy().copy(), buf.dones.cpu().numpy().copy())
+                buf.roll()
+        outs.append((first, buf.obs.cpu().numpy(), buf.rewards.cpu().numpy(), buf.dones.cpu().numpy(),
+                     venv.batch.get_state(), venv.batch.get_episode_words(), venv.batch.episode_stats()["episodes"]))
+        venv.close()
+    a, b = outs
+    assert int(a[3].sum()) > 50
+    for x, y in zip(a[0][:2], b[0][:2]):
+        assert same_bits(x, y)
+    for i in (1, 2, 4):
+        assert same_bits(a[i], b[i]), i
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[0][2], b[0][2])
+    assert np.array_equal(a[5], b[5]) and a[6] == b[6]
+
+    # in place: one [N, S] buffer is both source and destination
+    b1 = rmv.QuadBatch(env_id, n, seed=seed)
+    b2 = rmv.QuadBatch(env_id, n, seed=seed)
+    S, A = b1.state_dim, b1.action_dim
+    rows = torch.empty((n, S), dtype=torch.float32, device="cuda:0")
+    obs = torch.empty((n, S), dtype=torch.float32, device="cuda:0")
+    b1.reset(obs=rows)
+    b2.reset()
+    act = torch.empty((n, A), dtype=torch.float32, device="cuda:0")
+    r1 = torch.empty(n, dtype=torch.float32, device="cuda:0"); r2 = torch.empty_like(r1)
+    d1 = torch.empty(n, dtype=torch.uint8, device="cuda:0"); d2 = torch.empty_like(d1)
+    for t in range(60):
+        rmv.fill_uniform_actions(act, n, A, 2 * lo, 2 * hi, seed, step_index=t)
+        b1.step_rows(rows, act, r1, d1, rows)
+        b2.step(act, r2, d2, obs=obs)
+        assert torch.equal(rows.view(torch.int32), obs.view(torch.int32)) and torch.equal(r1.view(torch.int32), r2.view(torch.int32))
+        assert torch.equal(d1, d2)
+    b1.close(); b2.close()
 
 
 def test_vec_env_zero_copy_mode(rmv):

@@ -15,7 +15,7 @@ BOUNDS = {"quadrotor2d-v0": (-10, 10), "quadrotor2d-slungload-v0": (-10, 10), "q
           "quadrotor3d-slungload-v0": (-10, 10)}
 
 
-def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, ctas=0, obs=0, track=0, l2=0):
+def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, ctas=0, obs=0, track=0, l2=0, rows=0):
     dev = "cuda:0"
     b = rmv.QuadBatch(env_id, n, seed=0, track_episodes=bool(track))
     b.set_tuning(vec=vec, block=block)
@@ -40,7 +40,23 @@ def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, cta
     done = torch.empty((ring, n), dtype=torch.uint8, device=dev)
     lay = 1 if layout == "soa" else 0
 
-    if obs:
+    if rows:
+        # travelling state (rmv_step_rows): state read from rows[t], written to rows[t+1] of a ring; handle state untouched
+        R = 4
+        row_ring = torch.empty((R, n, b.state_dim), dtype=torch.float32, device=dev)
+        b.reset(obs=row_ring[0])
+        ap, rp, dp = [acts[t].data_ptr() for t in range(ring)], [rew[t].data_ptr() for t in range(ring)], [done[t].data_ptr() for t in range(ring)]
+        op = [row_ring[t].data_ptr() for t in range(R)]
+        stream = torch.cuda.current_stream().cuda_stream
+        pos = [0]
+
+        def run(k):
+            t0 = pos[0]
+            for t in range(t0, t0 + k):
+                b.step_rows(op[t % R], ap[t % ring], rp[t % ring], dp[t % ring], op[(t + 1) % R] if rows == 1 else op[t % R],
+                            layout=lay, act_ld=n, stream=stream)
+            pos[0] = t0 + k
+    elif obs:
         # obs rows [N][S] written by the kernel every step (the VecEnv / rollout-buffer variant); one C-ABI call per step
         obs_ring = torch.empty((2, n, b.state_dim), dtype=torch.float32, device=dev)
         ap, rp, dp = [acts[t].data_ptr() for t in range(ring)], [rew[t].data_ptr() for t in range(ring)], [done[t].data_ptr() for t in range(ring)]
@@ -71,7 +87,7 @@ def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, cta
     b_state_dim = b.state_dim
     b.close()
     sps = n / (best * 1e-3)
-    gbs = sps * (BYTES[env_id] + (4 * b_state_dim if obs else 0) + (8 if track else 0)) / 1e9
+    gbs = sps * (BYTES[env_id] + (4 * b_state_dim if (obs and not rows) else 0) + (8 if track else 0)) / 1e9
     return best * 1e3, sps, gbs, gbs / peak
 
 
@@ -90,6 +106,7 @@ def main():
     ap.add_argument("--ctas", default="0", help="comma list: persistent CTAs per SM for the TMA kernel (0 = max)")
     ap.add_argument("--obs", type=int, default=0, help="1: the kernel also writes row-per-env observations [N][S] every step")
     ap.add_argument("--track", type=int, default=0, help="1: episode tracking (Monitor) on")
+    ap.add_argument("--rows", type=int, default=0, help="1: rmv_step_rows through a ring of row buffers, 2: rmv_step_rows in place")
     ap.add_argument("--l2", type=int, default=0, help="1: opt-in L2 access-policy window on the state (rmv_set_l2_persist)")
     args = ap.parse_args()
     print("%-26s %9s %3s %5s %4s %5s %9s %11s %9s %6s" % ("env", "n", "vec", "block", "lay", "fused", "us/step", "steps/s", "GB/s(alg)", "frac"))
@@ -102,8 +119,8 @@ def main():
                             ring = max(2, min(args.ring, int(6e9 // (n * 4 * 6))))
                             for tma in (int(x) for x in args.tma.split(",")):
                                 for ctas in (int(x) for x in args.ctas.split(",")) if tma else (0,):
-                                    us, sps, gbs, frac = time_cfg(env_id, n, vec, block, layout, bool(fused), args.steps, ring, args.peak, tma, ctas, args.obs, args.track, args.l2)
-                                    print("%-26s %9d %3d %5d %4s %5d %9.2f %11.4g %9.1f %6.3f  tma=%d ctas=%d obs=%d track=%d l2=%d" % (env_id, n, vec, block, layout, fused, us, sps, gbs, frac, tma, ctas, args.obs, args.track, args.l2), flush=True)
+                                    us, sps, gbs, frac = time_cfg(env_id, n, vec, block, layout, bool(fused), args.steps, ring, args.peak, tma, ctas, args.obs, args.track, args.l2, args.rows)
+                                    print("%-26s %9d %3d %5d %4s %5d %9.2f %11.4g %9.1f %6.3f  tma=%d ctas=%d obs=%d track=%d l2=%d rows=%d" % (env_id, n, vec, block, layout, fused, us, sps, gbs, frac, tma, ctas, args.obs, args.track, args.l2, args.rows), flush=True)
 
 
 if __name__ == "__main__":
