@@ -177,6 +177,20 @@ __device__ __forceinline__ float on_done(const StepArgs& a, int64_t e, float n_r
   return r;
 }
 
+// Episode bookkeeping of a finished env without a dependent load: the caller fetched ep_return and ep_start together
+// with the state; everything here is a plain store or a fire-and-forget reduction (one writer per env and step, so the
+// sums are the same values a load-add-store would produce).
+__device__ __forceinline__ void track_finished(const StepArgs& a, uint32_t e, float total, uint32_t started) {
+  const uint32_t now = a.step_index + 1u;
+  const uint32_t len = now - started;
+  a.last_return[e] = total;
+  a.last_length[e] = len;
+  atomicAdd(a.cum_return + e, (double)total);
+  atomicAdd(a.cum_length + e, (unsigned long long)len);
+  atomicAdd(a.fin_count + e, 1u);
+  a.ep_start[e] = now;
+}
+
 // ---- the fused single-step kernel ------------------------------------------------------------
 // dynamics + done + reward + reset-on-done (+ optional episode bookkeeping, + optional
 // row-per-env observation copy) for n envs: the reference's step() and the caller's reset-on-done
@@ -242,6 +256,7 @@ __device__ __forceinline__ void step_envs(const StepArgs& a, uint32_t cta_e0, ui
   float s[V][S];
   float act[V][A];
   float ep_ret[V];
+  uint32_t ep_started[V];                          // TRACK: step index at which the running episode began
   uint32_t word[V];                                // PREF: the env's `episode` word, fetched with the state
   bool redraw[V];
 #pragma unroll
@@ -259,7 +274,11 @@ __device__ __forceinline__ void step_envs(const StepArgs& a, uint32_t cta_e0, ui
 #pragma unroll
       for (int v = 0; v < V; ++v) word[v] = a.episode[e0 + v];   // padded to whole tiles: in bounds
     }
-    if (TRACK) load_v<V, false>(a.ep_return + e0, ep_ret);
+    if (TRACK) {
+      load_v<V, false>(a.ep_return + e0, ep_ret);
+#pragma unroll
+      for (int v = 0; v < V; ++v) ep_started[v] = a.ep_start[e0 + v];      // padded to whole tiles: in bounds
+    }
     load_actions<KIND, V>(a, a.act, (int64_t)e0, full, act);
   }
   __syncthreads();                                 // *redraw_total = 0 is visible; the loads are in flight
@@ -288,15 +307,7 @@ __device__ __forceinline__ void step_envs(const StepArgs& a, uint32_t cta_e0, ui
           redraw_episode[slot] = count;            // the Philox episode index of the re-draw
         }
         if (TRACK) {
-          const float total = ep_ret[v] + r;
-          const uint32_t now = a.step_index + 1u;
-          const uint32_t len = now - a.ep_start[e];
-          a.last_return[e] = total;
-          a.last_length[e] = len;
-          a.cum_return[e] += (double)total;
-          a.cum_length[e] += len;
-          a.fin_count[e] += 1u;
-          a.ep_start[e] = now;
+          track_finished(a, e, ep_ret[v] + r, ep_started[v]);
           ep_ret[v] = -r;                          // becomes 0 after the "+= r" below
         }
       }
@@ -451,9 +462,10 @@ k_step_rows(const StepArgs a) {
   }
   float act[1][A];
   float ep_ret = 0.0f;
+  uint32_t ep_started = 0u;
   if (active) {
     load_actions<KIND, 1>(a, a.act, (int64_t)e, true, act);
-    if (TRACK) ep_ret = a.ep_return[e];
+    if (TRACK) { ep_ret = a.ep_return[e]; ep_started = a.ep_start[e]; }
   } else {
 #pragma unroll
     for (int c = 0; c < A; ++c) act[0][c] = 0.0f;
@@ -483,15 +495,7 @@ k_step_rows(const StepArgs a) {
         redraw_episode[slot] = count;
       }
       if (TRACK) {
-        const float total = ep_ret + r;
-        const uint32_t now = a.step_index + 1u;
-        const uint32_t len = now - a.ep_start[e];
-        a.last_return[e] = total;
-        a.last_length[e] = len;
-        a.cum_return[e] += (double)total;
-        a.cum_length[e] += len;
-        a.fin_count[e] += 1u;
-        a.ep_start[e] = now;
+        track_finished(a, e, ep_ret + r, ep_started);
         ep_ret = -r;
       }
     }
