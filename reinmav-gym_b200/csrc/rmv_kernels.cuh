@@ -177,6 +177,39 @@ __device__ __forceinline__ float on_done(const StepArgs& a, int64_t e, float n_r
   return r;
 }
 
+// ---- [32 rows][S] <-> a warp's shared tile [32][SP], coalesced on the global side ---------------------------
+// Element i = lane + 32k of the warp's 32*S contiguous floats is component c = i % S of row r = i / S.  The global
+// address is a compile-time offset from one per-lane pointer (128*k bytes), the shared index is i + r*(SP - S); r and
+// c advance incrementally (no division per element).  GUARD: only rows r < rows_here exist (last warp of a ragged batch).
+template <int S, int SP, bool GUARD, bool STREAM>
+__device__ __forceinline__ void tile_to_rows(const float* my, float* dst_lane, uint32_t lane, uint32_t rows_here) {
+  uint32_t r = lane / S, c = lane - r * S;
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    if (!GUARD || r < rows_here) {
+      const float x = my[(int)lane + 32 * k + (int)r * (SP - S)];
+      if (STREAM) __stcs(dst_lane + 32 * k, x); else dst_lane[32 * k] = x;
+    }
+    c += 32 % S; r += 32 / S;
+    if (c >= (uint32_t)S) { c -= S; r += 1; }
+  }
+}
+template <int S, int SP, bool GUARD>
+__device__ __forceinline__ void rows_to_tile(const float* src_lane, float* my, uint32_t lane, uint32_t rows_here) {
+  uint32_t r = lane / S, c = lane - r * S;
+  float x[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) {                      // all loads first: S independent 128-byte requests per warp in flight
+    x[k] = (!GUARD || (lane + 32u * k) < rows_here * S) ? src_lane[32 * k] : 0.0f;
+  }
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    my[(int)lane + 32 * k + (int)r * (SP - S)] = x[k];
+    c += 32 % S; r += 32 / S;
+    if (c >= (uint32_t)S) { c -= S; r += 1; }
+  }
+}
+
 // Episode bookkeeping of a finished env without a dependent load: the caller fetched ep_return and ep_start together
 // with the state; everything here is a plain store or a fire-and-forget reduction (one writer per env and step, so the
 // sums are the same values a load-add-store would produce).
@@ -349,23 +382,36 @@ __device__ __forceinline__ void step_envs(const StepArgs& a, uint32_t cta_e0, ui
   }
 
   if (OBS) {
-    // row-per-env observation copy [n][S]: transpose through a per-warp shared tile so that each
-    // store instruction writes runs of S contiguous floats instead of 32 scattered words.
-    // Rows of re-drawn envs are written by the re-draw pass instead.
+    // row-per-env observation copy [n][S]: transpose through a per-warp shared tile so that each store instruction
+    // writes 128 contiguous bytes instead of 32 scattered words.  Rows of re-drawn envs are written here with their
+    // terminal state and overwritten by the re-draw pass after the barrier (same CTA: ordered).
     float* my = tile + warp * 32 * SP;
     const uint32_t warp_e0 = e0 - lane * V;
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const uint32_t my_mask = __ballot_sync(0xffffffffu, redraw[v]);
+    if constexpr (V == 1) {
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < S; ++c) my[lane * SP + c] = s[v][c];
+      for (int c = 0; c < S; ++c) my[lane * SP + c] = s[0][c];
       __syncwarp();
+      float* const dst_lane = a.obs + (size_t)warp_e0 * S + lane;
+      if (FULL) {
+        tile_to_rows<S, SP, false, true>(my, dst_lane, lane, 32u);
+      } else {
+        const uint32_t rows_here = warp_e0 < n ? (n - warp_e0 < 32u ? n - warp_e0 : 32u) : 0u;
+        tile_to_rows<S, SP, true, true>(my, dst_lane, lane, rows_here);
+      }
+    } else {
 #pragma unroll
-      for (int i = lane; i < 32 * S; i += 32) {
-        const int r = i / S, c = i - r * S;
-        const uint32_t e = warp_e0 + (uint32_t)r * V + v;
-        if ((FULL || e < n) && !((my_mask >> r) & 1u)) __stcs(a.obs + (size_t)e * S + c, my[r * SP + c]);
+      for (int v = 0; v < V; ++v) {
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < S; ++c) my[lane * SP + c] = s[v][c];
+        __syncwarp();
+#pragma unroll
+        for (int i = lane; i < 32 * S; i += 32) {
+          const int r = i / S, c = i - r * S;
+          const uint32_t e = warp_e0 + (uint32_t)r * V + v;
+          if (FULL || e < n) __stcs(a.obs + (size_t)e * S + c, my[r * SP + c]);
+        }
       }
     }
   }
@@ -451,15 +497,9 @@ k_step_rows(const StepArgs a) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // rows in: coalesced, transposed through the warp's tile
-  {
-    const float* const src = a.rows_in + (size_t)warp_e0 * S;
-    const uint32_t rows_here = warp_e0 < n ? (n - warp_e0 < 32u ? n - warp_e0 : 32u) : 0u;
-#pragma unroll
-    for (int i = (int)lane; i < 32 * S; i += 32) {
-      const int r = i / S, c = i - r * S;
-      my[r * SP + c] = ((uint32_t)r < rows_here) ? src[i] : 0.0f;
-    }
-  }
+  const uint32_t rows_here = warp_e0 < n ? (n - warp_e0 < 32u ? n - warp_e0 : 32u) : 0u;
+  if (rows_here == 32u) rows_to_tile<S, SP, false>(a.rows_in + (size_t)warp_e0 * S + lane, my, lane, 32u);
+  else rows_to_tile<S, SP, true>(a.rows_in + (size_t)warp_e0 * S + lane, my, lane, rows_here);
   float act[1][A];
   float ep_ret = 0.0f;
   uint32_t ep_started = 0u;
@@ -504,20 +544,13 @@ k_step_rows(const StepArgs a) {
     if (TRACK) a.ep_return[e] = ep_ret + r;
   }
 
-  // rows out (plain stores: the next step reads them); rows of re-drawn envs are written by the re-draw pass
-  {
-    const uint32_t skip = __ballot_sync(0xffffffffu, redraw);
-    __syncwarp();
+  // rows out (plain stores: the next step reads them); a re-drawn env's row is overwritten by the re-draw pass
+  __syncwarp();
 #pragma unroll
-    for (int c = 0; c < S; ++c) my[lane * SP + c] = s[c];
-    __syncwarp();
-    float* const dst = a.obs + (size_t)warp_e0 * S;
-#pragma unroll
-    for (int i = (int)lane; i < 32 * S; i += 32) {
-      const int r = i / S, c = i - r * S;
-      if (warp_e0 + (uint32_t)r < n && !((skip >> r) & 1u)) dst[i] = my[r * SP + c];
-    }
-  }
+  for (int c = 0; c < S; ++c) my[lane * SP + c] = s[c];
+  __syncwarp();
+  if (rows_here == 32u) tile_to_rows<S, SP, false, false>(my, a.obs + (size_t)warp_e0 * S + lane, lane, 32u);
+  else tile_to_rows<S, SP, true, false>(my, a.obs + (size_t)warp_e0 * S + lane, lane, rows_here);
 
   __syncthreads();
   const uint32_t pairs = redraw_total * NB;

@@ -11,9 +11,9 @@ can carry the state — step t READS its state from ``obs[t]`` and writes the ne
 (``rmv_step_rows``); the handle's tiled state is not streamed at all during the rollout and is re-synchronised
 from ``obs[T]`` once at the end.  Per env-step that is 4(2S+A+1)+1 bytes instead of 4(3S+A+1)+1, and the rows
 read are the ones the previous step just wrote — but both directions now go through the shared-memory transpose:
-measured at N = 2^20 it is 15 % faster for quadrotor3d (18.7 vs 22.1 us per step), 5-7 % for the planar kinds,
-8 % SLOWER for quadrotor3d-slungload and slower with episode tracking (profiles/r1b_sweep_rows.txt), hence not
-the default.  Same results bit for bit (tests/test_gpu_vec_env.py).
+measured at N = 2^20 it is 13 % faster for quadrotor3d (17.3 vs 19.6 us per step) and 8 % for
+quadrotor3d-slungload, equal for quadrotor2d-slungload and 3 % SLOWER for quadrotor2d (profiles/r1b_sweep_rows.txt),
+hence not the default.  Same results bit for bit (tests/test_gpu_vec_env.py).
 """
 import torch
 
