@@ -497,8 +497,8 @@ static bool default_prefetch(int kind, int64_t n) {
 template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF>
 static cudaError_t launch_step_kvf(const StepArgs& args, const cudaAccessPolicyWindow* win, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
-  constexpr int SP = (S % 2 == 0) ? S + 1 : S;
-  size_t smem = OBS ? (size_t)BLOCK * SP * sizeof(float) : 0;           // [warps][32][SP] transpose tiles
+  constexpr int SP = V == 1 ? row_pitch<S>() : ((S % 2 == 0) ? S + 1 : S);
+  size_t smem = OBS ? (size_t)BLOCK * SP * sizeof(float) : 0;           // [warps][32][pitch] transpose tiles
   if (g_ctas_cap > 0) {               // developer experiment: cap resident CTAs per SM by padding dynamic shared memory
     const size_t per = (size_t)(227 * 1024) / (size_t)g_ctas_cap - 2048;
     if (per > smem) smem = per & ~(size_t)127;
@@ -536,7 +536,7 @@ static cudaError_t launch_step_kvf(const StepArgs& args, const cudaAccessPolicyW
 template <int KIND, bool TRACK, int BLOCK>
 static cudaError_t launch_step_rows_kb(const StepArgs& args, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
-  constexpr int SP = (S % 2 == 0) ? S + 1 : S;
+  constexpr int SP = row_pitch<S>();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(blocks_for(args.n, BLOCK));
   cfg.blockDim = dim3(BLOCK);

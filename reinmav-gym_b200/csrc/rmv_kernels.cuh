@@ -177,37 +177,69 @@ __device__ __forceinline__ float on_done(const StepArgs& a, int64_t e, float n_r
   return r;
 }
 
-// ---- [32 rows][S] <-> a warp's shared tile [32][SP], coalesced on the global side ---------------------------
-// Element i = lane + 32k of the warp's 32*S contiguous floats is component c = i % S of row r = i / S.  The global
-// address is a compile-time offset from one per-lane pointer (128*k bytes), the shared index is i + r*(SP - S); r and
-// c advance incrementally (no division per element).  GUARD: only rows r < rows_here exist (last warp of a ragged batch).
-template <int S, int SP, bool GUARD, bool STREAM>
-__device__ __forceinline__ void tile_to_rows(const float* my, float* dst_lane, uint32_t lane, uint32_t rows_here) {
-  uint32_t r = lane / S, c = lane - r * S;
+// ---- [32 rows][S] <-> a warp's shared tile, coalesced on the global side ------------------------------------
+// A warp's 32 rows are 32*S contiguous floats in global memory; element i = lane + 32k is accessed by lane `lane`
+// in pass k (one 128-byte request per pass).  In shared memory row r starts at r*P words, P = row_pitch<S>():
+//   S = 5, 9   P = S      a thread's row access (stride S, odd) and the pass access (consecutive words) are conflict-free
+//   S = 10     P = 10     the thread moves its row as five 64-bit words (stride 10: conflict-free per half-warp)
+//   S = 16     P = 20     four 128-bit words (stride 20: conflict-free per quarter-warp); the pass index gains 4*(i/16)
+// so that in every case the pass address is a COMPILE-TIME offset from one per-lane pointer on both sides — no
+// division, no index arithmetic per element.  GUARD: only rows r < rows_here exist (last warp of a ragged batch).
+template <int S> __host__ __device__ constexpr int row_pitch() { return S == 16 ? 20 : S; }
+
+template <int S>
+__device__ __forceinline__ void row_to_smem(float* row, const float (&s)[S]) {      // row = tile + lane * row_pitch<S>()
+  if constexpr (S == 10) {
 #pragma unroll
-  for (int k = 0; k < S; ++k) {
-    if (!GUARD || r < rows_here) {
-      const float x = my[(int)lane + 32 * k + (int)r * (SP - S)];
-      if (STREAM) __stcs(dst_lane + 32 * k, x); else dst_lane[32 * k] = x;
-    }
-    c += 32 % S; r += 32 / S;
-    if (c >= (uint32_t)S) { c -= S; r += 1; }
+    for (int j = 0; j < 5; ++j) reinterpret_cast<float2*>(row)[j] = make_float2(s[2 * j], s[2 * j + 1]);
+  } else if constexpr (S == 16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(row)[j] = make_float4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < S; ++c) row[c] = s[c];
   }
 }
-template <int S, int SP, bool GUARD>
-__device__ __forceinline__ void rows_to_tile(const float* src_lane, float* my, uint32_t lane, uint32_t rows_here) {
-  uint32_t r = lane / S, c = lane - r * S;
-  float x[S];
+template <int S>
+__device__ __forceinline__ void row_from_smem(const float* row, float (&s)[S]) {
+  if constexpr (S == 10) {
 #pragma unroll
-  for (int k = 0; k < S; ++k) {                      // all loads first: S independent 128-byte requests per warp in flight
-    x[k] = (!GUARD || (lane + 32u * k) < rows_here * S) ? src_lane[32 * k] : 0.0f;
+    for (int j = 0; j < 5; ++j) { const float2 t = reinterpret_cast<const float2*>(row)[j]; s[2 * j] = t.x; s[2 * j + 1] = t.y; }
+  } else if constexpr (S == 16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = reinterpret_cast<const float4*>(row)[j];
+      s[4 * j] = t.x; s[4 * j + 1] = t.y; s[4 * j + 2] = t.z; s[4 * j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < S; ++c) s[c] = row[c];
   }
+}
+// shared-memory word of element i = lane + 32k: a per-lane base plus a compile-time offset
+template <int S> __device__ __forceinline__ uint32_t pass_base(uint32_t lane) { return S == 16 ? lane + 4u * (lane >> 4) : lane; }
+template <int S> __host__ __device__ constexpr int pass_step() { return S == 16 ? 40 : 32; }
+
+template <int S, bool GUARD, bool STREAM>
+__device__ __forceinline__ void tile_to_rows(const float* my, float* dst_lane, uint32_t lane, uint32_t rows_here) {
+  const float* const src = my + pass_base<S>(lane);
 #pragma unroll
   for (int k = 0; k < S; ++k) {
-    my[(int)lane + 32 * k + (int)r * (SP - S)] = x[k];
-    c += 32 % S; r += 32 / S;
-    if (c >= (uint32_t)S) { c -= S; r += 1; }
+    if (!GUARD || (lane + 32u * k) < rows_here * S) {
+      const float x = src[pass_step<S>() * k];
+      if (STREAM) __stcs(dst_lane + 32 * k, x); else dst_lane[32 * k] = x;
+    }
   }
+}
+template <int S, bool GUARD>
+__device__ __forceinline__ void rows_to_tile(const float* src_lane, float* my, uint32_t lane, uint32_t rows_here) {
+  float x[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k)                        // all loads first: S independent 128-byte requests per warp in flight
+    x[k] = (!GUARD || (lane + 32u * k) < rows_here * S) ? src_lane[32 * k] : 0.0f;
+  float* const dst = my + pass_base<S>(lane);
+#pragma unroll
+  for (int k = 0; k < S; ++k) dst[pass_step<S>() * k] = x[k];
 }
 
 // Episode bookkeeping of a finished env without a dependent load: the caller fetched ep_return and ep_start together
@@ -267,7 +299,7 @@ constexpr int step_min_ctas(int kind, int v, bool obs, bool track, int block) {
   // quadrotor2d-slungload, 1280 when the obs copy / tracking / the 16-component state need registers
   if (v == 2) return (obs || track) ? 1 : 1024 / block;     // 64 registers: as many envs in flight per SM as V = 1 at 32
   if (v != 1) return 1;
-  const int threads = (obs || track || kind == QUAD3D_SLUNG) ? 1280 : (kind == QUAD2D_SLUNG ? 1536 : 2048);
+  const int threads = (kind == QUAD3D_SLUNG) ? 1280 : (kind == QUAD2D_SLUNG ? 1536 : 2048);
   return threads / block > 0 ? threads / block : 1;
 }
 
@@ -385,21 +417,21 @@ __device__ __forceinline__ void step_envs(const StepArgs& a, uint32_t cta_e0, ui
     // row-per-env observation copy [n][S]: transpose through a per-warp shared tile so that each store instruction
     // writes 128 contiguous bytes instead of 32 scattered words.  Rows of re-drawn envs are written here with their
     // terminal state and overwritten by the re-draw pass after the barrier (same CTA: ordered).
-    float* my = tile + warp * 32 * SP;
     const uint32_t warp_e0 = e0 - lane * V;
     if constexpr (V == 1) {
+      float* my = tile + warp * 32 * row_pitch<S>();
       __syncwarp();
-#pragma unroll
-      for (int c = 0; c < S; ++c) my[lane * SP + c] = s[0][c];
+      row_to_smem<S>(my + lane * row_pitch<S>(), s[0]);
       __syncwarp();
       float* const dst_lane = a.obs + (size_t)warp_e0 * S + lane;
       if (FULL) {
-        tile_to_rows<S, SP, false, true>(my, dst_lane, lane, 32u);
+        tile_to_rows<S, false, true>(my, dst_lane, lane, 32u);
       } else {
         const uint32_t rows_here = warp_e0 < n ? (n - warp_e0 < 32u ? n - warp_e0 : 32u) : 0u;
-        tile_to_rows<S, SP, true, true>(my, dst_lane, lane, rows_here);
+        tile_to_rows<S, true, true>(my, dst_lane, lane, rows_here);
       }
     } else {
+      float* my = tile + warp * 32 * SP;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         __syncwarp();
@@ -426,7 +458,7 @@ k_step(const StepArgs a) {
   __shared__ uint32_t redraw_total;                // finished envs of this CTA ...
   __shared__ uint16_t redraw_list[BLOCK * V];      // ... their indices inside the CTA, in arrival order ...
   __shared__ uint32_t redraw_episode[BLOCK * V];   // ... and their new reset counts
-  extern __shared__ float tile[];                  // [warps][32][SP], only when OBS
+  extern __shared__ __align__(16) float tile[];    // [warps][32][pitch], only when OBS
 
   // Programmatic dependent launch: let the NEXT launch in the stream become resident while this grid
   // drains, and do not touch global memory before the PREVIOUS grid has completed and flushed.
@@ -480,11 +512,11 @@ __global__ void __launch_bounds__(BLOCK, step_min_ctas(KIND, 1, true, TRACK, BLO
 k_step_rows(const StepArgs a) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   constexpr int NB = (S + 3) / 4;
-  constexpr int SP = (S % 2 == 0) ? S + 1 : S;
+  constexpr int SP = row_pitch<S>();
   __shared__ uint32_t redraw_total;
   __shared__ uint16_t redraw_list[BLOCK];
   __shared__ uint32_t redraw_episode[BLOCK];
-  extern __shared__ float tile[];                  // [warps][32][SP]
+  extern __shared__ __align__(16) float tile[];    // [warps][32][SP]
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -498,8 +530,8 @@ k_step_rows(const StepArgs a) {
 
   // rows in: coalesced, transposed through the warp's tile
   const uint32_t rows_here = warp_e0 < n ? (n - warp_e0 < 32u ? n - warp_e0 : 32u) : 0u;
-  if (rows_here == 32u) rows_to_tile<S, SP, false>(a.rows_in + (size_t)warp_e0 * S + lane, my, lane, 32u);
-  else rows_to_tile<S, SP, true>(a.rows_in + (size_t)warp_e0 * S + lane, my, lane, rows_here);
+  if (rows_here == 32u) rows_to_tile<S, false>(a.rows_in + (size_t)warp_e0 * S + lane, my, lane, 32u);
+  else rows_to_tile<S, true>(a.rows_in + (size_t)warp_e0 * S + lane, my, lane, rows_here);
   float act[1][A];
   float ep_ret = 0.0f;
   uint32_t ep_started = 0u;
@@ -512,8 +544,7 @@ k_step_rows(const StepArgs a) {
   }
   __syncwarp();
   float s[S];
-#pragma unroll
-  for (int c = 0; c < S; ++c) s[c] = my[lane * SP + c];
+  row_from_smem<S>(my + lane * SP, s);
   __syncthreads();                                 // redraw_total = 0 is visible
 
   bool redraw = false;
@@ -546,11 +577,10 @@ k_step_rows(const StepArgs a) {
 
   // rows out (plain stores: the next step reads them); a re-drawn env's row is overwritten by the re-draw pass
   __syncwarp();
-#pragma unroll
-  for (int c = 0; c < S; ++c) my[lane * SP + c] = s[c];
+  row_to_smem<S>(my + lane * SP, s);
   __syncwarp();
-  if (rows_here == 32u) tile_to_rows<S, SP, false, false>(my, a.obs + (size_t)warp_e0 * S + lane, lane, 32u);
-  else tile_to_rows<S, SP, true, false>(my, a.obs + (size_t)warp_e0 * S + lane, lane, rows_here);
+  if (rows_here == 32u) tile_to_rows<S, false, false>(my, a.obs + (size_t)warp_e0 * S + lane, lane, 32u);
+  else tile_to_rows<S, true, false>(my, a.obs + (size_t)warp_e0 * S + lane, lane, rows_here);
 
   __syncthreads();
   const uint32_t pairs = redraw_total * NB;

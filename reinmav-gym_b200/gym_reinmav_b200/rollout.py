@@ -6,21 +6,23 @@ fills ``mb_obs, mb_actions, mb_rewards, mb_dones`` of shape ``[nsteps, nenv, ...
 HBM and the step kernel writes straight into them: step t reads ``actions[t]``, writes ``rewards[t]``,
 ``dones[t]`` and the observation rows ``obs[t + 1]`` — no staging copy, no host hop.
 
-``travelling=True`` (opt-in): obs == state in the reference (quadrotor3d.py:104), so the rollout buffer itself
-can carry the state — step t READS its state from ``obs[t]`` and writes the new one to ``obs[t + 1]``
-(``rmv_step_rows``); the handle's tiled state is not streamed at all during the rollout and is re-synchronised
-from ``obs[T]`` once at the end.  Per env-step that is 4(2S+A+1)+1 bytes instead of 4(3S+A+1)+1, and the rows
-read are the ones the previous step just wrote — but both directions now go through the shared-memory transpose:
-measured at N = 2^20 it is 13 % faster for quadrotor3d (17.3 vs 19.6 us per step) and 8 % for
-quadrotor3d-slungload, equal for quadrotor2d-slungload and 3 % SLOWER for quadrotor2d (profiles/r1b_sweep_rows.txt),
-hence not the default.  Same results bit for bit (tests/test_gpu_vec_env.py).
+``travelling``: obs == state in the reference (quadrotor3d.py:104), so the rollout buffer itself can carry the
+state — step t READS its state from ``obs[t]`` and writes the new one to ``obs[t + 1]`` (``rmv_step_rows``); the
+handle's tiled state is not streamed at all during the rollout and is re-synchronised from ``obs[T]`` once at the
+end.  Per env-step that is 4(2S+A+1)+1 bytes instead of 4(3S+A+1)+1 (the state is written once, not twice), at the
+price of a shared-memory transpose on the load side as well.  Measured at N = 2^20 (profiles/r1b_sweep_obs_rows.txt):
+quadrotor3d 15.3 vs 19.5 us per step, quadrotor3d-slungload 29.5 vs 31.9, quadrotor2d-slungload 17.9 vs 18.1,
+quadrotor2d 11.4 vs 11.0 — so the default (``None``) turns it on for the 3D kinds only.  Same results bit for bit
+either way (tests/test_gpu_vec_env.py).
 """
 import torch
 
 
 class RolloutBuffer:
-    def __init__(self, venv, n_steps, travelling=False):
+    def __init__(self, venv, n_steps, travelling=None):
         self.venv, self.T = venv, int(n_steps)
+        if travelling is None:
+            travelling = venv.batch.state_dim in (10, 16)          # quadrotor3d, quadrotor3d-slungload
         self.travelling = bool(travelling) and venv.batch.action_dim > 0
         n, S, A = venv.num_envs, venv.batch.state_dim, venv.batch.action_dim
         dev = "cuda:%d" % venv.device
