@@ -16,7 +16,7 @@ def load_golden(env_id, repair="A"):
 
 def bits(a):
     a = np.ascontiguousarray(a)
-    return a.view({4: np.uint32, 8: np.uint64}[a.dtype.itemsize])
+    return a.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[a.dtype.itemsize])
 
 
 def same_bits(a, b):
