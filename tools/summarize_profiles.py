@@ -30,7 +30,7 @@ def raw_rows(path):
 
 
 traffic = {}
-for name in ("q3d_n20_cold", "q3d_n20_warm", "q3d_n23", "q2d_n20_warm", "q2d_n23"):
+for name in ("q3d_n20_cold", "q3d_n20_warm", "q3d_n23", "q2d_n20_warm", "q2d_n23", "q3d_obs_n20_warm", "q3d_rows_n20_warm"):
     p = os.path.join(src, name + ".raw.csv")
     if not os.path.exists(p):
         continue
