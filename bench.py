@@ -246,7 +246,11 @@ def run_gpu_arm(args):
 
     extras = {}
     if args.extras and world == 1:
-        extras = measure_extras(torch, rmv, args, local)
+        try:                                   # side measurements must never cost the contract line
+            extras = measure_extras(torch, rmv, args, local)
+        except Exception as exc:               # noqa: BLE001
+            extras = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            torch.cuda.synchronize()
 
     clocks = sampler.stop() if sampler else None
     cpu = None
