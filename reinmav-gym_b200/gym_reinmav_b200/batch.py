@@ -244,6 +244,10 @@ class QuadBatch:
 def fill_uniform_actions(actions, num_envs, action_dim, low, high, seed, env_id_offset=0, step_index=0,
                          layout=ACT_AOS, act_ld=0, device=0, stream=None):
     """Random-policy actions ~ U[low, high) written on the device (Philox, keyed by global env id)."""
+    need = int(action_dim) * (int(act_ld) if layout == ACT_SOA and act_ld else int(num_envs))
+    have = actions.numel() if hasattr(actions, "numel") else None      # a raw address cannot be checked
+    if have is not None and have < need:
+        raise ValueError("action buffer holds %d floats, %d x %d needs %d" % (have, num_envs, action_dim, need))
     check(lib().rmv_fill_uniform_actions(_ptr(actions), int(num_envs), int(action_dim), layout, int(act_ld),
                                          float(low), float(high), int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_id_offset),
                                          int(step_index), int(device), _stream(stream, device)))
