@@ -40,6 +40,16 @@ def _ptr(x):
     raise TypeError("cannot take the address of %r" % type(x))
 
 
+def _need(x, count, what):
+    """Refuse a tensor / array that is too small for what the kernel is about to read or write (raw addresses cannot
+    be checked).  The C-ABI takes plain pointers, so this is the only place an undersized buffer can be caught."""
+    if x is None or isinstance(x, int):
+        return
+    have = x.numel() if hasattr(x, "numel") else getattr(x, "size", None)
+    if have is not None and have < count:
+        raise ValueError("%s holds %d elements, %d needed" % (what, have, count))
+
+
 def _stream(stream, device):
     if stream is None:
         import sys
@@ -142,7 +152,16 @@ class QuadBatch:
         check(lib().rmv_reset(self._h, _ptr(mask), _ptr(obs), _stream(stream, self.device)))
         self.launches += 1
 
+    def _check_io(self, actions, reward, done, layout, act_ld, steps=1, out_ld=0):
+        n, A = self.num_envs, self.action_dim
+        per_step = A * (int(act_ld) if layout == ACT_SOA and act_ld else n)
+        _need(actions, steps * per_step, "actions")
+        _need(reward, (steps - 1) * int(out_ld or n) + n, "reward")
+        _need(done, (steps - 1) * int(out_ld or n) + n, "done")
+
     def step(self, actions, reward, done, obs=None, auto_reset=True, layout=ACT_AOS, act_ld=0, stream=None):
+        self._check_io(actions, reward, done, layout, act_ld)
+        _need(obs, self.num_envs * self.state_dim, "obs")
         check(lib().rmv_step(self._h, _ptr(actions), layout, int(act_ld), _ptr(reward), _ptr(done), _ptr(obs),
                              1 if auto_reset else 0, _stream(stream, self.device)))
         self.launches += 1
@@ -150,6 +169,9 @@ class QuadBatch:
     def step_rows(self, rows_in, actions, reward, done, rows_out, auto_reset=True, layout=ACT_AOS, act_ld=0, stream=None):
         """Step on row-major state: read [N, S] rows_in, write [N, S] rows_out (may alias); the handle's own tiled
         state is not touched (``set_state_device(rows_out)`` re-synchronises it)."""
+        self._check_io(actions, reward, done, layout, act_ld)
+        _need(rows_in, self.num_envs * self.state_dim, "rows_in")
+        _need(rows_out, self.num_envs * self.state_dim, "rows_out")
         check(lib().rmv_step_rows(self._h, _ptr(rows_in), _ptr(actions), layout, int(act_ld), _ptr(reward), _ptr(done),
                                   _ptr(rows_out), 1 if auto_reset else 0, _stream(stream, self.device)))
         self.launches += 1
@@ -160,6 +182,8 @@ class QuadBatch:
 
     def step_many(self, n_steps, actions, reward=None, done=None, out_ld=0, layout=ACT_SOA, act_ld=0, fused=False,
                   stream=None):
+        if self.action_dim:
+            self._check_io(actions, reward, done, layout, act_ld, steps=int(n_steps), out_ld=out_ld)
         check(lib().rmv_step_many(self._h, int(n_steps), _ptr(actions), layout, int(act_ld), _ptr(reward), _ptr(done),
                                   int(out_ld or self.num_envs), 1 if fused else 0, _stream(stream, self.device)))
         self.launches += 1 if fused else int(n_steps)
@@ -244,10 +268,7 @@ class QuadBatch:
 def fill_uniform_actions(actions, num_envs, action_dim, low, high, seed, env_id_offset=0, step_index=0,
                          layout=ACT_AOS, act_ld=0, device=0, stream=None):
     """Random-policy actions ~ U[low, high) written on the device (Philox, keyed by global env id)."""
-    need = int(action_dim) * (int(act_ld) if layout == ACT_SOA and act_ld else int(num_envs))
-    have = actions.numel() if hasattr(actions, "numel") else None      # a raw address cannot be checked
-    if have is not None and have < need:
-        raise ValueError("action buffer holds %d floats, %d x %d needs %d" % (have, num_envs, action_dim, need))
+    _need(actions, int(action_dim) * (int(act_ld) if layout == ACT_SOA and act_ld else int(num_envs)), "action buffer")
     check(lib().rmv_fill_uniform_actions(_ptr(actions), int(num_envs), int(action_dim), layout, int(act_ld),
                                          float(low), float(high), int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_id_offset),
                                          int(step_index), int(device), _stream(stream, device)))

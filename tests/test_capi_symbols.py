@@ -69,3 +69,15 @@ def test_sparse_infos():
     assert [i.get("episode") for i in infos].count(None) == 4
     with pytest.raises(IndexError):
         infos[5]
+
+
+def test_undersized_buffers_are_refused_before_the_abi():
+    """The C-ABI takes plain pointers; the Python binding is the only place an undersized tensor can be caught."""
+    import numpy as np
+    import pytest
+    from gym_reinmav_b200.batch import _need
+    _need(None, 10, "x")
+    _need(12345, 10, "x")                                  # raw address: cannot be checked
+    _need(np.empty(10, np.float32), 10, "x")
+    with pytest.raises(ValueError, match="actions holds 8 elements, 16 needed"):
+        _need(np.empty((4, 2), np.float32), 16, "actions")
