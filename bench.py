@@ -268,7 +268,9 @@ def run_gpu_arm(args):
             "config": {"workload": "%s N=%d envs per GPU, random-policy actions U[0,10)^4, reset-on-done in-kernel"
                                    % (ENV_ID, n),
                        "env_id": ENV_ID, "envs_per_gpu": n, "state_dim": S, "action_dim": A,
-                       "launch": "one fused step kernel per step (vec=%d, block=%s), %d-step action ring" % (args.vec, args.block or "auto", ring),
+                       "launch": "one fused step kernel per step (vec=%d, block=%s), %d-step action ring; rmv_step_many issues the launches of a "
+                                 "ring pass from C and replays them from a CUDA graph once it has seen the same call twice"
+                                 % (args.vec, args.block or "auto", ring),
                        "l2": "no flush: per-step traffic %.0f MB (state %.0f MB read+written in place, re-read next step; "
                              "actions stream from a %.2f GiB ring > 126 MB L2); extras.n23 is the same kernel with a "
                              "working set that cannot be L2-resident" % (ALG_BYTES * n / 1e6, 4 * S * n / 1e6, ring * n * A * 4 / 2 ** 30),

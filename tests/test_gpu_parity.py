@@ -254,6 +254,35 @@ def test_step_is_cuda_graph_capturable(torch, rmv):
         assert same_bits(x, y)
 
 
+def test_step_many_graph_replay_bitwise(torch, rmv):
+    """rmv_step_many(fused=0) captures a repeated call in a CUDA graph the second time it sees it and replays it from
+    then on: plain launch, capture + launch, replays, a second call shape (LRU), and a re-seed in between (the cached
+    graphs carry the old Philox key and must not be used) — all against single rmv_step launches, bit for bit."""
+    env_id, n, seed, K = "quadrotor3d-v0", 128 * 60 + 11, 13, 16
+    dev = "cuda:0"
+    acts = torch.empty((K, n, 4), dtype=torch.float32, device=dev)
+    for t in range(K):
+        rmv.fill_uniform_actions(acts[t], n, 4, 0.0, 14.0, seed, step_index=t)      # wide: plenty of resets
+    rew_a = torch.empty((K, n), dtype=torch.float32, device=dev); done_a = torch.empty((K, n), dtype=torch.uint8, device=dev)
+    rew_b = torch.empty_like(rew_a); done_b = torch.empty_like(done_a)
+    a = rmv.QuadBatch(env_id, n, seed=seed)
+    b = rmv.QuadBatch(env_id, n, seed=seed)
+    a.reset(); b.reset()
+    plan = [(K, None), (K, None), (K, None), (6, None), (6, None), (6, None), (K, None), (K, 99), (K, None), (K, None), (K, None)]
+    for m, reseed in plan:
+        if reseed is not None:
+            a.set_seed(reseed); b.set_seed(reseed)
+        a.step_many(m, acts, rew_a, done_a, out_ld=n, layout=0, fused=False)
+        for t in range(m):
+            b.step(acts[t], rew_b[t], done_b[t])
+        torch.cuda.synchronize()
+        assert torch.equal(rew_a[:m].view(torch.int32), rew_b[:m].view(torch.int32)) and torch.equal(done_a[:m], done_b[:m])
+        assert same_bits(a.get_state(), b.get_state())
+        assert np.array_equal(a.get_episode_words(), b.get_episode_words())
+    assert int(done_b.sum()) > 0
+    a.close(); b.close()
+
+
 def test_l2_persist_window_bitwise_and_refusal(torch, rmv):
     """Opt-in L2 access-policy window on the state: same bits; a state larger than the device's persisting
     carve-out is refused (a partial window thrashes) instead of silently running slower."""
