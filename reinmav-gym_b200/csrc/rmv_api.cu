@@ -729,10 +729,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
   a.fin_count = at(e->fin_count);
   a.n = cn; a.act_ld = act_ld; a.out_ld = out_ld; a.act_step_stride = act_step_stride;
   a.env_id_offset = e->env_id_offset + c0; a.seed = e->seed; a.step_index = e->step_index;
-  for (uint32_t r = 0; r < 10; ++r) {
-    a.ks[2 * r] = (uint32_t)e->seed + r * PHILOX_W0;
-    a.ks[2 * r + 1] = (uint32_t)(e->seed >> 32) + r * PHILOX_W1;
-  }
+  philox_key_schedule(e->seed, a.ks);
   a.n_steps = n_steps; a.act_soa = (act_layout == RMV_ACT_SOA); a.auto_reset = auto_reset ? 1 : 0;
   a.P = e->dp;
   cudaError_t err;
@@ -775,10 +772,7 @@ extern "C" RMV_API int rmv_step_rows(rmv_env* env, const float* rows_in_dev, con
   a.cum_return = e->cum_return; a.cum_length = e->cum_length; a.fin_count = e->fin_count;
   a.n = e->n; a.act_ld = act_ld; a.out_ld = e->n; a.act_step_stride = 0;
   a.env_id_offset = e->env_id_offset; a.seed = e->seed; a.step_index = e->step_index;
-  for (uint32_t r = 0; r < 10; ++r) {
-    a.ks[2 * r] = (uint32_t)e->seed + r * PHILOX_W0;
-    a.ks[2 * r + 1] = (uint32_t)(e->seed >> 32) + r * PHILOX_W1;
-  }
+  philox_key_schedule(e->seed, a.ks);
   a.n_steps = 1; a.act_soa = (act_layout == RMV_ACT_SOA); a.auto_reset = auto_reset ? 1 : 0;
   a.P = e->dp;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

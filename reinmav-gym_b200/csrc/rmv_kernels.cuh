@@ -274,26 +274,6 @@ __device__ __forceinline__ void track_finished(const StepArgs& a, uint32_t e, fl
 constexpr int kBlock = 128;           // CTA size of the TMA variant and of V > 1
 constexpr int kWarps = kBlock / 32;
 
-// Philox4x32-10 with the key schedule (k + r*W) taken from the kernel-parameter constant bank: per
-// round two wide multiplies and two three-input XORs.  Same function as philox4x32_10.
-__device__ __forceinline__ void philox4x32_10_ks(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                 const uint32_t (&ks)[20], uint32_t out[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
-    const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ ks[2 * r];
-    const uint32_t n2 = hi0 ^ c3 ^ ks[2 * r + 1];
-    c1 = lo1; c3 = lo0; c0 = n0; c2 = n2;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-// U[-1,1) from the top 24 bits: -1 + u24 * 2^-23 in ONE fma.  Every intermediate of
-// uniform_from_bits(bits, -1, 2) is exact (multiples of 2^-23 of magnitude <= 1), so this is the same value.
-__device__ __forceinline__ float uniform_pm1(uint32_t bits) {
-  return __fmaf_rn((float)(bits >> 8), 1.1920928955078125e-07f, -1.0f);
-}
-
 constexpr int step_min_ctas(int kind, int v, bool obs, bool track, int block) {
   // resident-thread target per SM: 2048 (<= 32 registers) for the small-state kinds, 1536 for
   // quadrotor2d-slungload, 1280 when the obs copy / tracking / the 16-component state need registers

@@ -161,6 +161,38 @@ RMV_HD float uniform_from_bits(uint32_t bits, float lo, float width) {
   return (rf(lo) + rf(width) * u).v;
 }
 
+// Philox4x32-10 with the key schedule ks[2r] = k0 + r*W0, ks[2r+1] = k1 + r*W1 precomputed by the host (the kernels
+// read it from the kernel-parameter constant bank): per round two wide multiplies and two three-input XORs.
+// Same function as philox4x32_10 (tests/test_philox.py).
+RMV_HD void philox_key_schedule(uint64_t seed, uint32_t (&ks)[20]) {
+  for (uint32_t r = 0; r < 10; ++r) {
+    ks[2 * r] = (uint32_t)seed + r * PHILOX_W0;
+    ks[2 * r + 1] = (uint32_t)(seed >> 32) + r * PHILOX_W1;
+  }
+}
+RMV_HD void philox4x32_10_ks(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&ks)[20],
+                             uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t hi0 = __umulhi(PHILOX_M0, c0), hi1 = __umulhi(PHILOX_M1, c2);
+#else
+    const uint32_t hi0 = (uint32_t)(((uint64_t)PHILOX_M0 * c0) >> 32), hi1 = (uint32_t)(((uint64_t)PHILOX_M1 * c2) >> 32);
+#endif
+    const uint32_t lo0 = PHILOX_M0 * c0, lo1 = PHILOX_M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ ks[2 * r];
+    const uint32_t n2 = hi0 ^ c3 ^ ks[2 * r + 1];
+    c1 = lo1; c3 = lo0; c0 = n0; c2 = n2;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// U[-1,1) from the top 24 bits: -1 + u24 * 2^-23 in ONE fma.  Every intermediate of
+// uniform_from_bits(bits, -1, 2) is exact (multiples of 2^-23 of magnitude <= 1), so this is the same value
+// (checked for all 2^24 inputs in tests/test_philox.py).
+RMV_HD float uniform_pm1(uint32_t bits) {
+  return fma(rf((float)(bits >> 8)), rf(1.1920928955078125e-07f), rf(-1.0f)).v;
+}
+
 // reset(): S draws of U[-1,1) for (seed, global env id, episode) — replaces
 // self.np_random.uniform(low=-1.0, high=1.0, size=(S,)), quadrotor3d.py:184 and twins.
 template <int KIND>

@@ -74,3 +74,13 @@ extern "C" void twin_fma(long n, const float* a, const float* b, const float* c,
 extern "C" void twin_philox(const unsigned* ctr, const unsigned* key, unsigned* out) {
   philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
 }
+
+// the re-draw pass of the step kernels: key-schedule Philox and the one-fma uniform
+extern "C" void twin_philox_ks(unsigned long long seed, const unsigned* ctr, unsigned* out) {
+  uint32_t ks[20];
+  philox_key_schedule(seed, ks);
+  philox4x32_10_ks(ctr[0], ctr[1], ctr[2], ctr[3], ks, out);
+}
+extern "C" void twin_uniform_pm1(long n, const unsigned* bits, float* fast, float* plain) {
+  for (long i = 0; i < n; ++i) { fast[i] = uniform_pm1(bits[i]); plain[i] = uniform_from_bits(bits[i], -1.0f, 2.0f); }
+}

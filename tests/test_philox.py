@@ -45,3 +45,37 @@ def test_kernel_generator_host_build_matches(host_twin):
         o = (ctypes.c_uint * 4)()
         host_twin.twin_philox(c, k, o)
         assert tuple(o) == want
+
+
+def test_key_schedule_generator_of_the_redraw_pass_matches(host_twin):
+    """The step kernels' re-draw pass runs Philox with a host-precomputed key schedule (rmv_math.cuh
+    philox4x32_10_ks): same function as the plain generator, on the KATs and on random counters / seeds."""
+    host_twin.twin_philox_ks.argtypes = [ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_uint)]
+    for ctr, key, want in KATS:
+        o = (ctypes.c_uint * 4)()
+        host_twin.twin_philox_ks(key[0] | (key[1] << 32), (ctypes.c_uint * 4)(*ctr), o)
+        assert tuple(o) == want
+    rng = np.random.RandomState(5)
+    for _ in range(2000):
+        ctr = [int(x) for x in rng.randint(0, 2 ** 32, size=4, dtype=np.uint64)]
+        seed = int(rng.randint(0, 2 ** 63, dtype=np.uint64)) * 2 + int(rng.randint(0, 2))
+        o = (ctypes.c_uint * 4)()
+        host_twin.twin_philox_ks(seed, (ctypes.c_uint * 4)(*ctr), o)
+        want = philox.philox4x32_10(*ctr, seed & 0xFFFFFFFF, seed >> 32)
+        assert tuple(o) == tuple(int(v) for v in want)
+
+
+def test_one_fma_uniform_equals_the_two_step_form_for_every_input(host_twin):
+    """uniform_pm1(bits) = fma(bits >> 8, 2^-23, -1) against uniform_from_bits(bits, -1, 2) for all 2^24 values of
+    the 24 bits that matter (and a few patterns in the ignored low byte): identical bits, all multiples of 2^-23."""
+    n = 1 << 24
+    bits = (np.arange(n, dtype=np.uint64) << 8).astype(np.uint32)
+    bits[::7] |= 0xA5                                      # the low byte is discarded
+    fast = np.empty(n, dtype=np.float32)
+    plain = np.empty(n, dtype=np.float32)
+    host_twin.twin_uniform_pm1.argtypes = [ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    host_twin.twin_uniform_pm1(n, bits.ctypes.data, fast.ctypes.data, plain.ctypes.data)
+    assert np.array_equal(fast.view(np.uint32), plain.view(np.uint32))
+    assert fast[0] == -1.0 and fast[-1] == np.float32(1.0 - 2.0 ** -23)
+    want = (-1.0 + np.arange(n, dtype=np.float64) * 2.0 ** -23).astype(np.float32)
+    assert np.array_equal(fast, want)
