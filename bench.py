@@ -79,6 +79,24 @@ def cpu_reference(steps, warmup, target_seconds=15.0, per_core_rate=15000.0):
                       "reset-on-done, float64 NumPy per env (oracle/scalar.py)" % (cores, envs, steps, warmup, ENV_ID)}
 
 
+def cpu_vectorised(seconds=3.0, n=1 << 16):
+    """A STRONGER CPU baseline than the reference's execution model, clearly not the reference: the vectorised float64
+    NumPy restatement (oracle/batch.py) stepping N = 65536 envs per call on one core, reset-on-done included."""
+    import numpy as np
+    from oracle.batch import BatchOracle
+    o = BatchOracle(ENV_ID, n, seed=SEED, dtype=np.float64)
+    o.reset()
+    acts = np.random.RandomState(7).uniform(ACT_LO, ACT_HI, size=(8, n, ACTION_DIM))
+    o.step(acts[0])
+    k, begin = 0, time.perf_counter()
+    while time.perf_counter() - begin < seconds:
+        o.step(acts[k % 8])
+        k += 1
+    dt = time.perf_counter() - begin
+    return {"value": n * k / dt, "unit": UNIT, "cores": 1, "kind": "vectorised float64 NumPy restatement (not the reference)",
+            "sample": "%d calls x %d envs in %.1f s, one core" % (k, n, dt)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -257,6 +275,10 @@ def run_gpu_arm(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         res = cpu_reference(args.cpu_steps, 20)
         cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]}
+        try:
+            cpu["vectorised_numpy"] = cpu_vectorised()
+        except Exception as exc:               # noqa: BLE001
+            cpu["vectorised_numpy"] = {"error": str(exc)}
 
     if rank == 0:
         peaks, peak_src = load_peak()
