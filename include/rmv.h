@@ -130,6 +130,9 @@ RMV_API int rmv_set_time(rmv_env* env, double t);
 /* Launch tuning (benchmarks / sweeps): vec = envs per thread (0 = auto, 1, 2, 4),
  * block = threads per CTA of the one-env-per-thread step kernel (0 = auto, 128, 256, 512; vec > 1 always uses 128). */
 RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block);
+/* the launch shape "auto" resolves to for a batch of n_envs of `kind` (device-free query): threads per CTA and whether the
+ * episode word is fetched with the state — by kind and by whether one step's working set stays in L2 */
+RMV_API int rmv_launch_shape(int kind, int64_t n_envs, int* block, int* prefetch);
 /* step-kernel variant: use_tma != 0 selects the persistent TMA-bulk-copy / mbarrier-pipelined kernel
  * (V = 1, row-per-env actions) where it applies, 0 the register-path kernel; ctas_per_sm caps the
  * persistent grid (0 = as many as fit).  Results are identical. */

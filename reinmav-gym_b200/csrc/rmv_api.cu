@@ -516,6 +516,14 @@ static bool default_prefetch(int kind, int64_t n) {
   return working_set_is_big(kind, n);
 }
 
+extern "C" RMV_API int rmv_launch_shape(int kind, int64_t n_envs, int* block, int* prefetch) {
+  RMV_REQUIRE(kind >= 0 && kind < RMV_REINMAV, "kind %d has no one-env-per-thread step kernel", kind);
+  RMV_REQUIRE(n_envs > 0, "n_envs must be positive");
+  if (block) *block = default_block(kind, n_envs);
+  if (prefetch) *prefetch = default_prefetch(kind, n_envs) ? 1 : 0;
+  return RMV_OK;
+}
+
 template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF>
 static cudaError_t launch_step_kvf(const StepArgs& args, const cudaAccessPolicyWindow* win, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;

@@ -55,6 +55,7 @@ SIGNATURES = {
     "rmv_set_time": (_i, [_vp, ctypes.c_double]),
     "rmv_set_tuning": (_i, [_vp, _i, _i]),
     "rmv_set_host_chunks": (_i, [_vp, _i]),
+    "rmv_launch_shape": (_i, [_i, _i64, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "rmv_set_kernel": (_i, [_vp, _i, _i]),
     "rmv_set_prefetch": (_i, [_vp, _i]),
     "rmv_set_l2_persist": (_i, [_vp, _i]),

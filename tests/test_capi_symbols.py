@@ -81,3 +81,26 @@ def test_undersized_buffers_are_refused_before_the_abi():
     _need(np.empty(10, np.float32), 10, "x")
     with pytest.raises(ValueError, match="actions holds 8 elements, 16 needed"):
         _need(np.empty((4, 2), np.float32), 16, "actions")
+
+
+def test_auto_launch_shape_policy(capi):
+    """What "auto" resolves to (profiles/r1b_sweep_block_prefetch.txt): CTA 256 for quadrotor2d while one
+    step's working set stays in L2, 128 otherwise; the episode word is fetched with the state for quadrotor2d always,
+    for the slung-load kinds only when the working set streams from HBM, never for quadrotor3d."""
+    import ctypes
+    import os
+    if os.environ.get("RMV_BLOCK") or os.environ.get("RMV_PREFETCH"):
+        pytest.skip("developer overrides set")
+    lib = capi.lib()
+
+    def shape(kind, n):
+        b, p = ctypes.c_int(), ctypes.c_int()
+        assert lib.rmv_launch_shape(kind, n, ctypes.byref(b), ctypes.byref(p)) == 0
+        return b.value, p.value
+    small, big = 1 << 20, 1 << 23
+    assert shape(capi.QUAD2D, small) == (256, 1) and shape(capi.QUAD2D, big) == (128, 1)
+    assert shape(capi.QUAD2D_SLUNG, small) == (128, 0) and shape(capi.QUAD2D_SLUNG, big) == (128, 1)
+    assert shape(capi.QUAD3D, small) == (128, 0) and shape(capi.QUAD3D, big) == (128, 0)
+    assert shape(capi.QUAD3D_SLUNG, small) == (128, 1) and shape(capi.QUAD3D_SLUNG, big) == (128, 1)
+    assert shape(capi.QUAD3D_SLUNG, 1 << 16) == (128, 0)
+    assert lib.rmv_launch_shape(capi.REINMAV, small, None, None) != 0
