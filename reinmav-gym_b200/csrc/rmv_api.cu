@@ -115,7 +115,7 @@ struct rmv_env {
     cudaGraphExec_t exec = nullptr;
   };
   StepGraph graphs[4];
-  StepGraph last_seen;             // a call is captured the second time it is seen in a row
+  StepGraph seen[4];               // recently seen call shapes: a call is captured the second time it is seen
   uint64_t config_epoch = 1;       // bumped by every setter that changes what a launch looks like
   uint64_t graph_clock = 0;
   int graphs_off = 0;              // capture failed once: plain launches from then on
@@ -843,13 +843,16 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
       return RMV_OK;
     }
   }
-  if (!same(env->last_seen)) {                     // first sighting: remember it, launch plainly
-    env->last_seen.n_steps = n_steps; env->last_seen.layout = act_layout; env->last_seen.act = act_dev;
-    env->last_seen.rew = rew0; env->last_seen.done = done0; env->last_seen.act_ld = act_ld; env->last_seen.out_ld = out_ld;
-    env->last_seen.epoch = env->config_epoch;
+  rmv_env::StepGraph* known = nullptr;
+  for (auto& g : env->seen) if (same(g)) known = &g;
+  if (!known) {                                    // first sighting: remember it (LRU of 4 shapes), launch plainly
+    rmv_env::StepGraph* slot = &env->seen[0];
+    for (auto& g : env->seen) if (g.stamp < slot->stamp) slot = &g;
+    slot->n_steps = n_steps; slot->layout = act_layout; slot->act = act_dev; slot->rew = rew0; slot->done = done0;
+    slot->act_ld = act_ld; slot->out_ld = out_ld; slot->epoch = env->config_epoch; slot->stamp = ++env->graph_clock;
     return launch_all(st, true);
   }
-  // second sighting in a row: capture on an internal stream (the caller's may be the legacy default stream)
+  // second sighting: capture on an internal stream (the caller's may be the legacy default stream)
   if (!env->capture_stream && cudaStreamCreateWithFlags(&env->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError(); env->graphs_off = 1; return launch_all(st, true);
   }
@@ -873,7 +876,7 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
     if (!slot || g.stamp < slot->stamp) slot = &g;
   }
   if (slot->exec) cudaGraphExecDestroy(slot->exec);
-  *slot = env->last_seen;
+  *slot = *known;
   slot->exec = exec;
   slot->stamp = ++env->graph_clock;
   RMV_CUDA(cudaGraphLaunch(exec, st));

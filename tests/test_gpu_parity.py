@@ -255,8 +255,8 @@ def test_step_is_cuda_graph_capturable(torch, rmv):
 
 
 def test_step_many_graph_replay_bitwise(torch, rmv):
-    """rmv_step_many(fused=0) captures a repeated call in a CUDA graph the second time it sees it and replays it from
-    then on: plain launch, capture + launch, replays, a second call shape (LRU), and a re-seed in between (the cached
+    """rmv_step_many(fused=0) captures a call shape in a CUDA graph the second time it sees it (consecutively or not) and
+    replays it from then on: plain launch, capture + launch, replays, a second call shape (LRU), and a re-seed in between (the cached
     graphs carry the old Philox key and must not be used) — all against single rmv_step launches, bit for bit."""
     env_id, n, seed, K = "quadrotor3d-v0", 128 * 60 + 11, 13, 16
     dev = "cuda:0"
@@ -268,7 +268,8 @@ def test_step_many_graph_replay_bitwise(torch, rmv):
     a = rmv.QuadBatch(env_id, n, seed=seed)
     b = rmv.QuadBatch(env_id, n, seed=seed)
     a.reset(); b.reset()
-    plan = [(K, None), (K, None), (K, None), (6, None), (6, None), (6, None), (K, None), (K, 99), (K, None), (K, None), (K, None)]
+    plan = [(K, None), (K, None), (K, None), (6, None), (6, None), (6, None), (K, None), (K, 99), (K, None), (K, None), (K, None),
+            (K, 7), (6, None), (K, None), (6, None), (K, None), (6, None)]      # alternating shapes are captured as well
     for m, reseed in plan:
         if reseed is not None:
             a.set_seed(reseed); b.set_seed(reseed)
