@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RMV_ABI_VERSION 1
+#define RMV_ABI_VERSION 2
 
 /* env kinds = the four registered native ids, gym_reinmav/__init__.py:8-26 */
 enum {
@@ -93,6 +93,9 @@ typedef struct rmv_params {
   int32_t thrust_clamp;     /* 1 for quadrotor2d: thrust = max(thrust, 0) (quadrotor2d.py:76-77) */
   float first_done_reward;  /* 1.0  first done ever returned by an env (quadrotor3d.py:114-117)  */
   float later_done_reward;  /* 0.0  every later done (quadrotor3d.py:118-122)                   */
+  float reward_scale;       /* 1.0  the launcher's --reward_scale (run.py:89 -> baselines RewardScaler, applied
+                               OUTSIDE Monitor): the reward a step returns is reward * reward_scale, one float32
+                               product; episode returns (info['episode']['r']) stay unscaled            */
 } rmv_params;
 
 typedef struct rmv_env rmv_env;
@@ -143,7 +146,8 @@ RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm);
 RMV_API int rmv_set_prefetch(rmv_env* env, int mode);
 /* Opt-in: keep the handle's state resident in L2 between steps with an access-policy window on the state buffer
  * (persisting on hit, streaming on miss).  mode 1 sets the DEVICE-WIDE cudaLimitPersistingL2CacheSize to the state size
- * (that much L2 is taken from everything else on the GPU) and fails with RMV_EINVAL if the state does not fit the
+ * (that much L2 is taken from everything else on the GPU; with several handles on one device the limit is the largest
+ * request and is released when the last window goes) and fails with RMV_EINVAL if the state does not fit the
  * device's carve-out; 0 / -1 (auto = off) release it.  Pays when the state fits the carve-out but state + per-step
  * streams do not fit L2 (+10-13 % measured); launches that also write observation rows do not use the window.
  * Results are identical. */
@@ -178,7 +182,10 @@ RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* obs_aos_dev,
  * Quadrotor3DSlungload.step (quadrotor3d_slungload.py:87-167) and, with auto_reset, the
  * reset-on-done of the caller (test/test_quadrotor3d.py:21-22) / of baselines' vec-envs behind
  * make_vec_env (run.py:89).
- *   act_dev      float32 actions, layout RMV_ACT_AOS ([n][A]) or RMV_ACT_SOA ([A][act_ld])
+ *   act_dev      float32 actions, layout RMV_ACT_AOS ([n][A]) or RMV_ACT_SOA ([A][act_ld]).  RMV_ACT_AOS rows are
+ *                fetched with one A*4-byte vector load each: act_dev must be aligned to A*4 bytes (16 for the 3D
+ *                kinds, 8 for the planar ones; any tensor allocation is), else RMV_EALIGN — also for
+ *                rmv_step_rows, rmv_step_many and rmv_step_host
  *   reward_dev   float32 [n]
  *   done_dev     uint8   [n]  (0 / 1)
  *   obs_aos_dev  NULL, or float32 [n][S]: observation rows after the step (obs == state in the

@@ -47,7 +47,8 @@ def default_params(kind, repair="A"):
     quadrotor2d_slungload.py:44-58)."""
     p = dict(mass=1.0, load_mass=0.1, dt=0.01, gravity=9.8, tether_len=0.0,
              pos_done=3.0, vel_done=10.0, thrust_scale=1.0, thrust_clamp=0,
-             first_done_reward=1.0, later_done_reward=0.0)
+             first_done_reward=1.0, later_done_reward=0.0,
+             reward_scale=1.0)                               # run.py:89 reward_scale= -> baselines RewardScaler
     if kind == QUAD2D:
         p.update(thrust_scale=10.0, thrust_clamp=1)          # quadrotor2d.py:75-77
         if repair == "B":
@@ -419,6 +420,9 @@ class BatchOracle:
                           np.where(self.ever_done, self._c(self.p["later_done_reward"]), self._c(self.p["first_done_reward"])),
                           -n_rew).astype(self.dtype)
         self.ever_done |= done
+        self.raw_reward = reward                           # what Monitor accumulates (RewardScaler wraps Monitor)
+        if self.p["reward_scale"] != 1.0:
+            reward = (reward * self._c(self.p["reward_scale"])).astype(self.dtype)
         if auto_reset and done.any():
             self.reset(mask=done)
         return self.obs(), reward, done

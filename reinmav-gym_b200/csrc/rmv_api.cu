@@ -131,6 +131,14 @@ static void disable_l2_window(rmv_env* e);
 // developer switch for A/B measurements (tools/sweep.py); the default is the product configuration
 static int g_use_pdl = (getenv("RMV_NO_PDL") == nullptr) ? 1 : 0;
 
+// per-device caches (function attributes, occupancy, the persisting-L2 carve-out) are indexed by device ordinal
+constexpr int kMaxDevices = 64;
+static inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 static inline bool aligned(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 static inline unsigned blocks_for(int64_t n, int64_t block) { return (unsigned)((n + block - 1) / block); }
@@ -144,6 +152,7 @@ static DevParams to_dev(const rmv_params& p) {
   d.tether_len = p.tether_len; d.pos_done = p.pos_done; d.vel_done = p.vel_done;
   d.thrust_scale = p.thrust_scale; d.first_done_reward = p.first_done_reward;
   d.later_done_reward = p.later_done_reward; d.thrust_clamp = p.thrust_clamp;
+  d.reward_scale = p.reward_scale;
   finish_params(d);
   return d;
 }
@@ -164,7 +173,7 @@ extern "C" RMV_API int rmv_default_params(int kind, rmv_params* out) {
   rmv_params p;
   p.mass = 1.0f; p.load_mass = 0.1f; p.dt = 0.01f; p.gravity = 9.8f; p.tether_len = 0.0f;
   p.pos_done = 3.0f; p.vel_done = 10.0f; p.thrust_scale = 1.0f; p.thrust_clamp = 0;
-  p.first_done_reward = 1.0f; p.later_done_reward = 0.0f;
+  p.first_done_reward = 1.0f; p.later_done_reward = 0.0f; p.reward_scale = 1.0f;
   if (kind == RMV_QUAD2D) { p.thrust_scale = 10.0f; p.thrust_clamp = 1; }
   if (kind == RMV_QUAD2D_SLUNG) { p.tether_len = 0.5f; p.pos_done = 2.0f; }
   if (kind == RMV_QUAD3D_SLUNG) { p.tether_len = 1.5f; }
@@ -459,6 +468,11 @@ extern "C" RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* o
 // 2.3x SLOWER with a hit ratio < 1 (state larger than the carve-out: the persisting subset thrashes), which is why that
 // case is refused; slower with observation rows (the carve-out is taken from the streams' share).  The carve-out is a
 // device-wide limit that also shrinks the L2 available to everything else on the GPU (the policy network) — hence opt-in.
+// The carve-out (cudaLimitPersistingL2CacheSize) is ONE device-wide number shared by every handle on the device:
+// it is kept at the largest request of the handles that currently hold a window and released by the last one.
+struct L2Carve { int users = 0; size_t bytes = 0; };
+static L2Carve g_l2_carve[kMaxDevices];
+
 static int enable_l2_window(rmv_env* e) {
   int max_persist = 0, max_window = 0;
   RMV_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device));
@@ -471,7 +485,12 @@ static int enable_l2_window(rmv_env* e) {
   if (state_bytes > (size_t)max_window || (double)carve < 0.9 * (double)state_bytes)
     return fail(RMV_EINVAL, "state (%zu bytes) exceeds the persisting L2 carve-out (%d bytes) / window (%d bytes): a partial "
                             "window thrashes (measured 2.3x slower), refused", state_bytes, max_persist, max_window);
-  RMV_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+  L2Carve& dev_carve = g_l2_carve[e->device < kMaxDevices ? e->device : 0];
+  if (carve > dev_carve.bytes) {                   // grow only: another handle's window stays covered
+    RMV_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    dev_carve.bytes = carve;
+  }
+  dev_carve.users += 1;
   e->l2_window = cudaAccessPolicyWindow{};
   e->l2_window.base_ptr = e->state;
   e->l2_window.num_bytes = state_bytes;
@@ -485,8 +504,13 @@ static void disable_l2_window(rmv_env* e) {
   if (!e->l2_ready) return;
   e->l2_ready = 0;
   e->l2_window = cudaAccessPolicyWindow{};
-  cudaCtxResetPersistingL2Cache();                             // un-pin the state's lines
-  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+  L2Carve& dev_carve = g_l2_carve[e->device < kMaxDevices ? e->device : 0];
+  if (dev_carve.users > 0) dev_carve.users -= 1;
+  if (dev_carve.users == 0) {                                  // last window on this device: un-pin and give the L2 back
+    cudaCtxResetPersistingL2Cache();
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    dev_carve.bytes = 0;
+  }
   cudaGetLastError();
 }
 // the window is attached to launches without observation rows only (measured: rows + carve-out is a net loss)
@@ -534,11 +558,12 @@ static cudaError_t launch_step_kvf(const StepArgs& args, const cudaAccessPolicyW
     if (per > smem) smem = per & ~(size_t)127;
   }
   if (smem > 48 * 1024) {
-    static bool raised = false;      // per instantiation
-    if (!raised) {
+    static bool raised[kMaxDevices] = {};      // per instantiation AND per device (function attributes are per context)
+    const int dev = current_device();
+    if (!raised[dev]) {
       cudaError_t e = cudaFuncSetAttribute(k_step<KIND, V, OBS, TRACK, BLOCK, PREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      raised = true;
+      raised[dev] = true;
     }
   }
   cudaLaunchConfig_t cfg{};
@@ -594,16 +619,16 @@ static cudaError_t launch_step_tma(const rmv_env* e, const StepArgs& args, cudaS
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   constexpr int SP = (S % 2 == 0) ? S + 1 : S;
   const size_t smem = (size_t)kTmaStages * (S + A) * kTile * 4 + (OBS ? (size_t)kWarps * 32 * SP * sizeof(float) : 0);
-  static int resident = 0, sms = 0;
-  if (resident == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int resident_of[kMaxDevices] = {}, sms_of[kMaxDevices] = {};      // per instantiation and per device
+  const int dev = current_device();
+  if (resident_of[dev] == 0) {
+    cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(k_step_tma<KIND, OBS, TRACK, kTmaStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_step_tma<KIND, OBS, TRACK, kTmaStages>, kBlock, smem);
-    if (resident < 1) resident = 1;
-    if (sms < 1) sms = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_tma<KIND, OBS, TRACK, kTmaStages>, kBlock, smem);
+    if (resident_of[dev] < 1) resident_of[dev] = 1;
+    if (sms_of[dev] < 1) sms_of[dev] = 1;
   }
+  const int resident = resident_of[dev], sms = sms_of[dev];
   const unsigned tiles = blocks_for(args.n, kTile);
   int per_sm = e->tma_ctas_per_sm > 0 && e->tma_ctas_per_sm < resident ? e->tma_ctas_per_sm : resident;
   const unsigned persistent = (unsigned)sms * (unsigned)per_sm;
@@ -709,6 +734,10 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
   RMV_REQUIRE(act_layout == RMV_ACT_AOS || act_layout == RMV_ACT_SOA, "bad act_layout %d", act_layout);
   if (act_layout == RMV_ACT_SOA) RMV_REQUIRE(act_ld >= cn, "act_ld (%lld) < n_envs", (long long)act_ld);
   RMV_REQUIRE(aligned(act, 4) && aligned(rew, 4) && aligned(obs, 4), "float buffers must be 4-byte aligned");
+  // a row-per-env action is fetched with ONE A*4-byte vector load (float4 / float2): every row must be aligned to it
+  if (act_layout == RMV_ACT_AOS && (!aligned(act, (size_t)e->A * 4u) || ((act_step_stride * 4) % ((int64_t)e->A * 4)) != 0))
+    return fail(RMV_EALIGN, "row-per-env actions must be aligned to one row (%d bytes); got %p, step stride %lld floats",
+                e->A * 4, (const void*)act, (long long)act_step_stride);
   // widest vector width every buffer supports (auto = 1: measured fastest, profiles/r1_sweep_v1_tiled.txt)
   int vec = e->vec ? e->vec : 1;
   auto ok_for = [&](int v) {

@@ -356,7 +356,7 @@ __device__ __forceinline__ void step_envs(const StepArgs& a, uint32_t cta_e0, ui
           ep_ret[v] = -r;                          // becomes 0 after the "+= r" below
         }
       }
-      rew[v] = r;
+      rew[v] = scaled_reward(a.P, r);
       if (TRACK) ep_ret[v] += r;
     }
     if (full) {
@@ -550,7 +550,7 @@ k_step_rows(const StepArgs a) {
         ep_ret = -r;
       }
     }
-    __stcs(a.reward + e, r);
+    __stcs(a.reward + e, scaled_reward(a.P, r));
     __stcs(reinterpret_cast<unsigned char*>(a.done) + e, (unsigned char)(done ? 1 : 0));
     if (TRACK) a.ep_return[e] = ep_ret + r;
   }
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(128) k_rollout(const StepArgs a) {
           }
         }
       }
-      rew[v] = r;
+      rew[v] = scaled_reward(a.P, r);
       if (a.ep_return) ep_ret[v] += r;
     }
     store_outputs<V>(a, (int64_t)step * a.out_ld + e0, e0, full, rew, dn);

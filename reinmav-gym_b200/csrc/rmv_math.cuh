@@ -92,6 +92,7 @@ struct DevParams {
   float mass, load_mass, dt, neg_gravity, tether_len;
   float pos_done, vel_done, thrust_scale;
   float first_done_reward, later_done_reward;
+  float reward_scale;     // baselines RewardScaler (run.py:89 reward_scale=): returned reward = reward * reward_scale
   float inv_total_mass;   // 1.0f / (mass + load_mass), two float32 ops
   float inv_mass;         // 1.0f / mass (exactly 1 for the reference's mass = 1)
   float pos_sq_max;       // largest float32 y with sqrt_rn(y) <= pos_done: |p| > pos_done  <=>  p.p > pos_sq_max
@@ -508,5 +509,8 @@ RMV_HD bool is_done(const DevParams& P, float pos_sq, float vel_sq) {
 RMV_HD float reward_of(const DevParams& P, bool done, bool ever_done, float n_rew) {
   return done ? (ever_done ? P.later_done_reward : P.first_done_reward) : -n_rew;
 }
+// what step() hands back: baselines' RewardScaler sits OUTSIDE Monitor (make_vec_env, run.py:89), so the episode
+// return keeps the raw reward and only the returned value is scaled.  One float32 product; exact for scale = 1.
+RMV_HD float scaled_reward(const DevParams& P, float r) { return (rf(r) * rf(P.reward_scale)).v; }
 
 }  // namespace rmv

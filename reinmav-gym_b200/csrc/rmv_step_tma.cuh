@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kBlock) k_step_tma(const StepArgs a) {
       }
     }
     if (valid) {
-      __stcs(a.reward + e, r);
+      __stcs(a.reward + e, scaled_reward(a.P, r));
       __stcs(reinterpret_cast<unsigned char*>(a.done) + e, (unsigned char)(done ? 1 : 0));
       if (TRACK) a.ep_return[e] = ep_ret + r;
     }

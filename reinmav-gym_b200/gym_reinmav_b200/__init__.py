@@ -42,10 +42,39 @@ def make(env_id, **kwargs):
     return getattr(import_module(mod), cls)(**kwargs)
 
 
-def make_vec_env(env_id, env_type="native", num_env=1, seed=0, device=0, **kwargs):
-    """Same call shape as baselines' ``make_vec_env(env_id, env_type, num_env, seed, ...)`` used at
-    /root/reference/gym_reinmav/run.py:89."""
-    return QuadVecEnv(env_id, num_env, device=device, seed=0 if seed is None else seed, **kwargs)
+def make_vec_env(env_id, env_type="native", num_env=1, seed=0, wrapper_kwargs=None, env_kwargs=None, start_index=0,
+                 reward_scale=1.0, flatten_dict_observations=True, gamestate=None, initializer=None, force_dummy=False,
+                 **options):
+    """baselines' ``make_vec_env`` for the native ids, with its signature — the reference's launcher calls it as
+    ``make_vec_env(env_id, env_type, args.num_env or 1, seed, reward_scale=args.reward_scale,
+    flatten_dict_observations=flatten_dict_observations)`` (/root/reference/gym_reinmav/run.py:89) and that call works
+    here verbatim.  What the baselines arguments mean on this path:
+
+    * ``num_env``, ``seed``: N envs in ONE handle; ``seed`` keys the Philox reset stream (``None`` -> 0).
+    * ``start_index``: baselines seeds sub-env ``i`` with ``seed + start_index + i``; here it is the global id of env 0
+      (``env_id_offset``), which is what the reset stream is keyed by.
+    * ``reward_scale``: baselines wraps each env in ``RewardScaler`` OUTSIDE ``Monitor`` when it is not 1 — the returned
+      rewards are multiplied inside the step kernel (``rmv_params.reward_scale``), ``info['episode']['r']`` is not.
+    * ``flatten_dict_observations``: observations are flat Boxes already (nothing to flatten).
+    * ``force_dummy``: irrelevant (there is no process fan-out).
+    * ``wrapper_kwargs`` / ``env_kwargs`` / ``gamestate`` / ``initializer``: atari / retro / user hooks that have no
+      meaning for these envs; anything but ``None`` / ``{}`` is refused rather than silently dropped.
+
+    ``options`` are QuadVecEnv's own keywords (``device``, ``params``, ``monitor``, ``return_obs``, ``copy_outputs``,
+    ``state_layout``)."""
+    if env_type not in (None, "native"):
+        raise ValueError("env_type %r: this package provides the 'native' envs only" % (env_type,))
+    for name, value in (("wrapper_kwargs", wrapper_kwargs), ("env_kwargs", env_kwargs), ("gamestate", gamestate),
+                        ("initializer", initializer)):
+        if value:
+            raise ValueError("make_vec_env(%s=%r) has no meaning for the native quadrotor envs" % (name, value))
+    params = dict(options.pop("params", None) or {})
+    if reward_scale is not None and float(reward_scale) != 1.0:
+        params["reward_scale"] = float(reward_scale)
+    if "env_id_offset" in options:
+        start_index = options.pop("env_id_offset")
+    return QuadVecEnv(env_id, int(num_env or 1), seed=0 if seed is None else seed, env_id_offset=int(start_index),
+                      params=params or None, **options)
 
 
 def _register_with_gym():

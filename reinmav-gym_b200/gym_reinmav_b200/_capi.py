@@ -13,6 +13,7 @@ QUAD2D, QUAD2D_SLUNG, QUAD3D, QUAD3D_SLUNG, REINMAV = 0, 1, 2, 3, 4
 ACT_AOS, ACT_SOA = 0, 1
 TRACK_EPISODES = 1
 EVER_DONE_BIT = 0x80000000
+ABI_VERSION = 2
 
 
 class RmvError(RuntimeError):
@@ -27,7 +28,7 @@ class Params(ctypes.Structure):
                 ("gravity", ctypes.c_float), ("tether_len", ctypes.c_float), ("pos_done", ctypes.c_float),
                 ("vel_done", ctypes.c_float), ("thrust_scale", ctypes.c_float),
                 ("thrust_clamp", ctypes.c_int32), ("first_done_reward", ctypes.c_float),
-                ("later_done_reward", ctypes.c_float)]
+                ("later_done_reward", ctypes.c_float), ("reward_scale", ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -95,8 +96,8 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.rmv_abi_version() != 1:
-            raise ImportError("librmv.so ABI version %d, expected 1" % handle.rmv_abi_version())
+        if handle.rmv_abi_version() != ABI_VERSION:
+            raise ImportError("librmv.so ABI version %d, expected %d" % (handle.rmv_abi_version(), ABI_VERSION))
         _lib = handle
     return _lib
 

@@ -20,22 +20,45 @@ ENV_IDS = {
 }
 
 
-def _ptr(x):
-    """Raw address of a device (or pinned host) buffer; None -> NULL."""
+HOST = "host"
+
+
+def _ptr(x, dtype=None, where=None, what="buffer"):
+    """Raw address of a device (or pinned host) buffer; None -> NULL.
+
+    The C-ABI takes plain pointers, so this is the only layer that can refuse a buffer of the wrong element type or on
+    the wrong side of the bus before a kernel reinterprets it (a float64 action tensor read as float32, a CPU tensor's
+    address dereferenced on the GPU — an illegal-address fault kills the CUDA context).  ``dtype``: expected element
+    type name ("float32", "uint8", ...); ``where``: a device ordinal (the buffer must live on that GPU), ``HOST`` (it
+    must be host memory) or None (not checked).  Integer addresses cannot be checked."""
     if x is None:
         return None
     if isinstance(x, int):
         return x
     if hasattr(x, "data_ptr"):                       # torch.Tensor
         if not x.is_contiguous():
-            raise ValueError("tensor passed to librmv must be contiguous")
+            raise ValueError("%s: tensor passed to librmv must be contiguous" % what)
+        if dtype is not None and str(x.dtype) != "torch." + dtype:
+            raise TypeError("%s must be %s, got %s" % (what, dtype, x.dtype))
+        if where == HOST and x.is_cuda:
+            raise ValueError("%s must be a host buffer, got a tensor on %s" % (what, x.device))
+        if isinstance(where, int) and (not x.is_cuda or x.device.index != where):
+            raise ValueError("%s must be on cuda:%d, got a tensor on %s" % (what, where, x.device))
         return x.data_ptr()
     cai = getattr(x, "__cuda_array_interface__", None)
     if cai is not None:
+        if dtype is not None and np.dtype(cai["typestr"]) != np.dtype(dtype):
+            raise TypeError("%s must be %s, got %s" % (what, dtype, np.dtype(cai["typestr"])))
+        if where == HOST:
+            raise ValueError("%s must be a host buffer, got a device array" % what)
         return cai["data"][0]
     if isinstance(x, np.ndarray):                    # host buffer (for the *_host entry points)
         if not x.flags["C_CONTIGUOUS"]:
-            raise ValueError("array passed to librmv must be C-contiguous")
+            raise ValueError("%s: array passed to librmv must be C-contiguous" % what)
+        if dtype is not None and x.dtype != np.dtype(dtype):
+            raise TypeError("%s must be %s, got %s" % (what, dtype, x.dtype))
+        if isinstance(where, int):
+            raise ValueError("%s must be a device buffer on cuda:%d, got a NumPy array" % (what, where))
         return x.ctypes.data
     raise TypeError("cannot take the address of %r" % type(x))
 
@@ -149,7 +172,8 @@ class QuadBatch:
 
     # ---------------------------------------------------------------- hot path (device buffers)
     def reset(self, mask=None, obs=None, stream=None):
-        check(lib().rmv_reset(self._h, _ptr(mask), _ptr(obs), _stream(stream, self.device)))
+        d = self.device
+        check(lib().rmv_reset(self._h, _ptr(mask, "uint8", d, "mask"), _ptr(obs, "float32", d, "obs"), _stream(stream, d)))
         self.launches += 1
 
     def _check_io(self, actions, reward, done, layout, act_ld, steps=1, out_ld=0):
@@ -162,8 +186,10 @@ class QuadBatch:
     def step(self, actions, reward, done, obs=None, auto_reset=True, layout=ACT_AOS, act_ld=0, stream=None):
         self._check_io(actions, reward, done, layout, act_ld)
         _need(obs, self.num_envs * self.state_dim, "obs")
-        check(lib().rmv_step(self._h, _ptr(actions), layout, int(act_ld), _ptr(reward), _ptr(done), _ptr(obs),
-                             1 if auto_reset else 0, _stream(stream, self.device)))
+        d = self.device
+        check(lib().rmv_step(self._h, _ptr(actions, "float32", d, "actions"), layout, int(act_ld),
+                             _ptr(reward, "float32", d, "reward"), _ptr(done, "uint8", d, "done"),
+                             _ptr(obs, "float32", d, "obs"), 1 if auto_reset else 0, _stream(stream, d)))
         self.launches += 1
 
     def step_rows(self, rows_in, actions, reward, done, rows_out, auto_reset=True, layout=ACT_AOS, act_ld=0, stream=None):
@@ -172,30 +198,39 @@ class QuadBatch:
         self._check_io(actions, reward, done, layout, act_ld)
         _need(rows_in, self.num_envs * self.state_dim, "rows_in")
         _need(rows_out, self.num_envs * self.state_dim, "rows_out")
-        check(lib().rmv_step_rows(self._h, _ptr(rows_in), _ptr(actions), layout, int(act_ld), _ptr(reward), _ptr(done),
-                                  _ptr(rows_out), 1 if auto_reset else 0, _stream(stream, self.device)))
+        d = self.device
+        check(lib().rmv_step_rows(self._h, _ptr(rows_in, "float32", d, "rows_in"), _ptr(actions, "float32", d, "actions"),
+                                  layout, int(act_ld), _ptr(reward, "float32", d, "reward"), _ptr(done, "uint8", d, "done"),
+                                  _ptr(rows_out, "float32", d, "rows_out"), 1 if auto_reset else 0, _stream(stream, d)))
         self.launches += 1
 
     def set_state_device(self, rows, stream=None):
         """Load [N, S] device rows into the handle's tiled state."""
-        check(lib().rmv_set_state(self._h, _ptr(rows), 1, _stream(stream, self.device)))
+        check(lib().rmv_set_state(self._h, _ptr(rows, "float32", self.device, "rows"), 1, _stream(stream, self.device)))
 
     def step_many(self, n_steps, actions, reward=None, done=None, out_ld=0, layout=ACT_SOA, act_ld=0, fused=False,
                   stream=None):
+        """``actions`` is [T, A, act_ld] (``ACT_SOA``, the default; ``act_ld`` 0 -> the handle's padded env count
+        ``self.ld``) or [T, N, A] (``ACT_AOS``)."""
+        if layout == ACT_SOA and not act_ld:
+            act_ld = self.ld
         if self.action_dim:
             self._check_io(actions, reward, done, layout, act_ld, steps=int(n_steps), out_ld=out_ld)
-        check(lib().rmv_step_many(self._h, int(n_steps), _ptr(actions), layout, int(act_ld), _ptr(reward), _ptr(done),
-                                  int(out_ld or self.num_envs), 1 if fused else 0, _stream(stream, self.device)))
+        d = self.device
+        check(lib().rmv_step_many(self._h, int(n_steps), _ptr(actions, "float32", d, "actions"), layout, int(act_ld),
+                                  _ptr(reward, "float32", d, "reward"), _ptr(done, "uint8", d, "done"),
+                                  int(out_ld or self.num_envs), int(fused), _stream(stream, d)))
         self.launches += 1 if fused else int(n_steps)
 
     # ---------------------------------------------------------------- hot path (host buffers)
     def step_host(self, actions, reward, done, obs=None, auto_reset=True, stream=None):
-        check(lib().rmv_step_host(self._h, _ptr(actions), _ptr(reward), _ptr(done), _ptr(obs),
+        check(lib().rmv_step_host(self._h, _ptr(actions, "float32", HOST, "actions"), _ptr(reward, "float32", HOST, "reward"),
+                                  _ptr(done, "uint8", HOST, "done"), _ptr(obs, "float32", HOST, "obs"),
                                   1 if auto_reset else 0, _stream(stream, self.device)))
         self.launches += 1
 
     def reset_host(self, obs, stream=None):
-        check(lib().rmv_reset_host(self._h, _ptr(obs), _stream(stream, self.device)))
+        check(lib().rmv_reset_host(self._h, _ptr(obs, "float32", HOST, "obs"), _stream(stream, self.device)))
         self.launches += 1
 
     # ---------------------------------------------------------------- controllers
@@ -208,13 +243,14 @@ class QuadBatch:
 
     def control(self, actions, ref_pos=None, ref_vel=None, layout=ACT_AOS, act_ld=0, stream=None):
         """The reference's geometric controller for every env -> device action buffer."""
-        check(lib().rmv_control(self._h, self._ref(ref_pos), self._ref(ref_vel), _ptr(actions), layout, int(act_ld),
+        check(lib().rmv_control(self._h, self._ref(ref_pos), self._ref(ref_vel),
+                                _ptr(actions, "float32", self.device, "actions"), layout, int(act_ld),
                                 _stream(stream, self.device)))
         self.launches += 1
 
     def control_host(self, actions, ref_pos=None, ref_vel=None, stream=None):
-        check(lib().rmv_control_host(self._h, self._ref(ref_pos), self._ref(ref_vel), _ptr(actions),
-                                     _stream(stream, self.device)))
+        check(lib().rmv_control_host(self._h, self._ref(ref_pos), self._ref(ref_vel),
+                                     _ptr(actions, "float32", HOST, "actions"), _stream(stream, self.device)))
         self.launches += 1
 
     # ---------------------------------------------------------------- state access
@@ -269,6 +305,6 @@ def fill_uniform_actions(actions, num_envs, action_dim, low, high, seed, env_id_
                          layout=ACT_AOS, act_ld=0, device=0, stream=None):
     """Random-policy actions ~ U[low, high) written on the device (Philox, keyed by global env id)."""
     _need(actions, int(action_dim) * (int(act_ld) if layout == ACT_SOA and act_ld else int(num_envs)), "action buffer")
-    check(lib().rmv_fill_uniform_actions(_ptr(actions), int(num_envs), int(action_dim), layout, int(act_ld),
+    check(lib().rmv_fill_uniform_actions(_ptr(actions, "float32", int(device), "action buffer"), int(num_envs), int(action_dim), layout, int(act_ld),
                                          float(low), float(high), int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_id_offset),
                                          int(step_index), int(device), _stream(stream, device)))

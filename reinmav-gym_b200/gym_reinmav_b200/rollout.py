@@ -31,6 +31,7 @@ class RolloutBuffer:
         self.rewards = torch.empty((self.T, n), dtype=torch.float32, device=dev)
         self.dones = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
         self._have_first = False
+        self._carry = False                                          # obs[T] of the last collect() is not yet in obs[0]
         # per-step views and raw addresses, built once: the collect() loop then costs one policy call and one
         # C-ABI call per step (at N = 2^20 a quadrotor2d step kernel takes ~10 us; seven tensor-indexing
         # operations per step cost more than that on the host)
@@ -44,14 +45,19 @@ class RolloutBuffer:
     def start(self):
         """reset() all envs; the first observation lands in ``obs[0]``."""
         self.venv.batch.reset(obs=self.obs[0])
-        self._have_first = True
+        self._have_first, self._carry = True, False
         return self.obs[0]
 
     def collect(self, policy):
         """Run ``T`` steps.  ``policy(obs[N,S]) -> actions[N,A]`` (CUDA tensors); its output is copied into
-        ``actions[t]`` unless it already is that slice.  Returns self; ``obs[T]`` is the bootstrap observation."""
+        ``actions[t]`` unless it already is that slice.  Returns self; ``obs[T]`` is the bootstrap observation.
+
+        A second ``collect()`` continues where the first one ended, as ppo2's Runner does by keeping ``self.obs``:
+        the bootstrap observation is carried into ``obs[0]`` first (``roll()``), whether or not the caller did so."""
         if not self._have_first:
             self.start()
+        if self._carry:
+            self.roll()
         b = self.venv.batch
         stream = torch.cuda.current_stream(self.venv.device).cuda_stream
         obs_t, act_t, obs_p, act_p, rew_p, done_p = self.obs_views, self.action_views, self._obs_p, self._act_p, self._rew_p, self._done_p
@@ -62,14 +68,18 @@ class RolloutBuffer:
                     act_t[t].copy_(a)
                 b.step_rows(obs_p[t], act_p[t], rew_p[t], done_p[t], obs_p[t + 1], auto_reset=True, stream=stream)
             b.set_state_device(obs_p[self.T], stream=stream)       # the handle's own state follows the rollout
+            self._carry = True
             return self
         for t in range(self.T):
             a = policy(obs_t[t])
             if a.data_ptr() != act_p[t]:
                 act_t[t].copy_(a)
             b.step(act_p[t], rew_p[t], done_p[t], obs=obs_p[t + 1], auto_reset=True, stream=stream)
+        self._carry = True
         return self
 
     def roll(self):
         """Make the bootstrap observation the first one of the next rollout (PPO2 keeps ``self.obs``)."""
-        self.obs[0].copy_(self.obs[self.T])
+        if self._carry:
+            self.obs[0].copy_(self.obs[self.T])
+            self._carry = False

@@ -16,6 +16,7 @@ Two ways to step:
   that alias internal buffers (valid until the next call).
 """
 import ctypes
+import time
 from collections.abc import Sequence
 
 import numpy as np
@@ -36,8 +37,12 @@ def make_spaces(kind):
     if kind == _capi.REINMAV:       # the reference leaves both spaces undefined (reinmav_env.py:65-70); no action input
         return Box(low=-np.inf, high=np.inf, shape=(s,), dtype=np.float32), None
     lo, hi = _ACTION_BOX[kind]
-    return (Box(low=-10.0, high=10.0, shape=(s,), dtype=np.float32),
-            Box(low=lo, high=hi, shape=(a,), dtype=np.float32))
+    # quadrotor3d.py:70-71 declares both spaces with dtype=np.float (float64); the other three kinds say float32.
+    # (The arrays step()/reset() return stay float32 — the kernel's arithmetic type; float32 is contained in a
+    # float64 Box.)
+    dt = np.float64 if kind == _capi.QUAD3D else np.float32
+    return (Box(low=-10.0, high=10.0, shape=(s,), dtype=dt),
+            Box(low=lo, high=hi, shape=(a,), dtype=dt))
 
 
 class _Pinned:
@@ -59,8 +64,8 @@ class _Pinned:
 
 class SparseInfos(Sequence):
     """``infos`` without building N dicts per step: ``infos[i]`` is ``{}`` unless env i just
-    finished an episode, in which case it is ``{'episode': {'r': return, 'l': length}}``
-    (the key baselines' ppo2 Runner collects: ``info.get('episode')``)."""
+    finished an episode, in which case it is ``{'episode': {'r': return, 'l': length, 't': seconds}}``
+    (baselines Monitor's record; ppo2's Runner collects it with ``info.get('episode')``)."""
 
     _EMPTY = {}
 
@@ -80,7 +85,7 @@ class SparseInfos(Sequence):
         return self._fin.get(i, self._EMPTY)
 
     def episodes(self):
-        """Only the finished ones: {env index: {'r':..., 'l':...}}."""
+        """Only the finished ones: {env index: {'r':..., 'l':..., 't':...}}."""
         return {i: d["episode"] for i, d in self._fin.items()}
 
 
@@ -111,7 +116,9 @@ class QuadVecEnv:
         self._done = _Pinned((n,), np.uint8)
         self._pending = None
         self._t = None            # torch buffers for step_tensor, made on first use
+        self._tstart = time.time()
         self.closed = False
+        self.viewer = None
 
     # ------------------------------------------------------------------ VecEnv protocol (host)
     def seed(self, seed=None):
@@ -159,7 +166,8 @@ class QuadVecEnv:
         if idx.size == 0:
             return {}
         r, l = self.batch.gather_episodes(idx)
-        return {int(i): {"episode": {"r": float(r[k]), "l": int(l[k])}} for k, i in enumerate(idx)}
+        t = round(time.time() - self._tstart, 6)          # Monitor: seconds since the env was created
+        return {int(i): {"episode": {"r": float(r[k]), "l": int(l[k]), "t": t}} for k, i in enumerate(idx)}
 
     # ------------------------------------------------------------------ device-resident stepping
     def _tensors(self):

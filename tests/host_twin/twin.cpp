@@ -14,6 +14,7 @@ static DevParams to_dev(const rmv_params& p) {
   d.tether_len = p.tether_len; d.pos_done = p.pos_done; d.vel_done = p.vel_done;
   d.thrust_scale = p.thrust_scale; d.first_done_reward = p.first_done_reward;
   d.later_done_reward = p.later_done_reward; d.thrust_clamp = p.thrust_clamp;
+  d.reward_scale = p.reward_scale;
   finish_params(d);
   return d;
 }

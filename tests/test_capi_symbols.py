@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(capi):
 
 def test_device_free_queries(capi):
     lib = capi.lib()
-    assert lib.rmv_abi_version() == 1
+    assert lib.rmv_abi_version() == 2
     assert [capi.kind_dims(k) for k in range(4)] == [(5, 2), (9, 2), (10, 4), (16, 4)]
     assert capi.action_bounds(capi.QUAD3D) == (0.0, 10.0)
     assert capi.action_bounds(capi.QUAD2D) == (-10.0, 10.0)
@@ -81,6 +81,30 @@ def test_undersized_buffers_are_refused_before_the_abi():
     _need(np.empty(10, np.float32), 10, "x")
     with pytest.raises(ValueError, match="actions holds 8 elements, 16 needed"):
         _need(np.empty((4, 2), np.float32), 16, "actions")
+
+
+def test_wrong_dtype_or_side_of_the_bus_is_refused_before_the_abi():
+    """A float64 / int buffer of the right element count would be reinterpreted as float32, and a host address
+    dereferenced by a kernel kills the CUDA context: the binding refuses both."""
+    import torch
+    from gym_reinmav_b200.batch import HOST, _ptr
+    f32, f64 = np.zeros((4, 2), np.float32), np.zeros((4, 2), np.float64)
+    assert _ptr(f32, "float32", HOST, "actions") == f32.ctypes.data
+    assert _ptr(None, "float32", 0) is None and _ptr(12345, "float32", 0) == 12345
+    with pytest.raises(TypeError, match="actions must be float32, got float64"):
+        _ptr(f64, "float32", HOST, "actions")
+    with pytest.raises(TypeError, match="done must be uint8"):
+        _ptr(np.zeros(4, bool), "uint8", HOST, "done")
+    with pytest.raises(ValueError, match="device buffer on cuda:0"):
+        _ptr(f32, "float32", 0, "actions")
+    t = torch.zeros((4, 2), dtype=torch.float32)
+    assert _ptr(t, "float32", HOST, "actions") == t.data_ptr()
+    with pytest.raises(ValueError, match="must be on cuda:0, got a tensor on cpu"):
+        _ptr(t, "float32", 0, "actions")
+    with pytest.raises(TypeError, match="actions must be float32, got torch.float64"):
+        _ptr(t.double(), "float32", HOST, "actions")
+    with pytest.raises(ValueError, match="contiguous"):
+        _ptr(t.t(), "float32", HOST, "actions")
 
 
 def test_auto_launch_shape_policy(capi):

@@ -313,6 +313,55 @@ def test_travelling_state_rollout_equals_in_place_rollout(rmv, env_id):
     b1.close(); b2.close()
 
 
+@pytest.mark.parametrize("travelling", [False, True])
+def test_second_collect_continues_without_an_explicit_roll(rmv, travelling):
+    """ppo2's Runner keeps self.obs between run() calls; collect() carries obs[T] into obs[0] itself (ADVICE r1:
+    in travelling mode a forgotten roll() used to restart every env from the previous rollout's first observation)."""
+    import torch
+    n, T, seed = 2048 + 33, 40, 5
+    outs = []
+    for explicit_roll in (True, False):
+        venv = rmv.QuadVecEnv("quadrotor3d-v0", n, seed=seed, monitor=True)
+        buf = rmv.RolloutBuffer(venv, T, travelling=travelling)
+        for rollout in range(3):
+            for t in range(T):
+                rmv.fill_uniform_actions(buf.actions[t], n, 4, 0.0, 10.0, seed, step_index=rollout * T + t)
+            buf.collect(lambda obs, _it=iter(range(T)): buf.action_views[next(_it)])
+            if explicit_roll:
+                buf.roll()
+                buf.roll()                                      # idempotent
+        outs.append((buf.obs.cpu().numpy(), buf.rewards.cpu().numpy(), buf.dones.cpu().numpy(),
+                     venv.batch.get_state(), venv.batch.get_episode_words(), venv.batch.episode_stats()))
+        venv.close()
+    a, b = outs
+    assert same_bits(a[0][1:], b[0][1:]) and same_bits(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert same_bits(a[3], b[3]) and np.array_equal(a[4], b[4]) and a[5] == b[5]
+    assert int(a[2].sum()) > 20
+
+
+def test_misaligned_action_rows_are_refused(rmv):
+    """A row-per-env action is one 16-byte (A = 4) / 8-byte (A = 2) vector load: a view at an odd float offset used to
+    fault with 'misaligned address' and poison the context; now RMV_EALIGN."""
+    import torch
+    n = 1000
+    b = rmv.QuadBatch("quadrotor3d-v0", n)
+    b.reset()
+    big = torch.zeros(n * 4 + 8, dtype=torch.float32, device="cuda:0")
+    rew = torch.empty(n, dtype=torch.float32, device="cuda:0")
+    done = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+    for off in (1, 2, 3):
+        with pytest.raises(rmv.RmvError) as exc:
+            b.step(big[off:off + n * 4], rew, done)
+        assert exc.value.code == -4 and "aligned" in str(exc.value)
+    b.step(big[4:4 + n * 4], rew, done)                     # 16-byte offset: fine
+    with pytest.raises(TypeError):
+        b.step(big[:n * 4].double(), rew, done)
+    with pytest.raises(ValueError):
+        b.step(big[:n * 4].cpu(), rew, done)
+    torch.cuda.synchronize()
+    b.close()
+
+
 def test_vec_env_zero_copy_mode(rmv):
     n = 2048
     venv = rmv.QuadVecEnv("quadrotor3d-v0", n, seed=1, copy_outputs=False, monitor=False)
