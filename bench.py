@@ -223,22 +223,44 @@ def run_gpu_arm(args):
 
     sampler = ClockSampler(world) if rank == 0 else None
 
-    # ---- value: K steps, device-resident inputs
+    # ---- value: device-resident inputs.  The driver asks for K = 20 steps (0.2 ms): a window that short is launch
+    # skew, not throughput, so the K-step block is repeated back to back until the timed region is >= 60 ms — one pair
+    # of events around the whole region (value), one event after every block (best block, reported beside it).
     run_steps(args.warmup)
-    times = []
-    for _ in range(args.repeats):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = batch.launches
-        e0.record()
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(); run_steps(args.steps); run_steps(args.steps); c1.record()
+    torch.cuda.synchronize()
+    est_block_ms = max_over_ranks(c0.elapsed_time(c1) / 2.0)
+    blocks = int(max(args.repeats, min(20000, -(-args.min_region_ms // max(est_block_ms, 1e-3)))))
+    barrier()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(blocks + 1)]
+    launches0 = batch.launches
+    marks[0].record()
+    for i in range(blocks):
         run_steps(args.steps)
-        e1.record()
-        barrier()
-        times.append(max_over_ranks(e0.elapsed_time(e1)))
-        launches = batch.launches - launches0
-    ms_total = min(times)            # best of --repeats runs of exactly K steps (each already the max over ranks)
-    ms_per_step = ms_total / args.steps
-    value = world * n * args.steps / (ms_total * 1e-3)
+        marks[i + 1].record()
+    barrier()
+    launches = batch.launches - launches0
+    region_ms = max_over_ranks(marks[0].elapsed_time(marks[blocks]))
+    best_block_ms = max_over_ranks(min(marks[i].elapsed_time(marks[i + 1]) for i in range(blocks)))
+    ms_per_step = region_ms / (blocks * args.steps)
+    value = world * n * args.steps * blocks / (region_ms * 1e-3)
+
+    # ---- the same steps as one launch per step (RMV_MANY_LAUNCHES: what the stream kernel replaces)
+    def run_launches(k):
+        left = k
+        while left > 0:
+            m = min(left, ring)
+            batch.step_many(m, acts, rew, done, out_ld=n, layout=0, fused=2)
+            left -= m
+    run_launches(2 * ring)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_l = max(args.steps, 200)
+    c0.record(); run_launches(k_l); c1.record()
+    barrier()
+    launch_per_step_us = max_over_ranks(c0.elapsed_time(c1)) / k_l * 1e3
 
     # ---- e2e: host buffers through rmv_step_host (H2D + kernel + D2H every step)
     from gym_reinmav_b200.vec_env import _Pinned
@@ -262,9 +284,19 @@ def run_gpu_arm(args):
     e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
     checksum = float(h_rew.array[:1024].sum())            # the step's result is read on the host
 
-    extras = {}
-    if args.extras and world == 1:
+    # ---- episode statistics through the collective the path has (logging only, never on the step path):
+    # a tracked handle per rank, all_reduce_episode_stats over NCCL, checked against an all_gather of the per-rank numbers
+    stats = measure_episode_stats(torch, dist, rmv, local, rank, world, dev)
+
+    points, extras = {}, {}
+    if world == 1:
         try:                                   # side measurements must never cost the contract line
+            points = measure_roofline_points(torch, rmv, args, local)
+        except Exception as exc:               # noqa: BLE001
+            points = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            torch.cuda.synchronize()
+    if args.extras and world == 1:
+        try:
             extras = measure_extras(torch, rmv, args, local)
         except Exception as exc:               # noqa: BLE001
             extras = {"error": "%s: %s" % (type(exc).__name__, exc)}
@@ -290,28 +322,41 @@ def run_gpu_arm(args):
             "config": {"workload": "%s N=%d envs per GPU, random-policy actions U[0,10)^4, reset-on-done in-kernel"
                                    % (ENV_ID, n),
                        "env_id": ENV_ID, "envs_per_gpu": n, "state_dim": S, "action_dim": A,
-                       "launch": "one fused step kernel per step (vec=%d, block=%s), %d-step action ring; rmv_step_many issues the launches of a "
-                                 "ring pass from C and replays them from a CUDA graph once it has seen the same call twice"
-                                 % (args.vec, args.block or "auto", ring),
+                       "launch": "rmv_step_many(RMV_MANY_STREAM): ONE launch of the persistent step-stream kernel per K-step block; every "
+                                 "step reads and writes the state in place (no state kept in registers across steps), actions from a "
+                                 "%d-step ring; roofline.launch_per_step is the same work as one launch per step" % ring,
                        "l2": "no flush: per-step traffic %.0f MB (state %.0f MB read+written in place, re-read next step; "
-                             "actions stream from a %.2f GiB ring > 126 MB L2); extras.n23 is the same kernel with a "
+                             "actions stream from a %.2f GiB ring > 126 MB L2); roofline.hbm_bound is the same kernel with a "
                              "working set that cannot be L2-resident" % (ALG_BYTES * n / 1e6, 4 * S * n / 1e6, ring * n * A * 4 / 2 ** 30),
-                       "timing": "CUDA events on the launch stream, best of %d runs of exactly K steps, max over ranks" % args.repeats},
+                       "timing": "CUDA events on the launch stream around %d back-to-back blocks of exactly K = %d steps (%.1f ms "
+                                 "region), max over ranks; best single block %.4f ms/step" % (blocks, args.steps, region_ms,
+                                                                                              best_block_ms / args.steps)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * A * 4, "d2h_bytes_per_step": n * (4 * S + 4 + 1),
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "per_rank": {"h2d_GBps": n * A * 4 / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+                                 "d2h_GBps": n * (4 * S + 4 + 1) / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+                                 "note": "both directions overlap inside rmv_step_host; rates = bytes per step / step time of the slowest rank"},
                     "path": "rmv_step_host (C-ABI, pinned host buffers): H2D actions, step kernel with obs rows, D2H obs+reward+done, stream sync"},
             "gpu_launches": launches * world,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks, "unit": "GB/s", "frac": achieved / peaks,
-                         "traffic": (load_traffic() or {}).get("dram_bytes_per_launch"),
-                         "traffic_steady_state": ((load_traffic() or {}).get("steady_state") or {}).get("dram_bytes_per_launch"),
-                         "traffic_note": "ncu --set full per launch: cold-cache capture (L2 flushed per replay) / "
-                                         "--cache-control none capture of a back-to-back run (42 MB state L2-resident)",
-                         "kernel": "rmv::k_step<QUAD3D, vec=%d, block=%s>" % (args.vec, args.block or "auto(128)"),
-                         "algorithmic_bytes_per_launch": ALG_BYTES * n, "avg_launch_us": ms_per_step * 1e3, "peak_source": peak_src,
-                         "note": "frac > 1 at N=2^20 because the 42 MB state stays L2-resident between steps "
-                                 "(traffic_steady_state << algorithmic bytes); the HBM-bound point of the same kernel is "
-                                 "extras.n23 (847 MB per step)"},
+            "roofline": dict({
+                "bound": "hbm", "achieved": achieved, "peak": peaks, "unit": "GB/s", "frac": achieved / peaks,
+                "traffic": (load_traffic("k_step_stream_quadrotor3d_n2pow20") or {}).get("dram_bytes_per_step"),
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, divided by "
+                                "the steps of the captured launch; a CITATION of profiles/traffic.json, not measured in this run",
+                "kernel": "rmv::k_step_stream<QUAD3D> (persistent; one launch = K steps of N envs)",
+                "steps_per_launch": min(args.steps, ring),
+                "algorithmic_bytes_per_step": ALG_BYTES * n,
+                "algorithmic_bytes_per_launch": ALG_BYTES * n * min(args.steps, ring),
+                "avg_launch_us": ms_per_step * 1e3 * min(args.steps, ring), "peak_source": peak_src,
+                "l2_resident": True,
+                "note": "frac > 1 at N=2^20 is NOT an HBM fraction: the 42 MB state stays in the 126 MB L2 between steps, only "
+                        "actions / rewards / done flags (22 MB per step) move through DRAM.  hbm_bound is the same kernel at "
+                        "N=2^23 (847 MB per step, cannot be L2-resident); cold_l2 is one isolated N=2^20 launch after an L2 flush",
+                "launch_per_step": {"us_per_step": launch_per_step_us, "frac": ALG_BYTES * n / (launch_per_step_us * 1e-6) / 1e9 / peaks,
+                                    "kernel": "rmv::k_step<QUAD3D> (one launch per step, PDL + CUDA-graph replay)"},
+            }, **points),
+            "episode_stats": stats,
             "cpu_baseline": cpu,
             "extras": extras,
             "result_checksum": checksum,
@@ -323,6 +368,125 @@ def run_gpu_arm(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def measure_episode_stats(torch, dist, rmv, local, rank, world, dev):
+    """The only collective of the path: episode statistics for logging.  A tracked handle per rank steps a small batch,
+    `dist.all_reduce_episode_stats` sums {episodes, return_sum, length_sum, env_steps} over the ranks (NCCL at N > 1),
+    and the sum is checked against an all_gather of the per-rank numbers."""
+    import gym_reinmav_b200.dist as rdist
+    n, T = 1 << 16, 256
+    venv = rmv.QuadVecEnv(ENV_ID, n, device=local, seed=SEED, env_id_offset=(1 << 40) + rank * n, monitor=True)
+    venv.batch.reset()
+    acts = torch.empty((T, n, ACTION_DIM), dtype=torch.float32, device=dev)
+    for t in range(T):
+        rmv.fill_uniform_actions(acts[t], n, ACTION_DIM, ACT_LO, ACT_HI, SEED, env_id_offset=rank * n, step_index=t, device=local)
+    venv.batch.step_many(T, acts, None, None, layout=0, fused=0)
+    mine = venv.episode_stats()
+    torch.cuda.synchronize()
+    rdist.all_reduce_episode_stats(venv)                       # warm-up (NCCL channel setup)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    total = rdist.all_reduce_episode_stats(venv)
+    torch.cuda.synchronize()
+    us = 1e6 * (time.perf_counter() - t0)
+    keys = ("episodes", "return_sum", "length_sum", "env_steps")
+    ok = True
+    if world > 1:
+        t = torch.tensor([mine[k] for k in keys], dtype=torch.float64, device=dev)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        summed = torch.stack(parts).sum(0).tolist()
+        ok = all(abs(total[k] - v) <= 1e-9 * max(1.0, abs(v)) for k, v in zip(keys, summed))
+    venv.close()
+    return {"episodes": total["episodes"], "mean_return": total["mean_return"], "mean_length": total["mean_length"],
+            "env_steps": total["env_steps"], "allreduce_us": us, "sum_equals_per_rank_sums": ok,
+            "backend": "nccl all_reduce (4 x float64)" if world > 1 else "single rank (no collective)",
+            "sample": "%d tracked envs per rank x %d steps through the step stream" % (n, T)}
+
+
+def _time_many(torch, batch, acts, rew, done, n, k, mode):
+    ring = acts.shape[0]
+
+    def run(kk):
+        left = kk
+        while left > 0:
+            m = min(left, ring)
+            batch.step_many(m, acts, rew, done, out_ld=n, layout=0, fused=mode)
+            left -= m
+    run(2 * ring)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(k); e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / k)
+    return best * 1e3            # us per step
+
+
+def measure_roofline_points(torch, rmv, args, local):
+    """The points that qualify the headline fraction, measured in the same run and carried INSIDE the roofline dict:
+    the HBM-bound size (N = 2^23), a cold-L2 isolated launch at N = 2^20, and BASELINE configs 1-2 (N = 65536)."""
+    dev = "cuda:0" if local == 0 else "cuda:%d" % local
+    peak, _ = load_peak()
+    out = {}
+    bounds = {ENV_ID: (0, 10), "quadrotor3d-slungload-v0": (-10, 10)}
+    bytes_of = {ENV_ID: 101, "quadrotor3d-slungload-v0": 149}
+
+    def make(env_id, n, ring):
+        b = rmv.QuadBatch(env_id, n, device=local, seed=SEED)
+        b.reset()
+        lo, hi = bounds[env_id]
+        acts = torch.empty((ring, n, 4), dtype=torch.float32, device=dev)
+        for t in range(ring):
+            rmv.fill_uniform_actions(acts[t], n, 4, lo, hi, SEED, step_index=t, device=local)
+        return b, acts, torch.empty((ring, n), dtype=torch.float32, device=dev), torch.empty((ring, n), dtype=torch.uint8, device=dev)
+
+    def entry(env_id, n, us, mode):
+        gbs = n * bytes_of[env_id] / (us * 1e-6) / 1e9
+        return {"env_id": env_id, "n_envs": n, "us_per_step": us, "env_steps_per_s": n / (us * 1e-6), "achieved": gbs,
+                "frac": gbs / peak, "mode": mode}
+
+    # HBM-bound: 847 MB per step
+    n = 1 << 23
+    b, acts, rew, done = make(ENV_ID, n, 8)
+    out["hbm_bound"] = entry(ENV_ID, n, _time_many(torch, b, acts, rew, done, n, 96, 0), "step stream, 8-step launches")
+    out["hbm_bound"]["launch_per_step_us"] = _time_many(torch, b, acts, rew, done, n, 96, 2)
+    out["hbm_bound"]["dram_bytes_per_step_ncu"] = (load_traffic("k_step_stream_quadrotor3d_n2pow23") or {}).get("dram_bytes_per_step")
+    b.close()
+    del acts, rew, done
+
+    # cold L2: 256 MiB are read between launches (> 126 MB L2, leaves it clean), each single-step launch timed alone
+    n = 1 << 20
+    b, acts, rew, done = make(ENV_ID, n, 8)
+    flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
+    for t in range(8):
+        b.step(acts[t], rew[t], done[t])
+    evs, sink = [], []
+    for t in range(40):
+        sink.append(flush.max())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); b.step(acts[t % 8], rew[t % 8], done[t % 8]); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(z) for a, z in evs)
+    out["cold_l2"] = entry(ENV_ID, n, ts[len(ts) // 2] * 1e3,
+                           "ONE isolated k_step launch after an L2 flush, its own event pair (~5 us of the figure is the pair), median of 40")
+    b.close()
+    del acts, rew, done, flush, sink
+
+    # BASELINE configs 1-2: N = 65536 (6.6 / 9.8 MB per step: latency-, not bandwidth-bound)
+    for key, env_id in (("n65536_quadrotor3d", ENV_ID), ("n65536_quadrotor3d_slungload", "quadrotor3d-slungload-v0")):
+        n = 1 << 16
+        b, acts, rew, done = make(env_id, n, 64)
+        e = entry(env_id, n, _time_many(torch, b, acts, rew, done, n, 4096, 0), "step stream, 64-step launches")
+        e["launch_per_step_us"] = _time_many(torch, b, acts, rew, done, n, 2048, 2)
+        e["rollout_in_registers_us"] = _time_many(torch, b, acts, rew, done, n, 4096, 1)
+        out[key] = e
+        b.close()
+        del acts, rew, done
+    return out
 
 
 def measure_extras(torch, rmv, args, local):
@@ -350,7 +514,7 @@ def measure_extras(torch, rmv, args, local):
         return best
 
     peak, _ = load_peak()
-    cases = [("n23", ENV_ID, 1 << 23, 8, 100, False), ("fused_rollout", ENV_ID, 1 << 20, 64, 256, True),
+    cases = [("fused_rollout", ENV_ID, 1 << 20, 64, 256, True),
              ("quadrotor3d-slungload-v0", "quadrotor3d-slungload-v0", 1 << 20, 32, 300, False),
              ("quadrotor2d-v0", "quadrotor2d-v0", 1 << 20, 32, 300, False),
              ("quadrotor2d-slungload-v0", "quadrotor2d-slungload-v0", 1 << 20, 32, 300, False)]
@@ -372,42 +536,9 @@ def measure_extras(torch, rmv, args, local):
         sps = n / (ms * 1e-3)
         out[name] = {"env_id": env_id, "n_envs": n, "us_per_step": ms * 1e3, "env_steps_per_s": sps,
                      "algorithmic_GBps": sps * bytes_of[env_id] / 1e9, "frac_of_hbm_peak": sps * bytes_of[env_id] / 1e9 / peak,
-                     "mode": "one launch per %d steps, state in registers" % ring if fused else "one launch per step"}
+                     "mode": "one launch per %d steps, state in registers" % ring if fused else "step stream (one launch per %d steps, state through memory every step)" % ring}
         b.close()
         del acts, rew, done
-
-    # The headline kernel with a COLD L2: 256 MiB are written between launches (> 126 MB L2), each launch is timed
-    # by its own pair of events.  Every state/action byte then comes from HBM; the isolated launch also pays its
-    # own ramp and launch latency (no overlap with a predecessor).
-    n = 1 << 20
-    b = rmv.QuadBatch(ENV_ID, n, device=local, seed=SEED)
-    b.set_tuning(vec=args.vec, block=args.block)
-    b.reset()
-    acts = torch.empty((8, n, ACTION_DIM), dtype=torch.float32, device=dev)
-    for t in range(8):
-        rmv.fill_uniform_actions(acts[t], n, ACTION_DIM, ACT_LO, ACT_HI, SEED, step_index=t, device=local)
-    rew = torch.empty((8, n), dtype=torch.float32, device=dev)
-    done = torch.empty((8, n), dtype=torch.uint8, device=dev)
-    flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)      # 256 MiB, READ between launches: L2 ends up clean
-    for t in range(8):
-        b.step(acts[t], rew[t], done[t])
-    evs = []
-    sink = []
-    for t in range(40):
-        sink.append(flush.max())
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); b.step(acts[t % 8], rew[t % 8], done[t % 8]); e1.record()
-        evs.append((e0, e1))
-    torch.cuda.synchronize()
-    ts = sorted(a.elapsed_time(z) for a, z in evs)
-    ms = ts[len(ts) // 2]
-    out["n20_l2_flushed"] = {"env_id": ENV_ID, "n_envs": n, "us_per_step": ms * 1e3, "env_steps_per_s": n / (ms * 1e-3),
-                             "algorithmic_GBps": n * 101 / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": n * 101 / (ms * 1e-3) / 1e9 / peak,
-                             "mode": "one launch per step, 256 MiB read between launches (L2 flushed, left clean), one event pair "
-                                     "per launch (the pair itself costs ~5 us: an N = 2^17 launch measures 8 us this way), "
-                                     "median of 40; all state/action bytes come from HBM, no overlap with a predecessor"}
-    b.close()
-    del acts, rew, done, flush, sink
 
     # opt-in L2 access-policy window on the state (rmv_set_l2_persist): the band where the state fits the carve-out but
     # state + streams of one step do not fit L2
@@ -433,24 +564,6 @@ def measure_extras(torch, rmv, args, local):
                      "frac_of_hbm_peak": n * bytes_of[env_id] / (ms * 1e-3) / 1e9 / peak,
                      "mode": "one launch per step, state pinned in L2 by an access-policy window (opt-in)"}
         b.set_l2_persist(0)
-        b.close()
-        del acts, rew, done
-
-    # BASELINE configs[1], [2]: N = 65536 (launch-latency-bound: one launch moves 6.6 / 9.8 MB)
-    for name, env_id in (("n65536_quadrotor3d", ENV_ID), ("n65536_quadrotor3d_slungload", "quadrotor3d-slungload-v0")):
-        n = 1 << 16
-        b = rmv.QuadBatch(env_id, n, device=local, seed=SEED)
-        b.reset()
-        lo, hi = bounds[env_id]
-        acts = torch.empty((64, n, 4), dtype=torch.float32, device=dev)
-        for t in range(64):
-            rmv.fill_uniform_actions(acts[t], n, 4, lo, hi, SEED, step_index=t, device=local)
-        rew = torch.empty((64, n), dtype=torch.float32, device=dev)
-        done = torch.empty((64, n), dtype=torch.uint8, device=dev)
-        ms = time_steps(b, acts, rew, done, n, 2000)
-        out[name] = {"env_id": env_id, "n_envs": n, "us_per_step": ms * 1e3, "env_steps_per_s": n / (ms * 1e-3),
-                     "algorithmic_GBps": n * bytes_of[env_id] / (ms * 1e-3) / 1e9,
-                     "frac_of_hbm_peak": n * bytes_of[env_id] / (ms * 1e-3) / 1e9 / peak, "mode": "one launch per step (launch-bound)"}
         b.close()
         del acts, rew, done
 
@@ -520,12 +633,12 @@ def load_peak():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
 
 
-def load_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed
-    ncu --set full capture (profiles/); None if no capture is recorded."""
+def load_traffic(key):
+    """An entry of profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of committed ncu --set full
+    captures); None if no capture is recorded under that key."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh)["k_step_quadrotor3d_n2pow20"]
+            return json.load(fh)[key]
     except Exception:
         return None
 
@@ -562,7 +675,8 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU")
     ap.add_argument("--vec", type=int, default=1)
     ap.add_argument("--block", type=int, default=0, help="threads per CTA of the step kernel (0 = the library's choice)")
-    ap.add_argument("--repeats", type=int, default=5)
+    ap.add_argument("--repeats", type=int, default=5, help="minimum number of K-step blocks in the timed region")
+    ap.add_argument("--min-region-ms", type=float, default=60.0, help="the K-step block is repeated until the timed region is this long")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-steps", type=int, default=2000)
     ap.add_argument("--no-cpu", action="store_true")

@@ -211,13 +211,29 @@ RMV_API int rmv_step_rows(rmv_env* env, const float* rows_in_dev, const float* a
 
 /* T consecutive steps with auto-reset from a pre-generated action block (random-policy or
  * replayed rollouts).  act_dev is [T][A][act_ld] (SOA) or [T][n][A] (AOS); reward_dev / done_dev
- * are [T][out_ld] or NULL.
- *   fused == 0: T launches of the step kernel (state streams through HBM every step — the
- *               access pattern of a policy-in-the-loop rollout);
- *   fused == 1: ONE launch, each thread keeps its envs' state in registers for all T steps
- *               (state is read and written once per call). Results are identical. */
+ * are [T][out_ld] or NULL.  `mode`:
+ *   RMV_MANY_STREAM   (0): the state makes the round trip through memory EVERY step (read from the state buffer,
+ *               written back in place: 4(2S+A+1)+1 bytes per env-step, the traffic of T calls of rmv_step), but
+ *               the T steps are ONE launch of the persistent step-stream kernel: every warp owns a fixed set of
+ *               32-env units and walks (step, unit) in order, so a step depends on nothing but its own envs'
+ *               previous step — no grid-wide barrier, no CTA barrier (csrc/rmv_stream.cuh);
+ *   RMV_MANY_ROLLOUT  (1): ONE launch, each thread keeps its envs' state in registers for all T steps
+ *               (state is read and written once per call);
+ *   RMV_MANY_LAUNCHES (2): T launches of the single-step kernel (what mode 0 was before the stream kernel; a
+ *               repeated call is replayed from a CUDA graph).
+ * Results are identical bit for bit in all three. */
+enum { RMV_MANY_STREAM = 0, RMV_MANY_ROLLOUT = 1, RMV_MANY_LAUNCHES = 2 };
 RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act_dev, int act_layout, int64_t act_ld,
-                  float* reward_dev, uint8_t* done_dev, int64_t out_ld, int fused, void* stream);
+                  float* reward_dev, uint8_t* done_dev, int64_t out_ld, int mode, void* stream);
+/* Tuning of the step-stream kernel (sweeps): pipe = prefetch the warp's next work item while the current one is
+ * computed (-1 auto, 0, 1); warps_per_sm caps the resident warps per SM (0 = as many as fit); block = threads per CTA
+ * (0 auto, 32, 64, 128 — a CTA is only a scheduling unit of this kernel).  Results are identical. */
+RMV_API int rmv_set_stream(rmv_env* env, int pipe, int warps_per_sm, int block);
+/* the shape the stream kernel takes for n_envs on a device with `sms` SMs and room for `resident_warps_per_sm` of its
+ * warps per SM (device-free query): every warp owns units_per_warp 32-env units (the last few one less), `warps`
+ * warps own work, launched as grid x block threads. */
+RMV_API int rmv_stream_shape(int64_t n_envs, int sms, int resident_warps_per_sm, int* units_per_warp, int* warps,
+                             int* grid, int* block);
 
 /* Same as rmv_step with HOST buffers (pinned memory recommended: rmv_host_alloc): copies the
  * actions host->device, runs the step kernel, copies reward/done/(obs) back and synchronises

@@ -14,6 +14,7 @@
 #include "rmv_kernels.cuh"
 #include "rmv_control.cuh"
 #include "rmv_step_tma.cuh"
+#include "rmv_stream.cuh"
 #include "rmv_reinmav.cuh"
 
 using namespace rmv;
@@ -106,6 +107,9 @@ struct rmv_env {
   int l2_ready = 0;        // window active
   cudaAccessPolicyWindow l2_window{};
   int use_tma = 0;         // 1: TMA-pipelined persistent step kernel where it applies
+  int stream_pipe = -1;    // step stream: -1 auto, 0 / 1 = prefetch the warp's next work item while the current one is computed
+  int stream_warps_per_sm = 0;   // 0 = as many as fit; else cap on resident warps per SM (sweeps)
+  int stream_block = 0;    // 0 = auto; else 32, 64 or 128 threads per CTA of the stream kernel
   // rmv_step_many(fused = 0): the K single-step launches of a repeated call are captured once in a CUDA graph and replayed
   struct StepGraph {
     int n_steps = 0, layout = 0;
@@ -124,6 +128,7 @@ struct rmv_env {
 };
 
 static int g_use_graph = (getenv("RMV_NO_GRAPH") == nullptr) ? 1 : 0;   // developer switch
+static int g_use_stream = (getenv("RMV_NO_STREAM") == nullptr) ? 1 : 0; // developer switch: rmv_step_many(mode 0) falls back to launches
 static int g_ctas_cap = getenv("RMV_CTAS_PER_SM") ? atoi(getenv("RMV_CTAS_PER_SM")) : 0;
 static int enable_l2_window(rmv_env* e);
 static void disable_l2_window(rmv_env* e);
@@ -318,6 +323,16 @@ extern "C" RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm
   RMV_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 32, "ctas_per_sm must be in [0, 32]");
   env->use_tma = use_tma ? 1 : 0;
   env->tma_ctas_per_sm = ctas_per_sm;
+  env->config_epoch++;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_set_stream(rmv_env* env, int pipe, int warps_per_sm, int block) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(pipe >= -1 && pipe <= 1, "pipe must be -1 (auto), 0 or 1");
+  RMV_REQUIRE(warps_per_sm >= 0 && warps_per_sm <= 64, "warps_per_sm must be in [0, 64] (0 = as many as fit)");
+  RMV_REQUIRE(block == 0 || block == 32 || block == 64 || block == 128, "block must be 0 (auto), 32, 64 or 128");
+  env->stream_pipe = pipe; env->stream_warps_per_sm = warps_per_sm; env->stream_block = block;
   env->config_epoch++;
   return RMV_OK;
 }
@@ -681,6 +696,91 @@ static cudaError_t launch_step_kv(rmv_env* e, const StepArgs& args, cudaStream_t
   return launch_step_kvb<KIND, V, 128, false>(args, win, st);
 }
 
+// ---- the persistent step stream (rmv_stream.cuh): one launch for n_steps steps ----------------------------
+// Shape: every warp owns the same number k of 32-env units and all warps are co-resident.
+static int g_stream_pipe_override = getenv("RMV_STREAM_PIPE") ? atoi(getenv("RMV_STREAM_PIPE")) : -1;   // developer switches
+static int g_stream_warps_override = getenv("RMV_STREAM_WARPS") ? atoi(getenv("RMV_STREAM_WARPS")) : 0;
+static int g_stream_block_override = getenv("RMV_STREAM_BLOCK") ? atoi(getenv("RMV_STREAM_BLOCK")) : 0;
+
+static void stream_shape_for(int64_t n, int sms, int resident_warps_per_sm, int cap_warps_per_sm, int forced_block,
+                             StreamShape* shape, unsigned* grid, unsigned* block) {
+  const uint32_t units = (uint32_t)((n + 31) / 32);
+  int per_sm = resident_warps_per_sm;
+  if (cap_warps_per_sm > 0 && cap_warps_per_sm < per_sm) per_sm = cap_warps_per_sm;
+  const uint32_t slots = (uint32_t)sms * (uint32_t)per_sm;
+  const uint32_t k = (units + slots - 1) / slots;
+  const uint32_t warps = (units + k - 1) / k;
+  // small batches: smaller CTAs spread the few warps evenly over the SMs (a CTA is only a scheduling unit here)
+  unsigned b = 128;
+  if (warps <= (uint32_t)sms * 24u) b = 32; else if (warps <= (uint32_t)sms * 48u) b = 64;
+  if (forced_block == 32 || forced_block == 64 || forced_block == 128) b = (unsigned)forced_block;
+  shape->units_per_warp = k; shape->warps = warps;
+  *block = b;
+  *grid = (warps * 32u + b - 1u) / b;
+}
+
+extern "C" RMV_API int rmv_stream_shape(int64_t n_envs, int sms, int resident_warps_per_sm, int* units_per_warp, int* warps,
+                                        int* grid, int* block) {
+  RMV_REQUIRE(n_envs > 0 && sms > 0 && resident_warps_per_sm > 0, "arguments must be positive");
+  StreamShape sh; unsigned g = 0, b = 0;
+  stream_shape_for(n_envs, sms, resident_warps_per_sm, 0, 0, &sh, &g, &b);
+  if (units_per_warp) *units_per_warp = (int)sh.units_per_warp;
+  if (warps) *warps = (int)sh.warps;
+  if (grid) *grid = (int)g;
+  if (block) *block = (int)b;
+  return RMV_OK;
+}
+
+template <int KIND, bool TRACK, bool PREF, bool PIPE>
+static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_t st) {
+  static int resident_of[kMaxDevices] = {}, sms_of[kMaxDevices] = {};      // per instantiation and per device
+  const int dev = current_device();
+  if (resident_of[dev] == 0) {
+    cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_stream<KIND, TRACK, PREF, PIPE>, 128, 0);
+    if (resident_of[dev] < 1) resident_of[dev] = 1;
+    if (sms_of[dev] < 1) sms_of[dev] = 1;
+  }
+  StreamShape shape; unsigned grid = 0, block = 0;
+  const int cap = e->stream_warps_per_sm > 0 ? e->stream_warps_per_sm : g_stream_warps_override;
+  const int fb = e->stream_block > 0 ? e->stream_block : g_stream_block_override;
+  stream_shape_for(args.n, sms_of[dev], resident_of[dev] * 4, cap, fb, &shape, &grid, &block);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (const cudaAccessPolicyWindow* win = l2_window_of(e, args)) {
+    attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[na].val.accessPolicyWindow = *win;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, k_step_stream<KIND, TRACK, PREF, PIPE>, args, shape);
+}
+
+template <int KIND>
+static cudaError_t launch_stream_k(rmv_env* e, const StepArgs& args, cudaStream_t st) {
+  const bool track = args.ep_return != nullptr;
+  const bool pref = e->prefetch >= 0 ? e->prefetch != 0 : default_prefetch(KIND, args.n);
+  int pipe = e->stream_pipe >= 0 ? e->stream_pipe : g_stream_pipe_override;
+  if (pipe < 0) pipe = 0;
+  if (pipe) {
+    if (track) return pref ? launch_stream_t<KIND, true, true, true>(e, args, st) : launch_stream_t<KIND, true, false, true>(e, args, st);
+    return pref ? launch_stream_t<KIND, false, true, true>(e, args, st) : launch_stream_t<KIND, false, false, true>(e, args, st);
+  }
+  if (track) return pref ? launch_stream_t<KIND, true, true, false>(e, args, st) : launch_stream_t<KIND, true, false, false>(e, args, st);
+  return pref ? launch_stream_t<KIND, false, true, false>(e, args, st) : launch_stream_t<KIND, false, false, false>(e, args, st);
+}
+
 template <int KIND>
 static cudaError_t launch_step_k(rmv_env* e, const StepArgs& args, int vec, cudaStream_t st) {
   if (e->use_tma && vec == 1 && args.n_steps == 1 && !args.act_soa && aligned(args.act, 16))
@@ -705,7 +805,7 @@ static void reinmav_inverse_inertia(double out[9]) {
 // 128-env tile; the whole handle when cn == n).  act / rew / done / obs point at env c0's element.
 static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act_ld, int64_t act_step_stride,
                        float* rew, uint8_t* done, int64_t out_ld, float* obs, int auto_reset, int n_steps,
-                       cudaStream_t st, int64_t c0 = 0, int64_t cn = -1, bool advance_clock = true) {
+                       cudaStream_t st, int64_t c0 = 0, int64_t cn = -1, bool advance_clock = true, bool stream = false) {
   if (cn < 0) cn = e->n;
   if (e->kind == RMV_REINMAV) {
     // no action; n_steps consecutive steps, each np.arange(t, t + dt, 1/5000) substeps (reinmav_env.py:90-98)
@@ -770,11 +870,20 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
   a.n_steps = n_steps; a.act_soa = (act_layout == RMV_ACT_SOA); a.auto_reset = auto_reset ? 1 : 0;
   a.P = e->dp;
   cudaError_t err;
-  switch (e->kind) {
-    case RMV_QUAD2D: err = launch_step_k<QUAD2D>(e, a, vec, st); break;
-    case RMV_QUAD2D_SLUNG: err = launch_step_k<QUAD2D_SLUNG>(e, a, vec, st); break;
-    case RMV_QUAD3D: err = launch_step_k<QUAD3D>(e, a, vec, st); break;
-    default: err = launch_step_k<QUAD3D_SLUNG>(e, a, vec, st); break;
+  if (stream) {
+    switch (e->kind) {
+      case RMV_QUAD2D: err = launch_stream_k<QUAD2D>(e, a, st); break;
+      case RMV_QUAD2D_SLUNG: err = launch_stream_k<QUAD2D_SLUNG>(e, a, st); break;
+      case RMV_QUAD3D: err = launch_stream_k<QUAD3D>(e, a, st); break;
+      default: err = launch_stream_k<QUAD3D_SLUNG>(e, a, st); break;
+    }
+  } else {
+    switch (e->kind) {
+      case RMV_QUAD2D: err = launch_step_k<QUAD2D>(e, a, vec, st); break;
+      case RMV_QUAD2D_SLUNG: err = launch_step_k<QUAD2D_SLUNG>(e, a, vec, st); break;
+      case RMV_QUAD3D: err = launch_step_k<QUAD3D>(e, a, vec, st); break;
+      default: err = launch_step_k<QUAD3D_SLUNG>(e, a, vec, st); break;
+    }
   }
   if (err != cudaSuccess) return fail(RMV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(err));
   if (advance_clock) e->step_index += (uint32_t)n_steps;
@@ -835,7 +944,11 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
   if (env->kind == RMV_REINMAV)
     return launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, reward_dev, done_dev, out_ld, nullptr, 0, n_steps, st);
   const int64_t stride = (act_layout == RMV_ACT_SOA) ? (int64_t)env->A * act_ld : env->n * env->A;
-  if (fused) return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st);
+  RMV_REQUIRE(fused >= 0 && fused <= 2, "mode must be RMV_MANY_STREAM (0), RMV_MANY_ROLLOUT (1) or RMV_MANY_LAUNCHES (2)");
+  if (fused == RMV_MANY_ROLLOUT)
+    return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st);
+  if (fused == RMV_MANY_STREAM && g_use_stream && n_steps >= 2)
+    return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st, 0, -1, true, true);
   if (!reward_dev || !done_dev) {                 // the single-step kernel always writes both: park them in scratch
     int rc = ensure_staging(env);
     if (rc) return rc;

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("RMV_LIB", os.path.join(_HERE, "lib", "librmv.so"))
 
 QUAD2D, QUAD2D_SLUNG, QUAD3D, QUAD3D_SLUNG, REINMAV = 0, 1, 2, 3, 4
 ACT_AOS, ACT_SOA = 0, 1
+MANY_STREAM, MANY_ROLLOUT, MANY_LAUNCHES = 0, 1, 2
 TRACK_EPISODES = 1
 EVER_DONE_BIT = 0x80000000
 ABI_VERSION = 2
@@ -69,6 +70,8 @@ SIGNATURES = {
     "rmv_step": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp]),
     "rmv_step_rows": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp]),
     "rmv_step_many": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp, _i64, _i, _vp]),
+    "rmv_set_stream": (_i, [_vp, _i, _i, _i]),
+    "rmv_stream_shape": (_i, [_i64, _i, _i, _pi, _pi, _pi, _pi]),
     "rmv_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rmv_reset_host": (_i, [_vp, _vp, _vp]),
     "rmv_control": (_i, [_vp, _pf, _pf, _vp, _i, _i64, _vp]),

@@ -167,6 +167,10 @@ class QuadBatch:
         """L2 access-policy window on the state (state stays L2-resident between steps): -1 auto, 0 off, 1 on."""
         check(lib().rmv_set_l2_persist(self._h, int(mode)))
 
+    def set_stream(self, pipe=-1, warps_per_sm=0, block=0):
+        """Tuning of the step-stream kernel behind ``step_many(fused=0)``; results are identical."""
+        check(lib().rmv_set_stream(self._h, int(pipe), int(warps_per_sm), int(block)))
+
     def set_host_chunks(self, chunks=0):
         check(lib().rmv_set_host_chunks(self._h, int(chunks)))
 
@@ -211,7 +215,8 @@ class QuadBatch:
     def step_many(self, n_steps, actions, reward=None, done=None, out_ld=0, layout=ACT_SOA, act_ld=0, fused=False,
                   stream=None):
         """``actions`` is [T, A, act_ld] (``ACT_SOA``, the default; ``act_ld`` 0 -> the handle's padded env count
-        ``self.ld``) or [T, N, A] (``ACT_AOS``)."""
+        ``self.ld``) or [T, N, A] (``ACT_AOS``).  ``fused``: False / 0 = the persistent step stream (state through
+        memory every step, one launch), True / 1 = state in registers for the whole call, 2 = one launch per step."""
         if layout == ACT_SOA and not act_ld:
             act_ld = self.ld
         if self.action_dim:
@@ -220,7 +225,7 @@ class QuadBatch:
         check(lib().rmv_step_many(self._h, int(n_steps), _ptr(actions, "float32", d, "actions"), layout, int(act_ld),
                                   _ptr(reward, "float32", d, "reward"), _ptr(done, "uint8", d, "done"),
                                   int(out_ld or self.num_envs), int(fused), _stream(stream, d)))
-        self.launches += 1 if fused else int(n_steps)
+        self.launches += int(n_steps) if int(fused) == _capi.MANY_LAUNCHES else 1
 
     # ---------------------------------------------------------------- hot path (host buffers)
     def step_host(self, actions, reward, done, obs=None, auto_reset=True, stream=None):

@@ -180,7 +180,7 @@ def test_every_cta_size_and_prefetch_mode_bitwise(torch, rmv, env_id, block, pre
 @pytest.mark.parametrize("vec", [1, 2])
 @pytest.mark.parametrize("env_id", ENV_IDS)
 def test_fused_rollout_equals_single_steps(torch, rmv, env_id, vec):
-    """rmv_step_many(fused=1) — T steps in one launch, state in registers, reset inside the loop — against T
+    """rmv_step_many(mode = RMV_MANY_ROLLOUT) — T steps in one launch, state in registers, reset inside the loop — against T
     single-step launches: same state, rewards, done flags, episode words and episode statistics, bit for bit.
     Wide initial states make a third of the envs finish at once, the batch is ragged, tracking is on."""
     kind = KIND_OF_ID[env_id]
@@ -194,7 +194,7 @@ def test_fused_rollout_equals_single_steps(torch, rmv, env_id, vec):
     for t in range(T):
         rmv.fill_uniform_actions(acts[t], n, A, lo, hi, seed, step_index=t)
     out = []
-    for fused in (False, True):
+    for fused in (2, 1):                          # RMV_MANY_LAUNCHES, RMV_MANY_ROLLOUT
         b = rmv.QuadBatch(env_id, n, seed=seed, track_episodes=True)
         b.set_tuning(vec=vec)
         b.reset()
@@ -209,6 +209,86 @@ def test_fused_rollout_equals_single_steps(torch, rmv, env_id, vec):
     assert np.array_equal(d0, d1) and same_bits(r0, r1) and same_bits(s0, s1) and np.array_equal(w0, w1)
     assert st0["episodes"] == st1["episodes"] > 0 and st0["length_sum"] == st1["length_sum"]
     assert abs(st0["return_sum"] - st1["return_sum"]) <= 1e-9 * max(1.0, abs(st0["return_sum"]))   # atomic double sums
+
+
+STREAM_CASES = [
+    # n, warps_per_sm cap, block, track, layout      (148 SMs: cap 1 -> 148 warps own everything)
+    (128 * 41 + 18, 0, 0, True, "aos"),              # one unit per warp, ragged last unit, small-batch CTA size
+    (20000 + 5, 1, 32, False, "soa"),                # 5 units per warp (the last few warps own 4), 1-warp CTAs
+    (20000 + 5, 2, 128, True, "aos"),                # 3 units per warp
+    (17, 0, 0, False, "aos"),                        # less than one unit
+    ((1 << 19) + 77, 0, 0, False, "aos"),            # more units than resident warps: k = 2 at full occupancy
+]
+
+
+@pytest.mark.parametrize("pipe", [0, 1])
+@pytest.mark.parametrize("case", range(len(STREAM_CASES)))
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_step_stream_bitwise(torch, rmv, env_id, case, pipe):
+    """rmv_step_many(mode = RMV_MANY_STREAM): the persistent step stream (one launch, every warp walks its own units
+    through all T steps, finished envs re-drawn inside the warp) against T launches of the single-step kernel — state,
+    rewards, done flags, episode words and episode statistics bit for bit; two consecutive calls (the second starts
+    from the first one's state), wide initial states (a third of the envs finish at once), with and without the
+    next-item prefetch, every ownership shape."""
+    n, cap, block, track, layout = STREAM_CASES[case]
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    lo, hi = ACTION_BOUNDS[kind]
+    T, seed = (12 if n > 100000 else 40), 8
+    start = np.random.RandomState(3).uniform(-3, 3, (n, S)).astype(np.float32)
+    dev = "cuda:0"
+    ld = ((n + 127) // 128) * 128
+    if layout == "aos":
+        acts = torch.empty((T, n, A), dtype=torch.float32, device=dev)
+        for t in range(T):
+            rmv.fill_uniform_actions(acts[t], n, A, lo, hi, seed, step_index=t)
+        kw = dict(layout=0)
+    else:
+        acts = torch.zeros((T, A, ld), dtype=torch.float32, device=dev)
+        for t in range(T):
+            rmv.fill_uniform_actions(acts[t], n, A, lo, hi, seed, step_index=t, layout=1, act_ld=ld)
+        kw = dict(layout=1, act_ld=ld)
+    out = []
+    for mode in (2, 0):                           # RMV_MANY_LAUNCHES, RMV_MANY_STREAM
+        b = rmv.QuadBatch(env_id, n, seed=seed, track_episodes=track)
+        b.set_stream(pipe=pipe, warps_per_sm=cap, block=block)
+        b.reset()
+        b.set_state(start)
+        rew = torch.empty((2, T, n), dtype=torch.float32, device=dev)
+        done = torch.empty((2, T, n), dtype=torch.uint8, device=dev)
+        for call in range(2):
+            b.step_many(T, acts, rew[call], done[call], out_ld=n, fused=mode, **kw)
+        torch.cuda.synchronize()
+        out.append((b.get_state(), rew.cpu().numpy(), done.cpu().numpy(), b.get_episode_words(),
+                    b.episode_stats() if track else None))
+        b.close()
+    (s0, r0, d0, w0, st0), (s1, r1, d1, w1, st1) = out
+    assert d0[0, 0].mean() > 0.1                  # the mass-finish case really happened
+    assert np.array_equal(d0, d1) and same_bits(r0, r1) and same_bits(s0, s1) and np.array_equal(w0, w1)
+    if track:
+        assert st0["episodes"] == st1["episodes"] > 0 and st0["length_sum"] == st1["length_sum"]
+        assert abs(st0["return_sum"] - st1["return_sum"]) <= 1e-9 * max(1.0, abs(st0["return_sum"]))   # atomic double sums
+
+
+def test_step_stream_without_outputs_and_vs_model(torch, rmv):
+    """reward_dev / done_dev may be NULL (only the state matters), and the stream equals the float32 model directly."""
+    env_id, n, T, seed = "quadrotor3d-slungload-v0", 9000, 30, 2
+    kind = KIND_OF_ID[env_id]
+    lo, hi = ACTION_BOUNDS[kind]
+    acts = torch.empty((T, n, 4), dtype=torch.float32, device="cuda:0")
+    for t in range(T):
+        rmv.fill_uniform_actions(acts[t], n, 4, lo, hi, seed, step_index=t)
+    b = rmv.QuadBatch(env_id, n, seed=seed)
+    o = BatchOracle(kind, n, seed=seed, dtype=np.float32)
+    b.reset(); o.reset()
+    b.step_many(T, acts, None, None, layout=0, fused=0)
+    a = acts.cpu().numpy()
+    for t in range(T):
+        o.step(a[t])
+    assert same_bits(b.get_state(), o.obs())
+    words = b.get_episode_words()
+    assert np.array_equal(words & 0x7FFFFFFF, o.episode) and np.array_equal((words >> 31).astype(bool), o.ever_done)
+    b.close()
 
 
 def test_step_is_cuda_graph_capturable(torch, rmv):
@@ -255,7 +335,7 @@ def test_step_is_cuda_graph_capturable(torch, rmv):
 
 
 def test_step_many_graph_replay_bitwise(torch, rmv):
-    """rmv_step_many(fused=0) captures a call shape in a CUDA graph the second time it sees it (consecutively or not) and
+    """rmv_step_many(mode = RMV_MANY_LAUNCHES) captures a call shape in a CUDA graph the second time it sees it (consecutively or not) and
     replays it from then on: plain launch, capture + launch, replays, a second call shape (LRU), and a re-seed in between (the cached
     graphs carry the old Philox key and must not be used) — all against single rmv_step launches, bit for bit."""
     env_id, n, seed, K = "quadrotor3d-v0", 128 * 60 + 11, 13, 16
@@ -273,7 +353,7 @@ def test_step_many_graph_replay_bitwise(torch, rmv):
     for m, reseed in plan:
         if reseed is not None:
             a.set_seed(reseed); b.set_seed(reseed)
-        a.step_many(m, acts, rew_a, done_a, out_ld=n, layout=0, fused=False)
+        a.step_many(m, acts, rew_a, done_a, out_ld=n, layout=0, fused=2)        # RMV_MANY_LAUNCHES
         for t in range(m):
             b.step(acts[t], rew_b[t], done_b[t])
         torch.cuda.synchronize()

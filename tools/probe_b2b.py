@@ -33,7 +33,7 @@ for env_id in args.envs.split(","):
         left = k
         while left > 0:
             m = min(left, ring)
-            b.step_many(m, acts, rew, done, out_ld=n, layout=0, fused=False)
+            b.step_many(m, acts, rew, done, out_ld=n, layout=0, fused=2)
             left -= m
     run(ring)
     torch.cuda.synchronize()

@@ -22,7 +22,7 @@ for env_id in ("quadrotor3d-v0", "quadrotor2d-v0"):
         done = torch.empty((K, n), dtype=torch.uint8, device=dev)
 
         def run():
-            b.step_many(K, acts, rew, done, out_ld=n, layout=0, fused=False)
+            b.step_many(K, acts, rew, done, out_ld=n, layout=0, fused=2)
         run(); torch.cuda.synchronize()
 
         def timeit(fn, reps=20):
