@@ -74,8 +74,14 @@ enum {
 
 /* rmv_create flags */
 enum {
-  RMV_TRACK_EPISODES = 1u  /* keep per-env episode return/length (baselines Monitor's info['episode']);
+  RMV_TRACK_EPISODES = 1u, /* keep per-env episode return/length (baselines Monitor's info['episode']);
                               costs 8 extra bytes per env-step */
+  RMV_STATE_ROWS = 2u      /* the handle keeps its state as float32 [n_pad][S] ROWS instead of tiles: the state buffer
+                              IS the observation matrix a policy reads (obs == state in the reference,
+                              quadrotor3d.py:104), rmv_step updates it in place through the row-state kernel and needs no
+                              observation copy — 4(2S+A+1)+1 bytes per env-step where tiles + obs rows move
+                              4(3S+A+1)+1.  rmv_state_ptr / rmv_step's obs_aos_dev == NULL then mean "read the rows
+                              at rmv_state_ptr".  Same results bit for bit.  Not for RMV_REINMAV. */
 };
 
 /* Model constants.  The reference hard-codes them in each __init__ (quadrotor3d.py:45-56,
@@ -157,7 +163,7 @@ RMV_API int rmv_set_l2_persist(rmv_env* env, int mode);
 RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks);
 
 /* ---- state access (parity tests, checkpoint/resume, zero-copy views) --------------------- */
-/* device pointers of the handle-owned buffers: state float32 [n_pad/128][S][128]; episode uint32 [n_pad]
+/* device pointers of the handle-owned buffers: state float32 [n_pad/128][S][128] (RMV_STATE_ROWS: [n_pad][S]); episode uint32 [n_pad]
  * (bit 31 = this env has returned done at least once — the reference's
  * `steps_beyond_done is not None`, quadrotor3d.py:68,114-122; bits 0..30 = number of resets,
  * the Philox episode index). */
@@ -188,7 +194,9 @@ RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* obs_aos_dev,
  *                rmv_step_rows, rmv_step_many and rmv_step_host
  *   reward_dev   float32 [n]
  *   done_dev     uint8   [n]  (0 / 1)
- *   obs_aos_dev  NULL, or float32 [n][S]: observation rows after the step (obs == state in the
+ *   obs_aos_dev  NULL, or float32 [n][S]: observation rows after the step (on an RMV_STATE_ROWS handle the state
+ *                buffer already is that matrix — pass NULL, or the pointer rmv_state_ptr returns; any other
+ *                pointer receives a device copy) (obs == state in the
  *                reference; with auto_reset a done env reports its RESET state, the VecEnv
  *                convention).  NULL saves 4*S bytes per env: the state buffer itself is the
  *                observation in tiled component-major form.
@@ -225,13 +233,12 @@ RMV_API int rmv_step_rows(rmv_env* env, const float* rows_in_dev, const float* a
 enum { RMV_MANY_STREAM = 0, RMV_MANY_ROLLOUT = 1, RMV_MANY_LAUNCHES = 2 };
 RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act_dev, int act_layout, int64_t act_ld,
                   float* reward_dev, uint8_t* done_dev, int64_t out_ld, int mode, void* stream);
-/* Tuning of the step-stream kernel (sweeps): pipe = prefetch the warp's next work item while the current one is
- * computed (-1 auto, 0, 1); warps_per_sm caps the resident warps per SM (0 = as many as fit); block = threads per CTA
- * (0 auto, 32, 64, 128 — a CTA is only a scheduling unit of this kernel).  Results are identical. */
-RMV_API int rmv_set_stream(rmv_env* env, int pipe, int warps_per_sm, int block);
+/* Tuning of the step-stream kernel (sweeps): warps_per_sm caps the resident warps per SM (0 = as many as fit);
+ * block = threads per CTA (0 auto, 32, 64, 128 — a CTA is only a scheduling unit of this kernel).  Results are identical. */
+RMV_API int rmv_set_stream(rmv_env* env, int warps_per_sm, int block);
 /* the shape the stream kernel takes for n_envs on a device with `sms` SMs and room for `resident_warps_per_sm` of its
  * warps per SM (device-free query): every warp owns units_per_warp 32-env units (the last few one less), `warps`
- * warps own work, launched as grid x block threads. */
+ * warps (a multiple of 4) own work, launched as grid x block threads. */
 RMV_API int rmv_stream_shape(int64_t n_envs, int sms, int resident_warps_per_sm, int* units_per_warp, int* warps,
                              int* grid, int* block);
 

@@ -71,6 +71,7 @@ struct rmv_env {
   int64_t n = 0, ld = 0, env_id_offset = 0;
   uint64_t seed = 0;
   uint32_t flags = 0, step_index = 0;
+  bool rows = false;       // RMV_STATE_ROWS: state is [n_pad][S] rows, stepped in place by the row-state kernel
   double sim_time = 0.0;   // reinmav-v0: self.t (reinmav_env.py:73,119)
   rmv_params params{};
   DevParams dp{};
@@ -107,7 +108,6 @@ struct rmv_env {
   int l2_ready = 0;        // window active
   cudaAccessPolicyWindow l2_window{};
   int use_tma = 0;         // 1: TMA-pipelined persistent step kernel where it applies
-  int stream_pipe = -1;    // step stream: -1 auto, 0 / 1 = prefetch the warp's next work item while the current one is computed
   int stream_warps_per_sm = 0;   // 0 = as many as fit; else cap on resident warps per SM (sweeps)
   int stream_block = 0;    // 0 = auto; else 32, 64 or 128 threads per CTA of the stream kernel
   // rmv_step_many(fused = 0): the K single-step launches of a repeated call are captured once in a CUDA graph and replayed
@@ -226,6 +226,7 @@ extern "C" RMV_API int rmv_create(rmv_env** out, int kind, int64_t n_envs, int64
   RMV_REQUIRE(n_envs > 0, "n_envs must be positive (got %lld)", (long long)n_envs);
   RMV_REQUIRE(env_id_offset >= 0, "env_id_offset must be >= 0");
   RMV_REQUIRE(n_envs <= (int64_t)1 << 30, "n_envs must be <= 2^30 per handle (32-bit env indices inside a launch)");
+  RMV_REQUIRE(!((flags & RMV_STATE_ROWS) && kind == RMV_REINMAV), "RMV_STATE_ROWS is not available for reinmav-v0");
   int count = 0;
   cudaError_t ce = cudaGetDeviceCount(&count);
   if (ce != cudaSuccess || count <= 0)
@@ -237,6 +238,7 @@ extern "C" RMV_API int rmv_create(rmv_env** out, int kind, int64_t n_envs, int64
   e->kind = kind; e->device = device; e->S = kS[kind]; e->A = kA[kind];
   e->n = n_envs; e->ld = rmv_padded_ld(n_envs); e->env_id_offset = env_id_offset;
   e->seed = seed; e->flags = flags;
+  e->rows = (flags & RMV_STATE_ROWS) != 0;
   if (params) e->params = *params; else rmv_default_params(kind, &e->params);
   e->dp = to_dev(e->params);
   cudaError_t err = alloc_zero(&e->state, (size_t)e->S * e->ld);
@@ -327,12 +329,11 @@ extern "C" RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm
   return RMV_OK;
 }
 
-extern "C" RMV_API int rmv_set_stream(rmv_env* env, int pipe, int warps_per_sm, int block) {
+extern "C" RMV_API int rmv_set_stream(rmv_env* env, int warps_per_sm, int block) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
-  RMV_REQUIRE(pipe >= -1 && pipe <= 1, "pipe must be -1 (auto), 0 or 1");
   RMV_REQUIRE(warps_per_sm >= 0 && warps_per_sm <= 64, "warps_per_sm must be in [0, 64] (0 = as many as fit)");
   RMV_REQUIRE(block == 0 || block == 32 || block == 64 || block == 128, "block must be 0 (auto), 32, 64 or 128");
-  env->stream_pipe = pipe; env->stream_warps_per_sm = warps_per_sm; env->stream_block = block;
+  env->stream_warps_per_sm = warps_per_sm; env->stream_block = block;
   env->config_epoch++;
   return RMV_OK;
 }
@@ -388,14 +389,24 @@ extern "C" RMV_API int rmv_set_state(rmv_env* env, const float* aos, int is_devi
   RMV_ON_DEVICE(env->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float* src = aos;
+  if (!is_device && env->rows) {
+    RMV_CUDA(cudaMemcpyAsync(env->state, aos, (size_t)env->n * env->S * sizeof(float), cudaMemcpyHostToDevice, st));
+    RMV_CUDA(cudaStreamSynchronize(st));
+    return RMV_OK;
+  }
   if (!is_device) {
     int rc = ensure_staging(env);
     if (rc) return rc;
     RMV_CUDA(cudaMemcpyAsync(env->h_obs, aos, (size_t)env->n * env->S * sizeof(float), cudaMemcpyHostToDevice, st));
     src = env->h_obs;
   }
-  k_rows_to_tiles<<<blocks_for(env->n, 256), 256, 0, st>>>(src, env->state, env->n, env->S);
-  RMV_CUDA(cudaGetLastError());
+  if (env->rows) {
+    if (src != env->state)
+      RMV_CUDA(cudaMemcpyAsync(env->state, src, (size_t)env->n * env->S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    k_rows_to_tiles<<<blocks_for(env->n, 256), 256, 0, st>>>(src, env->state, env->n, env->S);
+    RMV_CUDA(cudaGetLastError());
+  }
   if (!is_device) RMV_CUDA(cudaStreamSynchronize(st));
   return RMV_OK;
 }
@@ -405,10 +416,17 @@ extern "C" RMV_API int rmv_get_state(rmv_env* env, float* aos, int is_device, vo
   RMV_ON_DEVICE(env->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* dst = aos;
-  if (!is_device) {
+  if (!is_device && !env->rows) {
     int rc = ensure_staging(env);
     if (rc) return rc;
     dst = env->h_obs;
+  }
+  if (env->rows) {
+    if (aos != env->state)
+      RMV_CUDA(cudaMemcpyAsync(aos, env->state, (size_t)env->n * env->S * sizeof(float),
+                               is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!is_device) RMV_CUDA(cudaStreamSynchronize(st));
+    return RMV_OK;
   }
   k_tiles_to_rows<<<blocks_for(env->n, 256), 256, 0, st>>>(env->state, dst, env->n, env->S);
   RMV_CUDA(cudaGetLastError());
@@ -444,9 +462,12 @@ extern "C" RMV_API int rmv_get_episode(rmv_env* env, uint32_t* episode, int is_d
 // ------------------------------------------------------------------------------------------
 template <int KIND>
 static void launch_reset(rmv_env* e, const uint8_t* mask, float* obs, cudaStream_t st) {
-  k_reset<KIND><<<blocks_for(e->n, 256), 256, 0, st>>>(e->state, e->episode, e->n, mask, e->seed,
-                                                      e->env_id_offset, obs, e->ep_return, e->ep_start,
-                                                      e->step_index);
+  if (e->rows)
+    k_reset<KIND, true><<<blocks_for(e->n, 256), 256, 0, st>>>(e->state, e->episode, e->n, mask, e->seed, e->env_id_offset, obs,
+                                                              e->ep_return, e->ep_start, e->step_index);
+  else
+    k_reset<KIND, false><<<blocks_for(e->n, 256), 256, 0, st>>>(e->state, e->episode, e->n, mask, e->seed, e->env_id_offset, obs,
+                                                               e->ep_return, e->ep_start, e->step_index);
 }
 
 extern "C" RMV_API int rmv_reset(rmv_env* env, const uint8_t* mask_dev, float* obs_aos_dev, void* stream) {
@@ -698,7 +719,6 @@ static cudaError_t launch_step_kv(rmv_env* e, const StepArgs& args, cudaStream_t
 
 // ---- the persistent step stream (rmv_stream.cuh): one launch for n_steps steps ----------------------------
 // Shape: every warp owns the same number k of 32-env units and all warps are co-resident.
-static int g_stream_pipe_override = getenv("RMV_STREAM_PIPE") ? atoi(getenv("RMV_STREAM_PIPE")) : -1;   // developer switches
 static int g_stream_warps_override = getenv("RMV_STREAM_WARPS") ? atoi(getenv("RMV_STREAM_WARPS")) : 0;
 static int g_stream_block_override = getenv("RMV_STREAM_BLOCK") ? atoi(getenv("RMV_STREAM_BLOCK")) : 0;
 
@@ -709,7 +729,7 @@ static void stream_shape_for(int64_t n, int sms, int resident_warps_per_sm, int 
   if (cap_warps_per_sm > 0 && cap_warps_per_sm < per_sm) per_sm = cap_warps_per_sm;
   const uint32_t slots = (uint32_t)sms * (uint32_t)per_sm;
   const uint32_t k = (units + slots - 1) / slots;
-  const uint32_t warps = (units + k - 1) / k;
+  const uint32_t warps = ((units + k - 1) / k + 3u) & ~3u;      // whole tiles of 4 units: constant pointer strides per warp
   // small batches: smaller CTAs spread the few warps evenly over the SMs (a CTA is only a scheduling unit here)
   unsigned b = 128;
   if (warps <= (uint32_t)sms * 24u) b = 32; else if (warps <= (uint32_t)sms * 48u) b = 64;
@@ -731,13 +751,13 @@ extern "C" RMV_API int rmv_stream_shape(int64_t n_envs, int sms, int resident_wa
   return RMV_OK;
 }
 
-template <int KIND, bool TRACK, bool PREF, bool PIPE>
+template <int KIND, bool TRACK, bool PREF>
 static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_t st) {
   static int resident_of[kMaxDevices] = {}, sms_of[kMaxDevices] = {};      // per instantiation and per device
   const int dev = current_device();
   if (resident_of[dev] == 0) {
     cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_stream<KIND, TRACK, PREF, PIPE>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_stream<KIND, TRACK, PREF>, 128, 0);
     if (resident_of[dev] < 1) resident_of[dev] = 1;
     if (sms_of[dev] < 1) sms_of[dev] = 1;
   }
@@ -764,26 +784,20 @@ static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, k_step_stream<KIND, TRACK, PREF, PIPE>, args, shape);
+  return cudaLaunchKernelEx(&cfg, k_step_stream<KIND, TRACK, PREF>, args, shape);
 }
 
 template <int KIND>
 static cudaError_t launch_stream_k(rmv_env* e, const StepArgs& args, cudaStream_t st) {
   const bool track = args.ep_return != nullptr;
   const bool pref = e->prefetch >= 0 ? e->prefetch != 0 : default_prefetch(KIND, args.n);
-  int pipe = e->stream_pipe >= 0 ? e->stream_pipe : g_stream_pipe_override;
-  if (pipe < 0) pipe = 0;
-  if (pipe) {
-    if (track) return pref ? launch_stream_t<KIND, true, true, true>(e, args, st) : launch_stream_t<KIND, true, false, true>(e, args, st);
-    return pref ? launch_stream_t<KIND, false, true, true>(e, args, st) : launch_stream_t<KIND, false, false, true>(e, args, st);
-  }
-  if (track) return pref ? launch_stream_t<KIND, true, true, false>(e, args, st) : launch_stream_t<KIND, true, false, false>(e, args, st);
-  return pref ? launch_stream_t<KIND, false, true, false>(e, args, st) : launch_stream_t<KIND, false, false, false>(e, args, st);
+  if (track) return pref ? launch_stream_t<KIND, true, true>(e, args, st) : launch_stream_t<KIND, true, false>(e, args, st);
+  return pref ? launch_stream_t<KIND, false, true>(e, args, st) : launch_stream_t<KIND, false, false>(e, args, st);
 }
 
 template <int KIND>
 static cudaError_t launch_step_k(rmv_env* e, const StepArgs& args, int vec, cudaStream_t st) {
-  if (e->use_tma && vec == 1 && args.n_steps == 1 && !args.act_soa && aligned(args.act, 16))
+  if (e->use_tma && vec == 1 && args.n_steps == 1 && !args.act_soa && aligned(args.act, 16) && !e->rows)
     return launch_step_tma_k<KIND>(e, args, st);
   switch (vec) {
     case 4: return launch_step_kv<KIND, 4>(e, args, st);
@@ -870,7 +884,21 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
   a.n_steps = n_steps; a.act_soa = (act_layout == RMV_ACT_SOA); a.auto_reset = auto_reset ? 1 : 0;
   a.P = e->dp;
   cudaError_t err;
-  if (stream) {
+  if (e->rows) {
+    // RMV_STATE_ROWS: the state buffer is the [n][S] observation matrix; the row-state kernel updates it in place
+    if (n_steps != 1 || stream) return fail(RMV_EINVAL, "internal: multi-step launch on a row-state handle");
+    RMV_REQUIRE(rew != nullptr && done != nullptr, "reward_dev and done_dev must not be NULL");
+    float* const rows = e->state + c0 * e->S;
+    a.rows_in = rows; a.obs = rows;
+    switch (e->kind) {
+      case RMV_QUAD2D: err = launch_step_rows_k<QUAD2D>(e, a, st); break;
+      case RMV_QUAD2D_SLUNG: err = launch_step_rows_k<QUAD2D_SLUNG>(e, a, st); break;
+      case RMV_QUAD3D: err = launch_step_rows_k<QUAD3D>(e, a, st); break;
+      default: err = launch_step_rows_k<QUAD3D_SLUNG>(e, a, st); break;
+    }
+    if (err == cudaSuccess && obs != nullptr && obs != rows)
+      err = cudaMemcpyAsync(obs, rows, (size_t)cn * e->S * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  } else if (stream) {
     switch (e->kind) {
       case RMV_QUAD2D: err = launch_stream_k<QUAD2D>(e, a, st); break;
       case RMV_QUAD2D_SLUNG: err = launch_stream_k<QUAD2D_SLUNG>(e, a, st); break;
@@ -945,6 +973,7 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
     return launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, reward_dev, done_dev, out_ld, nullptr, 0, n_steps, st);
   const int64_t stride = (act_layout == RMV_ACT_SOA) ? (int64_t)env->A * act_ld : env->n * env->A;
   RMV_REQUIRE(fused >= 0 && fused <= 2, "mode must be RMV_MANY_STREAM (0), RMV_MANY_ROLLOUT (1) or RMV_MANY_LAUNCHES (2)");
+  if (env->rows) fused = RMV_MANY_LAUNCHES;       // row-state handles: one launch of the row-state kernel per step
   if (fused == RMV_MANY_ROLLOUT)
     return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st);
   if (fused == RMV_MANY_STREAM && g_use_stream && n_steps >= 2)
@@ -1052,14 +1081,16 @@ extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float*
   if (env->A == 0) chunks = 1;
   int64_t per = ((n + chunks - 1) / chunks + 1023) / 1024 * 1024;      // whole tiles, aligned for every vector width
   if (per >= n) chunks = 1;
+  // observation rows leave from the staging copy the kernel writes, or — on a row-state handle — from the state itself
+  float* const obs_dev = env->rows ? nullptr : (obs_host ? env->h_obs : nullptr);
+  const float* const obs_src = env->rows ? env->state : env->h_obs;
   if (chunks == 1) {
     if (A > 0) RMV_CUDA(cudaMemcpyAsync(env->h_act, act_host, (size_t)n * A * sizeof(float), cudaMemcpyHostToDevice, st));
-    rc = launch_step(env, env->h_act, RMV_ACT_AOS, 0, 0, env->h_rew, env->h_done, n, obs_host ? env->h_obs : nullptr,
-                     auto_reset, 1, st);
+    rc = launch_step(env, env->h_act, RMV_ACT_AOS, 0, 0, env->h_rew, env->h_done, n, obs_dev, auto_reset, 1, st);
     if (rc) return rc;
     if (reward_host) RMV_CUDA(cudaMemcpyAsync(reward_host, env->h_rew, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (done_host) RMV_CUDA(cudaMemcpyAsync(done_host, env->h_done, (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host, env->h_obs, (size_t)n * S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host, obs_src, (size_t)n * S * sizeof(float), cudaMemcpyDeviceToHost, st));
     RMV_CUDA(cudaStreamSynchronize(st));
     return RMV_OK;
   }
@@ -1073,9 +1104,9 @@ extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float*
     cudaStream_t ps = env->pipe[k % 3];
     RMV_CUDA(cudaMemcpyAsync(env->h_act + c0 * A, act_host + c0 * A, (size_t)cn * A * sizeof(float), cudaMemcpyHostToDevice, ps));
     rc = launch_step(env, env->h_act + c0 * A, RMV_ACT_AOS, 0, 0, env->h_rew + c0, env->h_done + c0, cn,
-                     obs_host ? env->h_obs + c0 * S : nullptr, auto_reset, 1, ps, c0, cn, false);
+                     obs_dev ? obs_dev + c0 * S : nullptr, auto_reset, 1, ps, c0, cn, false);
     if (rc) return rc;
-    if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host + c0 * S, env->h_obs + c0 * S, (size_t)cn * S * sizeof(float), cudaMemcpyDeviceToHost, ps));
+    if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host + c0 * S, obs_src + c0 * S, (size_t)cn * S * sizeof(float), cudaMemcpyDeviceToHost, ps));
     if (reward_host) RMV_CUDA(cudaMemcpyAsync(reward_host + c0, env->h_rew + c0, (size_t)cn * sizeof(float), cudaMemcpyDeviceToHost, ps));
     if (done_host) RMV_CUDA(cudaMemcpyAsync(done_host + c0, env->h_done + c0, (size_t)cn, cudaMemcpyDeviceToHost, ps));
   }
@@ -1094,9 +1125,9 @@ extern "C" RMV_API int rmv_reset_host(rmv_env* env, float* obs_host, void* strea
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = ensure_staging(env);
   if (rc) return rc;
-  rc = rmv_reset(env, nullptr, obs_host ? env->h_obs : nullptr, stream);
+  rc = rmv_reset(env, nullptr, (obs_host && !env->rows) ? env->h_obs : nullptr, stream);
   if (rc) return rc;
-  if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host, env->h_obs, (size_t)env->n * env->S * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host, env->rows ? env->state : env->h_obs, (size_t)env->n * env->S * sizeof(float), cudaMemcpyDeviceToHost, st));
   RMV_CUDA(cudaStreamSynchronize(st));
   return RMV_OK;
 }
@@ -1113,6 +1144,7 @@ extern "C" RMV_API int rmv_control(rmv_env* env, const float* ref_pos, const flo
   RMV_ON_DEVICE(env->device);
   ControlArgs a;
   a.state = env->state; a.act = act_dev; a.n = env->n; a.act_ld = act_ld; a.act_soa = (act_layout == RMV_ACT_SOA);
+  a.rows = env->rows ? 1 : 0;
   static const float kRef[RMV_NUM_KINDS][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 2.0f}, {0, 0, 1.0f}, {0, 0, 0}};
   const int D = (env->kind == RMV_QUAD2D || env->kind == RMV_QUAD2D_SLUNG) ? 2 : 3;
   for (int i = 0; i < 3; ++i) {

@@ -14,6 +14,7 @@ struct ControlArgs {
   float* act;             // [n][A] or [A][act_ld]
   int64_t n, act_ld;
   int act_soa;
+  int rows;               // state is [n][S] rows (RMV_STATE_ROWS handle)
   float ref_pos[3], ref_vel[3];
   float mass, gravity;
 };
@@ -48,11 +49,20 @@ __global__ void __launch_bounds__(128) k_control(const ControlArgs a) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A, D = Dims<KIND>::D;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n) return;
-  const float* const row = a.state + ((e >> 7) * (int64_t)(S * kTile) + (e & (kTile - 1)));
+  float st[S];
+  if (a.rows) {
+#pragma unroll
+    for (int c = 0; c < S; ++c) st[c] = a.state[e * S + c];
+  } else {
+    const float* const tile = a.state + ((e >> 7) * (int64_t)(S * kTile) + (e & (kTile - 1)));
+#pragma unroll
+    for (int c = 0; c < S; ++c) st[c] = tile[c * kTile];
+  }
+  const float* const row = st;
   float out[A];
   if constexpr (D == 2) {
     const float kp = -5.0f, kv = -4.0f, tau = 0.1f;
-    const float px = row[0], py = row[kTile], th = row[2 * kTile], vx = row[3 * kTile], vy = row[4 * kTile];
+    const float px = row[0], py = row[1], th = row[2], vx = row[3], vy = row[4];
     const float ax = kp * (px - a.ref_pos[0]) + kv * (vx - a.ref_vel[0]) + 0.0f;
     const float ay = kp * (py - a.ref_pos[1]) + kv * (vy - a.ref_vel[1]) + a.gravity;
     const float att = atan2f(ay, ax) - 1.57079632679489661923f;
@@ -62,9 +72,9 @@ __global__ void __launch_bounds__(128) k_control(const ControlArgs a) {
     const float kp = -5.0f, kv = -4.0f, tau = 0.3f;
     float p[3], q[4], v[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { p[i] = row[i * kTile]; v[i] = row[(7 + i) * kTile]; }
+    for (int i = 0; i < 3; ++i) { p[i] = row[i]; v[i] = row[7 + i]; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) q[i] = row[(3 + i) * kTile];
+    for (int i = 0; i < 4; ++i) q[i] = row[3 + i];
     float acc[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) acc[i] = kp * (p[i] - a.ref_pos[i]) + kv * (v[i] - a.ref_vel[i]) + (i == 2 ? a.gravity : 0.0f);

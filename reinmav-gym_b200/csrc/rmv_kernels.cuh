@@ -646,14 +646,16 @@ __global__ void __launch_bounds__(128) k_rollout(const StepArgs a) {
 }
 
 // ---- reset(): all envs or a masked subset --------------------------------------------------
-template <int KIND>
+// ROWS: the handle keeps its state as [n][S] rows (RMV_STATE_ROWS) instead of tiles.
+template <int KIND, bool ROWS>
 __global__ void k_reset(float* state, uint32_t* episode, int64_t n, const uint8_t* mask, uint64_t seed,
                         int64_t env_id_offset, float* obs, float* ep_return, uint32_t* ep_start,
                         uint32_t step_index) {
   constexpr int S = Dims<KIND>::S;
+  constexpr int kPitch = ROWS ? 1 : kTile;         // distance between two components of one env
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  float* const row = state + (e / kTile) * (int64_t)(S * kTile) + (e % kTile);
+  float* const row = ROWS ? state + e * S : state + (e / kTile) * (int64_t)(S * kTile) + (e % kTile);
   float s[S];
   if (mask == nullptr || mask[e] != 0) {
     const uint32_t word = episode[e];
@@ -661,13 +663,13 @@ __global__ void k_reset(float* state, uint32_t* episode, int64_t n, const uint8_
     episode[e] = (word & kEverDone) | count;     // reset() never clears steps_beyond_done (quadrotor3d.py:182-185)
     reset_draws<KIND>(seed, (uint64_t)(env_id_offset + e), count, s);
 #pragma unroll
-    for (int c = 0; c < S; ++c) row[c * kTile] = s[c];
+    for (int c = 0; c < S; ++c) row[c * kPitch] = s[c];
     if (ep_return) { ep_return[e] = 0.0f; ep_start[e] = step_index; }
   } else if (obs) {
 #pragma unroll
-    for (int c = 0; c < S; ++c) s[c] = row[c * kTile];
+    for (int c = 0; c < S; ++c) s[c] = row[c * kPitch];
   }
-  if (obs) {
+  if (obs && obs != state) {
 #pragma unroll
     for (int c = 0; c < S; ++c) obs[e * S + c] = s[c];
   }

@@ -13,6 +13,7 @@ QUAD2D, QUAD2D_SLUNG, QUAD3D, QUAD3D_SLUNG, REINMAV = 0, 1, 2, 3, 4
 ACT_AOS, ACT_SOA = 0, 1
 MANY_STREAM, MANY_ROLLOUT, MANY_LAUNCHES = 0, 1, 2
 TRACK_EPISODES = 1
+STATE_ROWS = 2
 EVER_DONE_BIT = 0x80000000
 ABI_VERSION = 2
 
@@ -70,7 +71,7 @@ SIGNATURES = {
     "rmv_step": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp]),
     "rmv_step_rows": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp]),
     "rmv_step_many": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp, _i64, _i, _vp]),
-    "rmv_set_stream": (_i, [_vp, _i, _i, _i]),
+    "rmv_set_stream": (_i, [_vp, _i, _i]),
     "rmv_stream_shape": (_i, [_i64, _i, _i, _pi, _pi, _pi, _pi]),
     "rmv_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rmv_reset_host": (_i, [_vp, _vp, _vp]),

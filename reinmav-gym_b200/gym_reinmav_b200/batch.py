@@ -95,7 +95,10 @@ class _DeviceView:
 
 
 class QuadBatch:
-    def __init__(self, kind, num_envs, device=0, seed=0, env_id_offset=0, params=None, track_episodes=False):
+    def __init__(self, kind, num_envs, device=0, seed=0, env_id_offset=0, params=None, track_episodes=False,
+                 state_layout="tiles"):
+        """``state_layout``: "tiles" (float32 [ld/128, S, 128], the default) or "rows" (float32 [ld, S]: the state
+        buffer is the observation matrix itself, stepped in place — ``RMV_STATE_ROWS``)."""
         if isinstance(kind, str):
             if kind not in ENV_IDS:
                 raise KeyError("unknown env id %r (have %s)" % (kind, sorted(ENV_IDS)))
@@ -109,7 +112,10 @@ class QuadBatch:
                 if not hasattr(p, k):
                     raise KeyError("rmv_params has no field %r" % k)
                 setattr(p, k, v)
-        flags = _capi.TRACK_EPISODES if track_episodes else 0
+        if state_layout not in ("tiles", "rows"):
+            raise ValueError("state_layout must be 'tiles' or 'rows', got %r" % (state_layout,))
+        self.state_layout = state_layout
+        flags = (_capi.TRACK_EPISODES if track_episodes else 0) | (_capi.STATE_ROWS if state_layout == "rows" else 0)
         check(lib().rmv_create(ctypes.byref(self._h), self.kind, int(num_envs), int(env_id_offset), self.device,
                                self.seed & 0xFFFFFFFFFFFFFFFF, ctypes.byref(p) if p is not None else None, flags))
         s, a, n, ld = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
@@ -167,9 +173,9 @@ class QuadBatch:
         """L2 access-policy window on the state (state stays L2-resident between steps): -1 auto, 0 off, 1 on."""
         check(lib().rmv_set_l2_persist(self._h, int(mode)))
 
-    def set_stream(self, pipe=-1, warps_per_sm=0, block=0):
+    def set_stream(self, warps_per_sm=0, block=0):
         """Tuning of the step-stream kernel behind ``step_many(fused=0)``; results are identical."""
-        check(lib().rmv_set_stream(self._h, int(pipe), int(warps_per_sm), int(block)))
+        check(lib().rmv_set_stream(self._h, int(warps_per_sm), int(block)))
 
     def set_host_chunks(self, chunks=0):
         check(lib().rmv_set_host_chunks(self._h, int(chunks)))
@@ -280,10 +286,13 @@ class QuadBatch:
         check(lib().rmv_set_episode(self._h, words.ctypes.data, 0, _stream(stream, self.device)))
 
     def state_view(self):
-        """Device view of the tiled state, float32 [ld/128, S, 128]: env e is [e // 128, :, e % 128]
-        (lanes of the last tile beyond N are padding)."""
+        """Device view of the handle's state.  Tiles: float32 [ld/128, S, 128], env e is [e // 128, :, e % 128]
+        (lanes of the last tile beyond N are padding).  Rows: float32 [ld, S], env e is row e (rows beyond N are
+        padding) — the observation matrix itself."""
         sp, ep = ctypes.c_void_p(), ctypes.c_void_p()
         check(lib().rmv_state_ptr(self._h, ctypes.byref(sp), ctypes.byref(ep)))
+        if self.state_layout == "rows":
+            return _DeviceView(sp.value, (self.ld, self.state_dim), "<f4", self)
         return _DeviceView(sp.value, (self.ld // 128, self.state_dim, 128), "<f4", self)
 
     def episode_stats(self, stream=None):

@@ -221,15 +221,14 @@ STREAM_CASES = [
 ]
 
 
-@pytest.mark.parametrize("pipe", [0, 1])
 @pytest.mark.parametrize("case", range(len(STREAM_CASES)))
 @pytest.mark.parametrize("env_id", ENV_IDS)
-def test_step_stream_bitwise(torch, rmv, env_id, case, pipe):
+def test_step_stream_bitwise(torch, rmv, env_id, case):
     """rmv_step_many(mode = RMV_MANY_STREAM): the persistent step stream (one launch, every warp walks its own units
-    through all T steps, finished envs re-drawn inside the warp) against T launches of the single-step kernel — state,
-    rewards, done flags, episode words and episode statistics bit for bit; two consecutive calls (the second starts
-    from the first one's state), wide initial states (a third of the envs finish at once), with and without the
-    next-item prefetch, every ownership shape."""
+    through all T steps, finished envs re-drawn by their own warp once per step) against T launches of the single-step
+    kernel — state, rewards, done flags, episode words and episode statistics bit for bit; two consecutive calls (the
+    second starts from the first one's state), wide initial states (a third of the envs finish at once: the per-warp
+    re-draw list overflows and is flushed mid-step), every ownership shape."""
     n, cap, block, track, layout = STREAM_CASES[case]
     kind = KIND_OF_ID[env_id]
     S, A = STATE_DIM[kind], ACTION_DIM[kind]
@@ -251,7 +250,7 @@ def test_step_stream_bitwise(torch, rmv, env_id, case, pipe):
     out = []
     for mode in (2, 0):                           # RMV_MANY_LAUNCHES, RMV_MANY_STREAM
         b = rmv.QuadBatch(env_id, n, seed=seed, track_episodes=track)
-        b.set_stream(pipe=pipe, warps_per_sm=cap, block=block)
+        b.set_stream(warps_per_sm=cap, block=block)
         b.reset()
         b.set_state(start)
         rew = torch.empty((2, T, n), dtype=torch.float32, device=dev)

@@ -71,9 +71,17 @@ def test_vec_env_tensor_path_matches_host_path(rmv):
         ob, rb, db = b_env.step_tensor(torch.as_tensor(act, device="cuda:0"))
         assert same_bits(oa, ob.cpu().numpy()) and same_bits(ra, rb.cpu().numpy())
         assert np.array_equal(da, db.cpu().numpy().astype(bool))
-    tiles = b_env.state_tensor()                       # [n/128, S, 128] view of the handle's own buffer
-    rows = tiles.permute(0, 2, 1).reshape(-1, 10)[:n]
-    assert same_bits(rows.cpu().numpy(), oa)
+    assert b_env.state_layout == "rows"                # the 3D kinds keep the observation matrix as their state
+    rows = b_env.state_tensor()[:n]                    # [n_pad, S] view of the handle's own buffer
+    assert same_bits(rows.cpu().numpy(), oa) and rows.data_ptr() == ob.data_ptr()      # step_tensor's obs IS the state
+    c_env = rmv.QuadVecEnv("quadrotor3d-v0", n, seed=seed, state_layout="tiles")
+    c_env.reset_tensor()
+    rng = np.random.RandomState(1)
+    for t in range(120):
+        oc, _, _ = c_env.step_tensor(torch.as_tensor(rng.uniform(0, 10, size=(n, 4)).astype(np.float32), device="cuda:0"))
+    tiles = c_env.state_tensor()                       # [n/128, S, 128]
+    assert same_bits(tiles.permute(0, 2, 1).reshape(-1, 10)[:n].cpu().numpy(), oa) and same_bits(oc.cpu().numpy(), oa)
+    c_env.close()
     a_env.close()
     b_env.close()
 
@@ -360,6 +368,83 @@ def test_misaligned_action_rows_are_refused(rmv):
         b.step(big[:n * 4].cpu(), rew, done)
     torch.cuda.synchronize()
     b.close()
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_row_state_handle_equals_tiled_handle(rmv, env_id):
+    """RMV_STATE_ROWS: the handle keeps [N, S] rows and steps them in place.  Every entry point against a tiled handle,
+    bit for bit: reset (all / masked, with obs), step (obs == NULL, obs == the state pointer, obs == another buffer),
+    step_host (single shot and chunked), step_many, control, set/get state, episode words and statistics."""
+    import torch
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    lo, hi = ACTION_BOUNDS[kind]
+    n, seed, dev = 70000 + 45, 17, "cuda:0"
+    t_ = rmv.QuadBatch(env_id, n, seed=seed, track_episodes=True)
+    r_ = rmv.QuadBatch(env_id, n, seed=seed, track_episodes=True, state_layout="rows")
+    rows = torch.as_tensor(r_.state_view(), device=dev)
+    assert rows.shape == (r_.ld, S)
+    obs_t = torch.empty((n, S), dtype=torch.float32, device=dev); obs_r = torch.empty_like(obs_t)
+    rew_t = torch.empty(n, dtype=torch.float32, device=dev); rew_r = torch.empty_like(rew_t)
+    done_t = torch.empty(n, dtype=torch.uint8, device=dev); done_r = torch.empty_like(done_t)
+    act = torch.empty((n, A), dtype=torch.float32, device=dev)
+
+    def same():
+        torch.cuda.synchronize()
+        assert same_bits(t_.get_state(), r_.get_state()) and same_bits(r_.get_state(), rows[:n].cpu().numpy())
+        assert np.array_equal(t_.get_episode_words(), r_.get_episode_words())
+
+    t_.reset(obs=obs_t); r_.reset(obs=obs_r)
+    assert torch.equal(obs_t.view(torch.int32), obs_r.view(torch.int32)); same()
+    mask = torch.as_tensor((np.arange(n) % 5 == 0).astype(np.uint8), device=dev)
+    t_.reset(mask=mask); r_.reset(mask=mask); same()
+    n_done = 0
+    for t in range(90):
+        rmv.fill_uniform_actions(act, n, A, 2 * lo, 2 * hi, seed, step_index=t)
+        t_.step(act, rew_t, done_t, obs=obs_t)
+        r_.step(act, rew_r, done_r, obs=[None, rows, obs_r][t % 3])
+        assert torch.equal(rew_t.view(torch.int32), rew_r.view(torch.int32)) and torch.equal(done_t, done_r), t
+        assert torch.equal(obs_t.view(torch.int32), rows[:n].view(torch.int32)), t
+        if t % 3 == 2:
+            assert torch.equal(obs_t.view(torch.int32), obs_r.view(torch.int32)), t
+        n_done += int(done_t.sum())
+    assert n_done > 100; same()
+    # controllers read the rows
+    a_t = torch.empty((n, A), dtype=torch.float32, device=dev); a_r = torch.empty_like(a_t)
+    t_.control(a_t); r_.control(a_r)
+    assert torch.equal(a_t.view(torch.int32), a_r.view(torch.int32))
+    # host path: single shot and chunked; observations leave from the state itself
+    ho_t, ho_r = np.empty((n, S), np.float32), np.empty((n, S), np.float32)
+    hr_t, hr_r, hd_t, hd_r = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.uint8), np.empty(n, np.uint8)
+    rng = np.random.RandomState(4)
+    for chunks in (1, 0, 3):
+        t_.set_host_chunks(chunks); r_.set_host_chunks(chunks)
+        for _ in range(4):
+            a = rng.uniform(lo, hi, size=(n, A)).astype(np.float32)
+            t_.step_host(a, hr_t, hd_t, ho_t); r_.step_host(a, hr_r, hd_r, ho_r)
+            assert same_bits(ho_t, ho_r) and same_bits(hr_t, hr_r) and np.array_equal(hd_t, hd_r)
+    same()
+    t_.reset_host(ho_t); r_.reset_host(ho_r)
+    assert same_bits(ho_t, ho_r); same()
+    # step_many (row-state handles launch the row-state kernel once per step), every mode
+    T = 12
+    acts = torch.empty((T, n, A), dtype=torch.float32, device=dev)
+    for t in range(T):
+        rmv.fill_uniform_actions(acts[t], n, A, lo, hi, seed, step_index=1000 + t)
+    rt = torch.empty((T, n), dtype=torch.float32, device=dev); rr = torch.empty_like(rt)
+    dt = torch.empty((T, n), dtype=torch.uint8, device=dev); dr = torch.empty_like(dt)
+    for mode in (0, 1, 2):
+        t_.step_many(T, acts, rt, dt, out_ld=n, layout=0, fused=mode); r_.step_many(T, acts, rr, dr, out_ld=n, layout=0, fused=mode)
+        assert torch.equal(rt.view(torch.int32), rr.view(torch.int32)) and torch.equal(dt, dr); same()
+    # set_state from host and from device rows
+    st = np.random.RandomState(5).uniform(-1, 1, (n, S)).astype(np.float32)
+    t_.set_state(st); r_.set_state(st); same()
+    r_.set_state_device(torch.as_tensor(st[::-1].copy(), device=dev)); t_.set_state(st[::-1].copy()); same()
+    a, b = t_.episode_stats(), r_.episode_stats()
+    assert a["episodes"] == b["episodes"] > 0 and a["length_sum"] == b["length_sum"] and a["env_steps"] == b["env_steps"]
+    t_.close(); r_.close()
+    with pytest.raises(rmv.RmvError):
+        rmv.QuadBatch("reinmav-v0", 8, state_layout="rows")
 
 
 def test_vec_env_zero_copy_mode(rmv):

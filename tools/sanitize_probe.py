@@ -27,8 +27,8 @@ for env_id, (lo, hi) in BOUNDS.items():
             b.step(act[t], rew[t], done[t], obs=obs if t % 2 else None)
         b.step_many(8, act, rew, done, out_ld=n, layout=0, fused=True)
         b.step_many(8, act, rew, done, out_ld=n, layout=0, fused=2)
-        for pipe in (0, 1):
-            b.set_stream(pipe=pipe, warps_per_sm=1)
+        for cap in (0, 1):
+            b.set_stream(warps_per_sm=cap)
             b.step_many(8, act, rew, done, out_ld=n, layout=0, fused=0)
         b.get_state(); b.episode_stats()
         torch.cuda.synchronize()
