@@ -261,6 +261,18 @@ RMV_API int rmv_reset_host(rmv_env* env, float* obs_host /*[n][S]*/, void* strea
  * (ref_pos (0,0) | (0,0,2) | slung 3D (0,0,1); ref_vel 0). */
 RMV_API int rmv_control(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_dev,
                         int act_layout, int64_t act_ld, void* stream);
+/* control() + step() FUSED: the closed loop of the reference's own tests — `action = env.control();
+ * env.step(action)` (test/test_quadrotor3d.py:16-22 and twins) — as ONE kernel: state in -> controller -> dynamics ->
+ * reward / done -> reset-on-done -> state out.  No action buffer is read: 4(2S+1)+1 bytes per env-step.  act_out_dev
+ * (NULL, or float32 [n][A] rows aligned to one row) receives the actions the controller produced; the other arguments
+ * are those of rmv_step.  Same results bit for bit as rmv_control followed by rmv_step. */
+RMV_API int rmv_control_step(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_out_dev,
+                             float* reward_dev, uint8_t* done_dev, float* obs_aos_dev, int auto_reset, void* stream);
+/* T closed-loop steps with reset-on-done (the 400-step loop of test/test_quadrotor3d.py:16-22): one launch of the step
+ * stream (one launch per step on an RMV_STATE_ROWS handle).  act_out_dev NULL or [T][n][A]; reward_dev / done_dev both
+ * NULL or [T][out_ld]. */
+RMV_API int rmv_control_step_many(rmv_env* env, int n_steps, const float* ref_pos, const float* ref_vel, float* act_out_dev,
+                                  float* reward_dev, uint8_t* done_dev, int64_t out_ld, void* stream);
 /* same with a host destination [n][A]; synchronises `stream` */
 RMV_API int rmv_control_host(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_host,
                              void* stream);

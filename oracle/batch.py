@@ -25,6 +25,7 @@ stream (replaces the MT19937 stream of quadrotor3d.py:77-79,184).
 import numpy as np
 
 from . import philox
+from .atan32 import atan2_32
 from .fma32 import fma32
 from .sincos32 import sincos32
 
@@ -334,7 +335,11 @@ class BatchOracle:
         from atan2, first-order attitude loop tau = 0.1).  3D kinds: quadrotor3d.py:126-180 /
         quadrotor3d_slungload.py:169-226 (PD acceleration, desired attitude via ``Quaternion(matrix=)``
         — pyquaternion's trace method on the transposed matrix — error quaternion from the
-        UN-normalised current attitude, tau = 0.3, thrust projected on the normalised body z)."""
+        UN-normalised current attitude, tau = 0.3, thrust projected on the normalised body z).
+
+        float32 (tier T1) is the bit model of ``control_law`` in csrc/rmv_math.cuh: the same expression order,
+        every operation individually rounded (NumPy float32 arithmetic), the sum of squares inside the norms and the
+        body-z projection fused as in ``step()``, ``atan2`` from oracle/atan32.py."""
         s = self.state
         rp = [self._c(v) for v in (ref_pos if ref_pos is not None else self.REF_POS[self.kind])]
         rv = [self._c(v) for v in (ref_vel if ref_vel is not None else (0.0,) * len(rp))]
@@ -344,7 +349,8 @@ class BatchOracle:
                 kp, kv, tau = self._c(-5.0), self._c(-4.0), self._c(0.1)
                 pos, th, vel = s[0:2], s[2], s[3:5]
                 acc = [kp * (pos[i] - rp[i]) + kv * (vel[i] - rv[i]) + (gr if i == 1 else self._c(0.0)) for i in range(2)]
-                att = np.arctan2(acc[1], acc[0]) - self._c(np.pi / 2)
+                atan2 = np.arctan2 if self.dtype is np.float64 else atan2_32
+                att = atan2(acc[1], acc[0]) - self._c(np.pi / 2)
                 w = (self._c(-1.0) / tau) * (th - att)
                 thrust = self._c(self.p["mass"]) * self._norm(acc)
                 return np.stack([thrust, w], axis=1)

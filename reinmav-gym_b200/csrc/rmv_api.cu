@@ -584,7 +584,7 @@ extern "C" RMV_API int rmv_launch_shape(int kind, int64_t n_envs, int* block, in
   return RMV_OK;
 }
 
-template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF>
+template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF, bool CTRL = false>
 static cudaError_t launch_step_kvf(const StepArgs& args, const cudaAccessPolicyWindow* win, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
   constexpr int SP = V == 1 ? row_pitch<S>() : ((S % 2 == 0) ? S + 1 : S);
@@ -597,7 +597,7 @@ static cudaError_t launch_step_kvf(const StepArgs& args, const cudaAccessPolicyW
     static bool raised[kMaxDevices] = {};      // per instantiation AND per device (function attributes are per context)
     const int dev = current_device();
     if (!raised[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(k_step<KIND, V, OBS, TRACK, BLOCK, PREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(k_step<KIND, V, OBS, TRACK, BLOCK, PREF, CTRL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       raised[dev] = true;
     }
@@ -621,10 +621,20 @@ static cudaError_t launch_step_kvf(const StepArgs& args, const cudaAccessPolicyW
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, k_step<KIND, V, OBS, TRACK, BLOCK, PREF>, args);
+  return cudaLaunchKernelEx(&cfg, k_step<KIND, V, OBS, TRACK, BLOCK, PREF, CTRL>, args);
 }
 
-template <int KIND, bool TRACK, int BLOCK>
+// fused control() + step(): one env per thread, 128-thread CTAs
+template <int KIND>
+static cudaError_t launch_control_step_k(const StepArgs& args, cudaStream_t st) {
+  const bool track = args.ep_return != nullptr;
+  if (args.obs) return track ? launch_step_kvf<KIND, 1, true, true, 128, false, true>(args, nullptr, st)
+                             : launch_step_kvf<KIND, 1, true, false, 128, false, true>(args, nullptr, st);
+  return track ? launch_step_kvf<KIND, 1, false, true, 128, false, true>(args, nullptr, st)
+               : launch_step_kvf<KIND, 1, false, false, 128, false, true>(args, nullptr, st);
+}
+
+template <int KIND, bool TRACK, int BLOCK, bool CTRL = false>
 static cudaError_t launch_step_rows_kb(const StepArgs& args, cudaStream_t st) {
   constexpr int S = Dims<KIND>::S;
   constexpr int SP = row_pitch<S>();
@@ -638,11 +648,12 @@ static cudaError_t launch_step_rows_kb(const StepArgs& args, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_use_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k_step_rows<KIND, TRACK, BLOCK>, args);
+  return cudaLaunchKernelEx(&cfg, k_step_rows<KIND, TRACK, BLOCK, CTRL>, args);
 }
 template <int KIND>
-static cudaError_t launch_step_rows_k(const rmv_env* e, const StepArgs& args, cudaStream_t st) {
+static cudaError_t launch_step_rows_k(const rmv_env* e, const StepArgs& args, cudaStream_t st, bool ctrl = false) {
   const bool track = args.ep_return != nullptr;
+  if (ctrl) return track ? launch_step_rows_kb<KIND, true, 128, true>(args, st) : launch_step_rows_kb<KIND, false, 128, true>(args, st);
   const int block = e->block ? e->block : (KIND == QUAD2D ? 256 : 128);
   if (block == 256) return track ? launch_step_rows_kb<KIND, true, 256>(args, st) : launch_step_rows_kb<KIND, false, 256>(args, st);
   return track ? launch_step_rows_kb<KIND, true, 128>(args, st) : launch_step_rows_kb<KIND, false, 128>(args, st);
@@ -735,6 +746,7 @@ static void stream_shape_for(int64_t n, int sms, int resident_warps_per_sm, int 
   if (warps <= (uint32_t)sms * 24u) b = 32; else if (warps <= (uint32_t)sms * 48u) b = 64;
   if (forced_block == 32 || forced_block == 64 || forced_block == 128) b = (unsigned)forced_block;
   shape->units_per_warp = k; shape->warps = warps;
+  shape->limit = units * 32u; shape->env_stride = warps * 32u;
   *block = b;
   *grid = (warps * 32u + b - 1u) / b;
 }
@@ -751,13 +763,13 @@ extern "C" RMV_API int rmv_stream_shape(int64_t n_envs, int sms, int resident_wa
   return RMV_OK;
 }
 
-template <int KIND, bool TRACK, bool PREF>
+template <int KIND, bool TRACK, bool PREF, bool CTRL = false>
 static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_t st) {
   static int resident_of[kMaxDevices] = {}, sms_of[kMaxDevices] = {};      // per instantiation and per device
   const int dev = current_device();
   if (resident_of[dev] == 0) {
     cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_stream<KIND, TRACK, PREF>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_stream<KIND, TRACK, PREF, CTRL>, 128, 0);
     if (resident_of[dev] < 1) resident_of[dev] = 1;
     if (sms_of[dev] < 1) sms_of[dev] = 1;
   }
@@ -784,12 +796,13 @@ static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, k_step_stream<KIND, TRACK, PREF>, args, shape);
+  return cudaLaunchKernelEx(&cfg, k_step_stream<KIND, TRACK, PREF, CTRL>, args, shape);
 }
 
 template <int KIND>
-static cudaError_t launch_stream_k(rmv_env* e, const StepArgs& args, cudaStream_t st) {
+static cudaError_t launch_stream_k(rmv_env* e, const StepArgs& args, cudaStream_t st, bool ctrl = false) {
   const bool track = args.ep_return != nullptr;
+  if (ctrl) return track ? launch_stream_t<KIND, true, false, true>(e, args, st) : launch_stream_t<KIND, false, false, true>(e, args, st);
   const bool pref = e->prefetch >= 0 ? e->prefetch != 0 : default_prefetch(KIND, args.n);
   if (track) return pref ? launch_stream_t<KIND, true, true>(e, args, st) : launch_stream_t<KIND, true, false>(e, args, st);
   return pref ? launch_stream_t<KIND, false, true>(e, args, st) : launch_stream_t<KIND, false, false>(e, args, st);
@@ -819,7 +832,8 @@ static void reinmav_inverse_inertia(double out[9]) {
 // 128-env tile; the whole handle when cn == n).  act / rew / done / obs point at env c0's element.
 static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act_ld, int64_t act_step_stride,
                        float* rew, uint8_t* done, int64_t out_ld, float* obs, int auto_reset, int n_steps,
-                       cudaStream_t st, int64_t c0 = 0, int64_t cn = -1, bool advance_clock = true, bool stream = false) {
+                       cudaStream_t st, int64_t c0 = 0, int64_t cn = -1, bool advance_clock = true, bool stream = false,
+                       const CtrlParams* ctrl = nullptr, float* act_out = nullptr) {
   if (cn < 0) cn = e->n;
   if (e->kind == RMV_REINMAV) {
     // no action; n_steps consecutive steps, each np.arange(t, t + dt, 1/5000) substeps (reinmav_env.py:90-98)
@@ -844,7 +858,12 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
     if (advance_clock) { e->sim_time = t; e->step_index += (uint32_t)n_steps; }
     return RMV_OK;
   }
-  RMV_REQUIRE(act != nullptr, "act_dev is NULL");
+  if (ctrl) {                                      // fused control() + step(): no action input
+    act = nullptr; act_layout = RMV_ACT_AOS; act_ld = 0; act_step_stride = cn * e->A;
+    RMV_REQUIRE(aligned(act_out, (size_t)e->A * 4u), "act_out_dev must be aligned to one action row (%d bytes)", e->A * 4);
+  } else {
+    RMV_REQUIRE(act != nullptr, "act_dev is NULL");
+  }
   RMV_REQUIRE(act_layout == RMV_ACT_AOS || act_layout == RMV_ACT_SOA, "bad act_layout %d", act_layout);
   if (act_layout == RMV_ACT_SOA) RMV_REQUIRE(act_ld >= cn, "act_ld (%lld) < n_envs", (long long)act_ld);
   RMV_REQUIRE(aligned(act, 4) && aligned(rew, 4) && aligned(obs, 4), "float buffers must be 4-byte aligned");
@@ -883,6 +902,10 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
   philox_key_schedule(e->seed, a.ks);
   a.n_steps = n_steps; a.act_soa = (act_layout == RMV_ACT_SOA); a.auto_reset = auto_reset ? 1 : 0;
   a.P = e->dp;
+  a.C = ctrl ? *ctrl : CtrlParams{};
+  a.act_out = act_out;
+  a.rows_in = nullptr;
+  const bool fused_ctrl = ctrl != nullptr;
   cudaError_t err;
   if (e->rows) {
     // RMV_STATE_ROWS: the state buffer is the [n][S] observation matrix; the row-state kernel updates it in place
@@ -891,19 +914,27 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
     float* const rows = e->state + c0 * e->S;
     a.rows_in = rows; a.obs = rows;
     switch (e->kind) {
-      case RMV_QUAD2D: err = launch_step_rows_k<QUAD2D>(e, a, st); break;
-      case RMV_QUAD2D_SLUNG: err = launch_step_rows_k<QUAD2D_SLUNG>(e, a, st); break;
-      case RMV_QUAD3D: err = launch_step_rows_k<QUAD3D>(e, a, st); break;
-      default: err = launch_step_rows_k<QUAD3D_SLUNG>(e, a, st); break;
+      case RMV_QUAD2D: err = launch_step_rows_k<QUAD2D>(e, a, st, fused_ctrl); break;
+      case RMV_QUAD2D_SLUNG: err = launch_step_rows_k<QUAD2D_SLUNG>(e, a, st, fused_ctrl); break;
+      case RMV_QUAD3D: err = launch_step_rows_k<QUAD3D>(e, a, st, fused_ctrl); break;
+      default: err = launch_step_rows_k<QUAD3D_SLUNG>(e, a, st, fused_ctrl); break;
     }
     if (err == cudaSuccess && obs != nullptr && obs != rows)
       err = cudaMemcpyAsync(obs, rows, (size_t)cn * e->S * sizeof(float), cudaMemcpyDeviceToDevice, st);
   } else if (stream) {
     switch (e->kind) {
-      case RMV_QUAD2D: err = launch_stream_k<QUAD2D>(e, a, st); break;
-      case RMV_QUAD2D_SLUNG: err = launch_stream_k<QUAD2D_SLUNG>(e, a, st); break;
-      case RMV_QUAD3D: err = launch_stream_k<QUAD3D>(e, a, st); break;
-      default: err = launch_stream_k<QUAD3D_SLUNG>(e, a, st); break;
+      case RMV_QUAD2D: err = launch_stream_k<QUAD2D>(e, a, st, fused_ctrl); break;
+      case RMV_QUAD2D_SLUNG: err = launch_stream_k<QUAD2D_SLUNG>(e, a, st, fused_ctrl); break;
+      case RMV_QUAD3D: err = launch_stream_k<QUAD3D>(e, a, st, fused_ctrl); break;
+      default: err = launch_stream_k<QUAD3D_SLUNG>(e, a, st, fused_ctrl); break;
+    }
+  } else if (fused_ctrl) {
+    if (n_steps != 1) return fail(RMV_EINVAL, "internal: the fused control+step kernel is single-step");
+    switch (e->kind) {
+      case RMV_QUAD2D: err = launch_control_step_k<QUAD2D>(a, st); break;
+      case RMV_QUAD2D_SLUNG: err = launch_control_step_k<QUAD2D_SLUNG>(a, st); break;
+      case RMV_QUAD3D: err = launch_control_step_k<QUAD3D>(a, st); break;
+      default: err = launch_control_step_k<QUAD3D_SLUNG>(a, st); break;
     }
   } else {
     switch (e->kind) {
@@ -976,15 +1007,19 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
   if (env->rows) fused = RMV_MANY_LAUNCHES;       // row-state handles: one launch of the row-state kernel per step
   if (fused == RMV_MANY_ROLLOUT)
     return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st);
-  if (fused == RMV_MANY_STREAM && g_use_stream && n_steps >= 2)
-    return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st, 0, -1, true, true);
-  if (!reward_dev || !done_dev) {                 // the single-step kernel always writes both: park them in scratch
+  if (!reward_dev || !done_dev) {                 // the step kernels always write both: park a missing one in scratch
     int rc = ensure_staging(env);
     if (rc) return rc;
   }
   float* const rew0 = reward_dev ? reward_dev : env->h_rew;
   uint8_t* const done0 = done_dev ? done_dev : env->h_done;
   const int64_t out_stride = reward_dev ? out_ld : 0, done_stride = done_dev ? out_ld : 0;
+  if (fused == RMV_MANY_STREAM && g_use_stream && n_steps >= 2) {
+    // one stride for both outputs: if only one of them is parked, the other one's scratch must be T rows as well
+    if ((reward_dev == nullptr) != (done_dev == nullptr))
+      return fail(RMV_EINVAL, "rmv_step_many(RMV_MANY_STREAM): pass both reward_dev and done_dev, or neither");
+    return launch_step(env, act_dev, act_layout, act_ld, stride, rew0, done0, out_stride, nullptr, 1, n_steps, st, 0, -1, true, true);
+  }
   auto launch_all = [&](cudaStream_t s, bool advance) -> int {
     for (int t = 0; t < n_steps; ++t) {
       int rc = launch_step(env, act_dev + (int64_t)t * stride, act_layout, act_ld, 0, rew0 + (int64_t)t * out_stride,
@@ -1135,6 +1170,54 @@ extern "C" RMV_API int rmv_reset_host(rmv_env* env, float* obs_host, void* strea
 // ------------------------------------------------------------------------------------------
 // controllers
 // ------------------------------------------------------------------------------------------
+// self.ref_pos / self.ref_vel defaults of the reference classes (quadrotor3d.py:55-56 and twins) + the constants control() reads
+static CtrlParams ctrl_params_of(const rmv_env* env, const float* ref_pos, const float* ref_vel) {
+  static const float kRef[RMV_NUM_KINDS][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 2.0f}, {0, 0, 1.0f}, {0, 0, 0}};
+  const int D = (env->kind == RMV_QUAD2D || env->kind == RMV_QUAD2D_SLUNG) ? 2 : 3;
+  CtrlParams C;
+  for (int i = 0; i < 3; ++i) {
+    C.ref_pos[i] = (i < D) ? (ref_pos ? ref_pos[i] : kRef[env->kind][i]) : 0.0f;
+    C.ref_vel[i] = (i < D && ref_vel) ? ref_vel[i] : 0.0f;
+  }
+  C.mass = env->params.mass; C.gravity = env->params.gravity;
+  return C;
+}
+
+extern "C" RMV_API int rmv_control_step(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_out_dev,
+                                        float* reward_dev, uint8_t* done_dev, float* obs_aos_dev, int auto_reset, void* stream) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(env->kind != RMV_REINMAV, "reinmav-v0 runs its controller inside step() already");
+  RMV_REQUIRE(reward_dev != nullptr && done_dev != nullptr, "reward_dev and done_dev must not be NULL");
+  RMV_ON_DEVICE(env->device);
+  const CtrlParams C = ctrl_params_of(env, ref_pos, ref_vel);
+  return launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, reward_dev, done_dev, env->n, obs_aos_dev, auto_reset, 1,
+                     static_cast<cudaStream_t>(stream), 0, -1, true, false, &C, act_out_dev);
+}
+
+extern "C" RMV_API int rmv_control_step_many(rmv_env* env, int n_steps, const float* ref_pos, const float* ref_vel,
+                                             float* act_out_dev, float* reward_dev, uint8_t* done_dev, int64_t out_ld, void* stream) {
+  RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(env->kind != RMV_REINMAV, "reinmav-v0 runs its controller inside step() already");
+  RMV_REQUIRE(n_steps > 0, "n_steps must be positive");
+  RMV_REQUIRE((reward_dev == nullptr) == (done_dev == nullptr), "pass both reward_dev and done_dev, or neither");
+  if (reward_dev) RMV_REQUIRE(out_ld >= env->n, "out_ld (%lld) < n_envs", (long long)out_ld);
+  RMV_ON_DEVICE(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const CtrlParams C = ctrl_params_of(env, ref_pos, ref_vel);
+  if (!reward_dev) { int rc = ensure_staging(env); if (rc) return rc; }
+  float* const rew0 = reward_dev ? reward_dev : env->h_rew;
+  uint8_t* const done0 = done_dev ? done_dev : env->h_done;
+  const int64_t stride = reward_dev ? out_ld : 0;
+  if (!env->rows && g_use_stream && n_steps >= 2)       // ONE launch: the closed loop runs inside the step stream
+    return launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, rew0, done0, stride, nullptr, 1, n_steps, st, 0, -1, true, true, &C, act_out_dev);
+  for (int t = 0; t < n_steps; ++t) {
+    int rc = launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, rew0 + (int64_t)t * stride, done0 + (int64_t)t * stride, env->n, nullptr, 1, 1,
+                         st, 0, -1, true, false, &C, act_out_dev ? act_out_dev + (int64_t)t * env->n * env->A : nullptr);
+    if (rc) return rc;
+  }
+  return RMV_OK;
+}
+
 extern "C" RMV_API int rmv_control(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_dev,
                                    int act_layout, int64_t act_ld, void* stream) {
   RMV_REQUIRE(env != nullptr && act_dev != nullptr, "NULL argument");
@@ -1145,13 +1228,7 @@ extern "C" RMV_API int rmv_control(rmv_env* env, const float* ref_pos, const flo
   ControlArgs a;
   a.state = env->state; a.act = act_dev; a.n = env->n; a.act_ld = act_ld; a.act_soa = (act_layout == RMV_ACT_SOA);
   a.rows = env->rows ? 1 : 0;
-  static const float kRef[RMV_NUM_KINDS][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 2.0f}, {0, 0, 1.0f}, {0, 0, 0}};
-  const int D = (env->kind == RMV_QUAD2D || env->kind == RMV_QUAD2D_SLUNG) ? 2 : 3;
-  for (int i = 0; i < 3; ++i) {
-    a.ref_pos[i] = (i < D) ? (ref_pos ? ref_pos[i] : kRef[env->kind][i]) : 0.0f;
-    a.ref_vel[i] = (i < D && ref_vel) ? ref_vel[i] : 0.0f;
-  }
-  a.mass = env->params.mass; a.gravity = env->params.gravity;
+  a.C = ctrl_params_of(env, ref_pos, ref_vel);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = blocks_for(env->n, 128);
   switch (env->kind) {

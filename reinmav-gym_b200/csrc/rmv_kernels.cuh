@@ -50,6 +50,10 @@ struct StepArgs {
   uint32_t step_index;
   int n_steps, act_soa, auto_reset;
   DevParams P;
+  // fused control() + step() (CTRL instantiations): the action is computed from the state by the reference's geometric
+  // controller instead of being read; act_out (nullable, [n][A] rows) receives it for logging / tests
+  CtrlParams C;
+  float* act_out;
 };
 
 // ---- V-wide global access ----------------------------------------------------------------
@@ -102,6 +106,12 @@ __device__ __forceinline__ void load_contig_stream(const float* p, float (&o)[N]
     const float2 t = __ldcs(reinterpret_cast<const float2*>(p));
     o[0] = t.x; o[1] = t.y;
   }
+}
+
+template <int A>
+__device__ __forceinline__ void store_action_row(float* p, const float (&a)[A]) {
+  if constexpr (A == 4) *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+  else *reinterpret_cast<float2*>(p) = make_float2(a[0], a[1]);
 }
 
 template <int KIND, int V>
@@ -285,7 +295,7 @@ constexpr int step_min_ctas(int kind, int v, bool obs, bool track, int block) {
 
 // One CTA's worth of envs up to (not including) the re-draw pass.  FULL: every env of the CTA exists
 // (all CTAs but the last of a ragged batch), so no per-thread bounds checks.
-template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF, bool FULL>
+template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF, bool FULL, bool CTRL>
 __device__ __forceinline__ void step_envs(const StepArgs& a, uint32_t cta_e0, uint32_t* redraw_total,
                                           uint16_t* redraw_list, uint32_t* redraw_episode, float* tile) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
@@ -324,9 +334,16 @@ __device__ __forceinline__ void step_envs(const StepArgs& a, uint32_t cta_e0, ui
 #pragma unroll
       for (int v = 0; v < V; ++v) ep_started[v] = a.ep_start[e0 + v];      // padded to whole tiles: in bounds
     }
-    load_actions<KIND, V>(a, a.act, (int64_t)e0, full, act);
+    if constexpr (!CTRL) load_actions<KIND, V>(a, a.act, (int64_t)e0, full, act);
   }
   __syncthreads();                                 // *redraw_total = 0 is visible; the loads are in flight
+  if constexpr (CTRL) {
+    static_assert(!CTRL || V == 1, "the fused controller is built for one env per thread");
+    if (active) {
+      control_law<KIND>(a.C, s[0], act[0]);        // quadrotor3d.py:126-180 and twins, from the state just loaded
+      if (a.act_out) store_action_row<A>(a.act_out + (size_t)e0 * A, act[0]);
+    }
+  }
 
   if (active) {
     float rew[V];
@@ -429,8 +446,8 @@ __device__ __forceinline__ void step_envs(const StepArgs& a, uint32_t cta_e0, ui
   }
 }
 
-template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF>
-__global__ void __launch_bounds__(BLOCK, step_min_ctas(KIND, V, OBS, TRACK, BLOCK))
+template <int KIND, int V, bool OBS, bool TRACK, int BLOCK, bool PREF, bool CTRL = false>
+__global__ void __launch_bounds__(BLOCK, CTRL ? 8 : step_min_ctas(KIND, V, OBS, TRACK, BLOCK))
 k_step(const StepArgs a) {
   constexpr int S = Dims<KIND>::S;
   constexpr int NB = (S + 3) / 4;                  // Philox blocks per reset
@@ -449,9 +466,9 @@ k_step(const StepArgs a) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (cta_e0 + (uint32_t)(BLOCK * V) <= (uint32_t)a.n)     // uniform
-    step_envs<KIND, V, OBS, TRACK, BLOCK, PREF, true>(a, cta_e0, &redraw_total, redraw_list, redraw_episode, tile);
+    step_envs<KIND, V, OBS, TRACK, BLOCK, PREF, true, CTRL>(a, cta_e0, &redraw_total, redraw_list, redraw_episode, tile);
   else
-    step_envs<KIND, V, OBS, TRACK, BLOCK, PREF, false>(a, cta_e0, &redraw_total, redraw_list, redraw_episode, tile);
+    step_envs<KIND, V, OBS, TRACK, BLOCK, PREF, false, CTRL>(a, cta_e0, &redraw_total, redraw_list, redraw_episode, tile);
 
   // ---- re-draw the finished envs of this CTA: one (env, Philox block) pair per thread ------------
   __syncthreads();
@@ -487,8 +504,8 @@ k_step(const StepArgs a) {
 //
 // A warp owns 32 consecutive rows = 32*S contiguous floats: loaded with S coalesced 128-byte requests into a
 // shared tile [32][S|1] (odd pitch), read back one row per thread; stored the same way in reverse.
-template <int KIND, bool TRACK, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, step_min_ctas(KIND, 1, true, TRACK, BLOCK))
+template <int KIND, bool TRACK, int BLOCK, bool CTRL = false>
+__global__ void __launch_bounds__(BLOCK, CTRL ? 1024 / BLOCK : step_min_ctas(KIND, 1, true, TRACK, BLOCK))
 k_step_rows(const StepArgs a) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   constexpr int NB = (S + 3) / 4;
@@ -516,7 +533,7 @@ k_step_rows(const StepArgs a) {
   float ep_ret = 0.0f;
   uint32_t ep_started = 0u;
   if (active) {
-    load_actions<KIND, 1>(a, a.act, (int64_t)e, true, act);
+    if constexpr (!CTRL) load_actions<KIND, 1>(a, a.act, (int64_t)e, true, act);
     if (TRACK) { ep_ret = a.ep_return[e]; ep_started = a.ep_start[e]; }
   } else {
 #pragma unroll
@@ -526,6 +543,12 @@ k_step_rows(const StepArgs a) {
   float s[S];
   row_from_smem<S>(my + lane * SP, s);
   __syncthreads();                                 // redraw_total = 0 is visible
+  if constexpr (CTRL) {
+    if (active) {
+      control_law<KIND>(a.C, s, act[0]);
+      if (a.act_out) store_action_row<A>(a.act_out + (size_t)e * A, act[0]);
+    }
+  }
 
   bool redraw = false;
   if (active) {

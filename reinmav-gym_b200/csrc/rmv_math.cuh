@@ -501,6 +501,121 @@ template <> struct EnvStep<QUAD2D_SLUNG> {  // quadrotor2d_slungload.py:79-143
   }
 };
 
+// ------------------------------------------------------------------------------------------
+// control(): the reference's geometric controllers, one env, pinned arithmetic.
+//   2D kinds: quadrotor2d.py:115-138, quadrotor2d_slungload.py:156-183
+//   3D kinds: quadrotor3d.py:126-180, quadrotor3d_slungload.py:169-226
+// Every operation is individually rounded and in the reference's own left-to-right order (the only fused steps are
+// the sum-of-squares inside the norms and attitude_3d, as in step()); oracle/batch.py control() in float32 is the same
+// sequence, so the kernels are checked bit for bit (tests/test_host_twin.py on the CPU, tests/test_gpu_vec_env.py on
+// the GPU) and within 1e-5 of the float64 reference.
+// ------------------------------------------------------------------------------------------
+struct CtrlParams {
+  float ref_pos[3], ref_vel[3];   // self.ref_pos / self.ref_vel (quadrotor3d.py:55-56)
+  float mass, gravity;
+};
+
+// atan / atan2 in float32 with a pinned sequence (mirror of oracle/atan32.py): octant reduction + degree-4 polynomial
+// in x^2 (Cephes atanf coefficients), no fused multiply-add.  <= 2.8e-7 absolute on [-pi, pi].
+RMV_HD float atan_pinned(float xin) {
+  const bool neg = (bits_of(xin) >> 31) != 0u;
+  const rf ax(fabsf(xin));
+  const bool big = ax.v > 2.414213562373095f, mid = ax.v > 0.4142135623730950f;
+  const rf y0(big ? 1.57079632679489661923f : (mid ? 0.78539816339744830962f : 0.0f));
+  rf r = ax;
+  if (big) r = -(rf(1.0f) / ax);
+  else if (mid) r = (ax - rf(1.0f)) / (ax + rf(1.0f));
+  const rf z = r * r;
+  const rf p = (((rf(8.05374449538e-2f) * z - rf(1.38776856032e-1f)) * z + rf(1.99777106478e-1f)) * z - rf(3.33329491539e-1f)) * z * r + r;
+  const rf y = y0 + p;
+  return neg ? -y.v : y.v;
+}
+RMV_HD float atan2_pinned(float y, float x) {
+  const float pi = 3.14159265358979323846f, pio2 = 1.57079632679489661923f;
+  if (x != x || y != y) return float_of(0x7fc00000u);
+  if (x == 0.0f) return y < 0.0f ? -pio2 : (y == 0.0f ? 0.0f : pio2);
+  if (y == 0.0f) return x < 0.0f ? ((bits_of(y) >> 31) ? -pi : pi) : y;      // +-0 -> +-pi or +-0, as libm
+  const rf z(atan_pinned((rf(y) / rf(x)).v));
+  const rf w(x < 0.0f ? (y < 0.0f ? -pi : pi) : 0.0f);
+  return (w + z).v;
+}
+
+// pyquaternion Quaternion(matrix=R) on m = R^T (rows xb, yb, zb): trace method, largest component first
+RMV_HD void quat_from_rows(const rf (&m)[3][3], rf (&q)[4]) {
+  const rf one(1.0f);
+  rf t;
+  if (m[2][2].v < 0.0f) {
+    if (m[0][0].v > m[1][1].v) {
+      t = one + m[0][0] - m[1][1] - m[2][2];
+      q[0] = m[1][2] - m[2][1]; q[1] = t; q[2] = m[0][1] + m[1][0]; q[3] = m[2][0] + m[0][2];
+    } else {
+      t = one - m[0][0] + m[1][1] - m[2][2];
+      q[0] = m[2][0] - m[0][2]; q[1] = m[0][1] + m[1][0]; q[2] = t; q[3] = m[1][2] + m[2][1];
+    }
+  } else {
+    if (m[0][0].v < -m[1][1].v) {
+      t = one - m[0][0] - m[1][1] + m[2][2];
+      q[0] = m[0][1] - m[1][0]; q[1] = m[2][0] + m[0][2]; q[2] = m[1][2] + m[2][1]; q[3] = t;
+    } else {
+      t = one + m[0][0] + m[1][1] + m[2][2];
+      q[0] = t; q[1] = m[1][2] - m[2][1]; q[2] = m[2][0] - m[0][2]; q[3] = m[0][1] - m[1][0];
+    }
+  }
+  const rf sc = rf(0.5f) / sqrt(t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = q[i] * sc;
+}
+
+template <int KIND>
+RMV_HD void control_law(const CtrlParams& C, const float (&s)[Dims<KIND>::S], float (&out)[Dims<KIND>::A]) {
+  constexpr int D = Dims<KIND>::D;
+  const rf kp(-5.0f), kv(-4.0f), g(C.gravity);
+  if constexpr (D == 2) {
+    const rf tau(0.1f);
+    const rf pos[2] = {s[0], s[1]}, th(s[2]), vel[2] = {s[3], s[4]};
+    rf acc[2];
+    acc[0] = kp * (pos[0] - rf(C.ref_pos[0])) + kv * (vel[0] - rf(C.ref_vel[0])) + rf(0.0f);
+    acc[1] = kp * (pos[1] - rf(C.ref_pos[1])) + kv * (vel[1] - rf(C.ref_vel[1])) + g;
+    const rf att = rf(atan2_pinned(acc[1].v, acc[0].v)) - rf(1.57079632679489661923f);
+    out[1] = ((rf(-1.0f) / tau) * (th - att)).v;
+    out[0] = (rf(C.mass) * norm<2>(acc)).v;
+  } else {
+    const rf tau(0.3f);
+    const rf pos[3] = {s[0], s[1], s[2]}, q[4] = {s[3], s[4], s[5], s[6]}, vel[3] = {s[7], s[8], s[9]};
+    rf acc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      acc[i] = kp * (pos[i] - rf(C.ref_pos[i])) + kv * (vel[i] - rf(C.ref_vel[i])) - (i == 2 ? -g : rf(0.0f));
+    const rf na = norm<3>(acc);
+    rf zb[3] = {acc[0] / na, acc[1] / na, acc[2] / na};
+    rf xb[3] = {zb[2], rf(0.0f) * zb[0], -zb[0]};                  // (0,1,0) x zb
+    const rf nx = norm<3>(xb);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) xb[i] = xb[i] / nx;
+    const rf yb[3] = {zb[1] * xb[2] - zb[2] * xb[1], zb[2] * xb[0] - zb[0] * xb[2], zb[0] * xb[1] - zb[1] * xb[0]};
+    const rf nz = norm<3>(zb);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) zb[i] = zb[i] / nz;
+    const rf m[3][3] = {{xb[0], xb[1], xb[2]}, {yb[0], yb[1], yb[2]}, {zb[0], zb[1], zb[2]}};
+    rf qd[4];
+    quat_from_rows(m, qd);
+    // error quaternion = conj(q) * qd with the RAW state quaternion (no normalisation, as the reference)
+    const rf w0 = q[0], x0 = -q[1], y0 = -q[2], z0 = -q[3];
+    const rf ew = w0 * qd[0] - x0 * qd[1] - y0 * qd[2] - z0 * qd[3];
+    const rf ex = x0 * qd[0] + w0 * qd[1] - z0 * qd[2] + y0 * qd[3];
+    const rf ey = y0 * qd[0] + z0 * qd[1] + w0 * qd[2] - x0 * qd[3];
+    const rf ez = z0 * qd[0] - y0 * qd[1] + x0 * qd[2] + w0 * qd[3];
+    const rf sgn(ew.v > 0.0f ? 1.0f : (ew.v < 0.0f ? -1.0f : (ew.v == 0.0f ? 0.0f : ew.v)));   // np.sign (NaN stays NaN)
+    const rf gain = (rf(2.0f) / tau) * sgn;
+    // thrust = desired_acc . R(q^) e3
+    const rf om[3] = {0.0f, 0.0f, 0.0f};
+    rf e3[3], qdot[4];
+    attitude_3d(q, om, e3, qdot);
+    out[0] = (acc[0] * e3[0] + acc[1] * e3[1] + acc[2] * e3[2]).v;
+    out[1] = (gain * ex).v; out[2] = (gain * ey).v; out[3] = (gain * ez).v;
+  }
+}
+
 // done / reward block shared by the four envs (quadrotor3d.py:106-122).  Strict '>' so that a
 // NaN norm is "not done", as in the reference; `ever_done` is steps_beyond_done is not None.
 RMV_HD bool is_done(const DevParams& P, float pos_sq, float vel_sq) {

@@ -10,10 +10,10 @@
 // tiled state buffer, written back in place; the next step reads what this one wrote (L2 at N = 2^20, HBM at N = 2^23:
 // the same 4(2S+A+1)+1 bytes per env-step as k_step) — but no warp ever waits for another one:
 //   * no grid-wide barrier between steps (one launch per T steps);
-//   * no CTA barrier either: a warp appends its finished envs to its OWN list in shared memory (ballot + prefix
-//     popcount, no atomics) and re-draws them itself once per step, one (env, Philox block) pair per lane — the Philox
-//     code then runs once per warp and step (for k = 4 units: in 81 % of the warp-steps, with 5 of 32 lanes busy on
-//     average) instead of once per unit that holds a finished env;
+//   * no CTA barrier per tile either: a warp appends its finished envs to its OWN list in shared memory (ballot + prefix
+//     popcount, no atomics); once per STEP the CTA meets at a barrier and re-draws everything its warps collected, one
+//     (env, Philox block) pair per thread — the Philox code then runs in one warp per CTA and step (k = 4 units per warp:
+//     512 env-steps, 6.6 finished envs, 20 busy lanes) instead of in every warp that saw a finish;
 //   * the grid is sized so that every warp owns the same number of units (k = ceil(units / resident warps), warps =
 //     ceil(units / k) rounded to whole CTAs of 4) and all of them are co-resident: at N = 2^20 that is 8192 warps x 4
 //     units = 2048 CTAs on 2368 slots.  Unit u of warp w is w + j * warps: the warp's pointers advance by CONSTANT
@@ -27,8 +27,10 @@
 namespace rmv {
 
 struct StreamShape {
-  uint32_t units_per_warp;   // k (informational)
+  uint32_t units_per_warp;   // k
   uint32_t warps;            // warps that own work, a multiple of 4; warp w owns units w, w + warps, ...
+  uint32_t limit;            // envs covered by existing units: n rounded up to 32
+  uint32_t env_stride;       // 32 * warps: envs between two units of one warp
 };
 
 constexpr int kStreamWarps = 4;       // warps per CTA at most (the launch may use fewer: a CTA is only a scheduling unit)
@@ -41,16 +43,15 @@ constexpr int stream_min_ctas(int kind, bool track) {
   return track ? 12 : 16;
 }
 
-// re-draw the `pending` finished envs of this warp's list: pair i = (entry i / NB, Philox block i % NB), one per lane
-template <int KIND>
-__device__ __forceinline__ void stream_flush(const StepArgs& a, const uint2* list, uint32_t pending, uint32_t lane) {
+// re-draw `pairs / NB` finished envs: pair i = (entry i / NB, Philox block i % NB), pairs idx0, idx0 + stride, ...
+// `item_of(slot)` returns (env index inside the launch, new reset count) of list entry `slot`.
+template <int KIND, typename ItemOf>
+__device__ __forceinline__ void stream_redraw(const StepArgs& a, uint32_t pairs, uint32_t idx0, uint32_t stride, ItemOf item_of) {
   constexpr int S = Dims<KIND>::S;
   constexpr int NB = (S + 3) / 4;
-  __syncwarp();                                    // the list entries written by other lanes are visible
-  const uint32_t pairs = pending * NB;
-  for (uint32_t i = lane; i < pairs; i += 32u) {
+  for (uint32_t i = idx0; i < pairs; i += stride) {
     const uint32_t slot = i / NB, b = i - slot * NB;
-    const uint2 item = list[slot];                 // (env index inside the launch, new reset count)
+    const uint2 item = item_of(slot);
     const uint32_t er = item.x;
     const uint64_t id = (uint64_t)a.env_id_offset + er;
     uint32_t w4[4];
@@ -60,105 +61,130 @@ __device__ __forceinline__ void stream_flush(const StepArgs& a, const uint2* lis
     for (int l = 0; l < 4; ++l)
       if (S % 4 == 0 || 4 * b + l < S) row[l * kTile] = uniform_pm1(w4[l]);
   }
-  __syncwarp();                                    // the owner lanes read these rows at the next step
 }
 
-template <int KIND, bool TRACK, bool PREF>
-__global__ void __launch_bounds__(128, stream_min_ctas(KIND, TRACK))
+template <int KIND, bool TRACK, bool PREF, bool CTRL = false>
+__global__ void __launch_bounds__(128, CTRL ? 8 : stream_min_ctas(KIND, TRACK))
 k_step_stream(const StepArgs a, const StreamShape shape) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
+  constexpr int NB = (S + 3) / 4;
   __shared__ uint2 redraw_list[kStreamWarps][kStreamList];
+  __shared__ uint32_t redraw_count[kStreamWarps];
 
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t gw = (blockIdx.x * blockDim.x + tid) >> 5;
   const uint32_t n = (uint32_t)a.n;
-  const uint32_t units = (n + 31u) >> 5;
-  const uint32_t W = shape.warps;
+  const uint32_t limit = shape.limit;                                   // envs covered by existing units
+  const uint32_t W = shape.warps, K = shape.units_per_warp;
   const uint32_t T = (uint32_t)a.n_steps;
+  if (tid < kStreamWarps) redraw_count[tid] = 0u;
   asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous launch on the stream has completed and flushed
-  // units this warp owns: gw, gw + W, ..., K of them (the last one does not exist for some warps).  Both loops below have
-  // UNIFORM trip counts (kernel parameters): with a per-warp trip count the compiler treats the loop as divergent and
-  // re-materialises the memory descriptors of every load and store from vector registers (2 R2UR per access).
-  const uint32_t K = shape.units_per_warp;
-  if (gw >= W || gw >= units) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
+  __syncthreads();
 
-  uint2* const list = redraw_list[(threadIdx.x >> 5) & (kStreamWarps - 1)];
-  const uint32_t e_first = (gw << 5) + lane;
-  const uint32_t de = W << 5;                                            // envs between two units of this warp
-  const size_t ds = (size_t)(W >> 2) * (S * kTile);                      // the same distance in the tiled state (W % 4 == 0)
+  // Units this warp owns: gw, gw + W, ..., K of them (the last one does not exist for some warps; warps gw >= W own none).
+  // Control flow is kept CTA-uniform — loops with kernel-parameter trip counts, no early exit, the per-unit work under one
+  // predicate — so that everything that is uniform (step pointers, counters, memory descriptors) lives in the uniform
+  // register file; a per-warp trip count or a break makes the compiler re-materialise it per access from vector registers.
+  uint2* const list = redraw_list[warp & (kStreamWarps - 1)];
+  const uint32_t e_first = (gw < W) ? (gw << 5) + lane : limit;          // warps without work start past the end
+  const uint32_t de = shape.env_stride;                                  // envs between two units of this warp
+  const size_t ds = (size_t)(de >> 7) * (S * kTile);                     // the same distance in the tiled state (W % 4 == 0)
   float* const sp_first = a.state + ((size_t)(e_first >> 7) * (S * kTile) + (e_first & (kTile - 1)));
 
-  for (uint32_t t = 0; t < T; ++t) {
+  // per-step base pointers: uniform, advanced by a constant per step (the host always passes reward / done buffers:
+  // a caller's NULL is parked in scratch with out_ld = 0)
+  const float* act_t = a.act;
+  float* rew_t = a.reward;
+  unsigned char* done_t = reinterpret_cast<unsigned char*>(a.done);
+  uint32_t now = a.step_index;
+  for (uint32_t t = 0; t < T; ++t, act_t += a.act_step_stride, rew_t += a.out_ld, done_t += a.out_ld) {
     if (t + 1u == T) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next launch may become resident as we drain
-    const float* const act_t = a.act + (size_t)t * a.act_step_stride;
-    // uniform per step (never dereferenced when the base is NULL): candidates for the uniform register file
-    float* const rew_t = a.reward + (size_t)t * a.out_ld;
-    unsigned char* const done_t = reinterpret_cast<unsigned char*>(a.done) + (size_t)t * a.out_ld;
-    const uint32_t now = a.step_index + t + 1u;
+    ++now;
     float* sp = sp_first;
     uint32_t e = e_first, pending = 0u;
     for (uint32_t j = 0; j < K; ++j, sp += ds, e += de) {
-      if (e >= (units << 5)) break;               // this warp's last unit does not exist (only ever at j = K - 1)
-      const bool active = e < n;
-      float s[S], act[A];
-      uint32_t word = 0u, ep_started = 0u;
-      float ep_ret = 0.0f;
+      if (e < limit) {                             // warp-uniform: this unit exists
+        const bool active = e < n;
+        float s[S], act[A];
+        uint32_t word = 0u, ep_started = 0u;
+        float ep_ret = 0.0f;
 #pragma unroll
-      for (int c = 0; c < S; ++c) s[c] = sp[c * kTile];                 // tiles (and the per-env arrays) are padded: in bounds
-      if (PREF) word = a.episode[e];
-      if (TRACK) { ep_ret = a.ep_return[e]; ep_started = a.ep_start[e]; }
-      if (a.act_soa) {
+        for (int c = 0; c < S; ++c) s[c] = sp[c * kTile];               // tiles (and the per-env arrays) are padded: in bounds
+        if (PREF) word = a.episode[e];
+        if (TRACK) { ep_ret = a.ep_return[e]; ep_started = a.ep_start[e]; }
+        if constexpr (CTRL) {                        // closed loop: the reference's controller on the state just loaded
+          control_law<KIND>(a.C, s, act);
+          if (a.act_out && active) store_action_row<A>(a.act_out + (size_t)t * a.act_step_stride + (size_t)(e * (uint32_t)A), act);
+        } else if (a.act_soa) {
 #pragma unroll
-        for (int c = 0; c < A; ++c) act[c] = active ? __ldcs(act_t + (size_t)c * a.act_ld + e) : 0.0f;
-      } else if (active) {
-        load_contig_stream<A>(act_t + (size_t)(e * (uint32_t)A), act);  // n <= 2^30: e * A fits 32 bits
-      } else {
+          for (int c = 0; c < A; ++c) act[c] = active ? __ldcs(act_t + (size_t)c * a.act_ld + e) : 0.0f;
+        } else if (active) {
+          load_contig_stream<A>(act_t + (size_t)(e * (uint32_t)A), act);  // n <= 2^30: e * A fits 32 bits
+        } else {
 #pragma unroll
-        for (int c = 0; c < A; ++c) act[c] = 0.0f;
-      }
+          for (int c = 0; c < A; ++c) act[c] = 0.0f;
+        }
 
-      float pos_sq, vel_sq, n_rew;
-      EnvStep<KIND>::run(a.P, s, act, pos_sq, vel_sq, n_rew);
-      const bool done = is_done(a.P, pos_sq, vel_sq) && active;
-      float rew = -n_rew;
-      uint32_t count = 0u;
-      bool redraw = false;
-      if (done) {
-        // rare lane: the ever-done flag decides the terminal reward (quadrotor3d.py:112-122)
-        const uint32_t w = PREF ? word : a.episode[e];
-        rew = reward_of(a.P, true, (w & kEverDone) != 0u, n_rew);
-        count = (w & ~kEverDone) + (a.auto_reset ? 1u : 0u);
-        a.episode[e] = count | kEverDone;
-        redraw = a.auto_reset != 0;
-        if (TRACK) {
-          const float total = ep_ret + rew;
-          a.last_return[e] = total;
-          a.last_length[e] = now - ep_started;
-          atomicAdd(a.cum_return + e, (double)total);
-          atomicAdd(a.cum_length + e, (unsigned long long)(now - ep_started));
-          atomicAdd(a.fin_count + e, 1u);
-          a.ep_start[e] = now;
-          ep_ret = -rew;                          // becomes 0 after the "+ rew" below
+        float pos_sq, vel_sq, n_rew;
+        EnvStep<KIND>::run(a.P, s, act, pos_sq, vel_sq, n_rew);
+        const bool done = is_done(a.P, pos_sq, vel_sq) && active;
+        const bool redraw = done && a.auto_reset != 0;
+        float rew = -n_rew;
+        uint32_t count = 0u;
+        if (done) {
+          // rare lane: the ever-done flag decides the terminal reward (quadrotor3d.py:112-122)
+          const uint32_t w = PREF ? word : a.episode[e];
+          rew = reward_of(a.P, true, (w & kEverDone) != 0u, n_rew);
+          count = (w & ~kEverDone) + (a.auto_reset ? 1u : 0u);
+          a.episode[e] = count | kEverDone;
+          if (TRACK) {
+            const float total = ep_ret + rew;
+            a.last_return[e] = total;
+            a.last_length[e] = now - ep_started;
+            atomicAdd(a.cum_return + e, (double)total);
+            atomicAdd(a.cum_length + e, (unsigned long long)(now - ep_started));
+            atomicAdd(a.fin_count + e, 1u);
+            a.ep_start[e] = now;
+            ep_ret = -rew;                          // becomes 0 after the "+ rew" below
+          }
         }
-      }
-      if (active) {
-        if (a.reward) __stcs(rew_t + e, scaled_reward(a.P, rew));
-        if (a.done) __stcs(done_t + e, (unsigned char)(done ? 1 : 0));
-        if (TRACK) a.ep_return[e] = ep_ret + rew;
-        if (!redraw) {
+        if (active) {
+          __stcs(rew_t + e, scaled_reward(a.P, rew));
+          __stcs(done_t + e, (unsigned char)(done ? 1 : 0));
+          if (TRACK) a.ep_return[e] = ep_ret + rew;
+          if (!redraw) {
 #pragma unroll
-          for (int c = 0; c < S; ++c) sp[c * kTile] = s[c];
+            for (int c = 0; c < S; ++c) sp[c * kTile] = s[c];
+          }
         }
-      }
-      // finished envs go to the warp's list; they are re-drawn once per step (or when the list runs full)
-      const uint32_t mask = __ballot_sync(0xffffffffu, redraw);
-      if (mask != 0u) {                            // warp-uniform
-        if (redraw) list[pending + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = make_uint2(e, count);
-        pending += (uint32_t)__popc(mask);
-        if (pending > 32u) { stream_flush<KIND>(a, list, pending, lane); pending = 0u; }
+        // finished envs go to the warp's list (ballot + prefix popcount: no atomics)
+        const uint32_t mask = __ballot_sync(0xffffffffu, redraw);
+        if (mask != 0u) {                            // warp-uniform
+          if (redraw) list[pending + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = make_uint2(e, count);
+          pending += (uint32_t)__popc(mask);
+          if (pending > 32u) {                       // a mass finish: the warp empties its own list right away
+            __syncwarp();
+            stream_redraw<KIND>(a, pending * NB, lane, 32u, [&](uint32_t slot) { return list[slot]; });
+            __syncwarp();
+            pending = 0u;
+          }
+        }
       }
     }
-    if (pending != 0u) stream_flush<KIND>(a, list, pending, lane);
+    // once per step the CTA re-draws what its warps collected: pair i goes to thread i, so the Philox code runs in one
+    // warp per CTA and step (20 of its lanes busy for quadrotor3d at k = 4) instead of once per warp that saw a finish
+    if (lane == 0u) redraw_count[warp & (kStreamWarps - 1)] = pending;
+    __syncthreads();
+    const uint32_t c0 = redraw_count[0], c1 = redraw_count[1], c2 = redraw_count[2], c3 = redraw_count[3];
+    const uint32_t total = c0 + c1 + c2 + c3;
+    if (total != 0u) {                               // CTA-uniform
+      stream_redraw<KIND>(a, total * NB, tid, blockDim.x, [&](uint32_t slot) {
+        uint32_t w = 0u;
+        if (slot >= c0) { slot -= c0; w = 1u; if (slot >= c1) { slot -= c1; w = 2u; if (slot >= c2) { slot -= c2; w = 3u; } } }
+        return redraw_list[w][slot];
+      });
+      __syncthreads();                               // owners read these rows at the next step; the lists are free again
+    }
   }
 }
 

@@ -76,6 +76,8 @@ SIGNATURES = {
     "rmv_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rmv_reset_host": (_i, [_vp, _vp, _vp]),
     "rmv_control": (_i, [_vp, _pf, _pf, _vp, _i, _i64, _vp]),
+    "rmv_control_step": (_i, [_vp, _pf, _pf, _vp, _vp, _vp, _vp, _i, _vp]),
+    "rmv_control_step_many": (_i, [_vp, _i, _pf, _pf, _vp, _vp, _vp, _i64, _vp]),
     "rmv_control_host": (_i, [_vp, _pf, _pf, _vp, _vp]),
     "rmv_fill_uniform_actions": (_i, [_vp, _i64, _i, _i, _i64, _f, _f, _u64, _i64, _u32, _i, _vp]),
     "rmv_episode_stats": (_i, [_vp, ctypes.POINTER(ctypes.c_double), _vp]),

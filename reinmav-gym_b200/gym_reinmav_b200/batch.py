@@ -259,6 +259,27 @@ class QuadBatch:
                                 _stream(stream, self.device)))
         self.launches += 1
 
+    def control_step(self, reward, done, obs=None, actions_out=None, ref_pos=None, ref_vel=None, auto_reset=True, stream=None):
+        """``action = control(); step(action)`` as ONE kernel (no action buffer is read); ``actions_out`` (optional
+        [N, A] device buffer) receives the controller's actions."""
+        d = self.device
+        _need(reward, self.num_envs, "reward"); _need(done, self.num_envs, "done")
+        _need(obs, self.num_envs * self.state_dim, "obs"); _need(actions_out, self.num_envs * self.action_dim, "actions_out")
+        check(lib().rmv_control_step(self._h, self._ref(ref_pos), self._ref(ref_vel), _ptr(actions_out, "float32", d, "actions_out"),
+                                     _ptr(reward, "float32", d, "reward"), _ptr(done, "uint8", d, "done"),
+                                     _ptr(obs, "float32", d, "obs"), 1 if auto_reset else 0, _stream(stream, d)))
+        self.launches += 1
+
+    def control_step_many(self, n_steps, reward=None, done=None, out_ld=0, actions_out=None, ref_pos=None, ref_vel=None, stream=None):
+        """``n_steps`` closed-loop steps with reset-on-done in one launch of the step stream."""
+        d, n = self.device, self.num_envs
+        _need(reward, (int(n_steps) - 1) * int(out_ld or n) + n, "reward"); _need(done, (int(n_steps) - 1) * int(out_ld or n) + n, "done")
+        _need(actions_out, int(n_steps) * n * self.action_dim, "actions_out")
+        check(lib().rmv_control_step_many(self._h, int(n_steps), self._ref(ref_pos), self._ref(ref_vel),
+                                          _ptr(actions_out, "float32", d, "actions_out"), _ptr(reward, "float32", d, "reward"),
+                                          _ptr(done, "uint8", d, "done"), int(out_ld or n), _stream(stream, d)))
+        self.launches += 1 if self.state_layout == "tiles" else int(n_steps)
+
     def control_host(self, actions, ref_pos=None, ref_vel=None, stream=None):
         check(lib().rmv_control_host(self._h, self._ref(ref_pos), self._ref(ref_vel),
                                      _ptr(actions, "float32", HOST, "actions"), _stream(stream, self.device)))

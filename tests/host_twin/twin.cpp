@@ -85,3 +85,34 @@ extern "C" void twin_philox_ks(unsigned long long seed, const unsigned* ctr, uns
 extern "C" void twin_uniform_pm1(long n, const unsigned* bits, float* fast, float* plain) {
   for (long i = 0; i < n; ++i) { fast[i] = uniform_pm1(bits[i]); plain[i] = uniform_from_bits(bits[i], -1.0f, 2.0f); }
 }
+
+// pinned atan2 and the geometric controllers (control_law, rmv_math.cuh)
+extern "C" void twin_atan2(long n, const float* y, const float* x, float* out) {
+  for (long i = 0; i < n; ++i) out[i] = atan2_pinned(y[i], x[i]);
+}
+
+template <int KIND>
+static void run_control(const CtrlParams& C, long n, const float* s_in, float* a_out) {
+  constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
+  for (long e = 0; e < n; ++e) {
+    float s[S], a[A];
+    memcpy(s, s_in + e * S, sizeof(s));
+    control_law<KIND>(C, s, a);
+    memcpy(a_out + e * A, a, sizeof(a));
+  }
+}
+
+// ctrl = {ref_pos[3], ref_vel[3], mass, gravity}
+extern "C" int twin_control(int kind, const float* ctrl, long n, const float* s_in, float* a_out) {
+  CtrlParams C;
+  for (int i = 0; i < 3; ++i) { C.ref_pos[i] = ctrl[i]; C.ref_vel[i] = ctrl[3 + i]; }
+  C.mass = ctrl[6]; C.gravity = ctrl[7];
+  switch (kind) {
+    case QUAD2D: run_control<QUAD2D>(C, n, s_in, a_out); break;
+    case QUAD2D_SLUNG: run_control<QUAD2D_SLUNG>(C, n, s_in, a_out); break;
+    case QUAD3D: run_control<QUAD3D>(C, n, s_in, a_out); break;
+    case QUAD3D_SLUNG: run_control<QUAD3D_SLUNG>(C, n, s_in, a_out); break;
+    default: return -1;
+  }
+  return 0;
+}

@@ -120,4 +120,7 @@ def test_batch_control_matches_reference_controller(env_id, repair):
     o32 = BatchOracle(env_id, T, dtype=np.float32, repair=repair)
     o32.state = states.T.astype(np.float32)
     a32 = o32.control()
-    assert (np.abs(a32 - g["ctrl_a"]) <= 3e-5 * np.maximum(1.0, np.abs(g["ctrl_a"]))).all()
+    # float32 model (pinned atan2, the kernel's bit model): 1e-5; quadrotor2d-v0 1.5e-5 — its own loop flies the
+    # vehicle out of bounds, the states are large and rounding THEM to float32 is what the gain of 10 sees
+    tol = 1.5e-5 if env_id == "quadrotor2d-v0" else 1e-5
+    assert (np.abs(a32 - g["ctrl_a"]) <= tol * np.maximum(1.0, np.abs(g["ctrl_a"]))).all()
