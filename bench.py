@@ -4,16 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]          (N > 1: launched by torchrun)
     python bench.py --impl reference ...                          (the reference CPU arm)
 
-A "step" is ONE pass of the hot path (one fused step kernel: dynamics + reward + done +
-reset-on-done) over one batch of N_ENVS = 2^20 quadrotor3d-v0 envs per GPU with random-policy
-actions (BASELINE.json metric / configs[1] scaled to the metric's N = 2^20).
+A "step" is ONE pass of the hot path (the fused step: dynamics + reward + done + reset-on-done, state read from and
+written back to the state buffer) over one batch of N_ENVS = 2^20 quadrotor3d-v0 envs per GPU with random-policy
+actions (BASELINE.json metric / configs[1] scaled to the metric's N = 2^20).  K steps are issued with ONE call of
+rmv_step_many(RMV_MANY_STREAM): the persistent step-stream kernel (csrc/rmv_stream.cuh).
 
 * value     whole-job env-steps/s, inputs resident in HBM when the timed region starts
-            (state in the handle, actions in a 64-step ring written by the Philox fill kernel).
+            (state in the handle, actions in a 64-step ring written by the Philox fill kernel); the K-step block is
+            repeated until the timed region is >= 60 ms.
 * e2e       the same metric through the C-ABI call with HOST buffers (rmv_step_host: pinned
             host actions -> H2D -> kernel -> D2H of obs/reward/done every step).
 * roofline  algorithmic bytes (101 B per env-step) / CUDA-event time per launch,
-            against MEASURED_PEAKS.json hbm_gbs.
+            against MEASURED_PEAKS.json hbm_gbs; the dict also carries the points that qualify the L2-assisted headline:
+            hbm_bound (N = 2^23), cold_l2, the N = 65536 configs, and the same work as one launch per step.
 * cpu_baseline  oracle/scalar.py (one Python object per env, the reference's execution model) on
             all host cores, a bounded sample.
 """
@@ -242,6 +245,7 @@ def run_gpu_arm(args):
         marks[i + 1].record()
     barrier()
     launches = batch.launches - launches0
+    headline_kernel = batch.last_kernel
     region_ms = max_over_ranks(marks[0].elapsed_time(marks[blocks]))
     best_block_ms = max_over_ranks(min(marks[i].elapsed_time(marks[i + 1]) for i in range(blocks)))
     ms_per_step = region_ms / (blocks * args.steps)
@@ -344,7 +348,8 @@ def run_gpu_arm(args):
                 "traffic": (load_traffic("k_step_stream_quadrotor3d_n2pow20") or {}).get("dram_bytes_per_step"),
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, divided by "
                                 "the steps of the captured launch; a CITATION of profiles/traffic.json, not measured in this run",
-                "kernel": "rmv::k_step_stream<QUAD3D> (persistent; one launch = K steps of N envs)",
+                "kernel": "rmv::%s<QUAD3D> (%s)" % (headline_kernel, "persistent; one launch = K steps of N envs"
+                                                     if "stream" in headline_kernel else "one launch per step"),
                 "steps_per_launch": min(args.steps, ring),
                 "algorithmic_bytes_per_step": ALG_BYTES * n,
                 "algorithmic_bytes_per_launch": ALG_BYTES * n * min(args.steps, ring),
@@ -443,17 +448,18 @@ def measure_roofline_points(torch, rmv, args, local):
             rmv.fill_uniform_actions(acts[t], n, 4, lo, hi, SEED, step_index=t, device=local)
         return b, acts, torch.empty((ring, n), dtype=torch.float32, device=dev), torch.empty((ring, n), dtype=torch.uint8, device=dev)
 
-    def entry(env_id, n, us, mode):
+    def entry(env_id, n, us, mode, kernel=None):
         gbs = n * bytes_of[env_id] / (us * 1e-6) / 1e9
         return {"env_id": env_id, "n_envs": n, "us_per_step": us, "env_steps_per_s": n / (us * 1e-6), "achieved": gbs,
-                "frac": gbs / peak, "mode": mode}
+                "frac": gbs / peak, "mode": mode, "kernel": kernel}
 
     # HBM-bound: 847 MB per step
     n = 1 << 23
     b, acts, rew, done = make(ENV_ID, n, 8)
-    out["hbm_bound"] = entry(ENV_ID, n, _time_many(torch, b, acts, rew, done, n, 96, 0), "step stream, 8-step launches")
-    out["hbm_bound"]["launch_per_step_us"] = _time_many(torch, b, acts, rew, done, n, 96, 2)
-    out["hbm_bound"]["dram_bytes_per_step_ncu"] = (load_traffic("k_step_stream_quadrotor3d_n2pow23") or {}).get("dram_bytes_per_step")
+    us = _time_many(torch, b, acts, rew, done, n, 96, 0)
+    out["hbm_bound"] = entry(ENV_ID, n, us, "rmv_step_many(RMV_MANY_STREAM), 8-step calls: at this size the library issues one launch per "
+                             "step (rmv_stream_pays)", b.last_kernel)
+    out["hbm_bound"]["dram_bytes_per_step_ncu"] = (load_traffic("k_step_quadrotor3d_n2pow23") or {}).get("dram_bytes_per_step")
     b.close()
     del acts, rew, done
 
@@ -472,7 +478,8 @@ def measure_roofline_points(torch, rmv, args, local):
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(z) for a, z in evs)
     out["cold_l2"] = entry(ENV_ID, n, ts[len(ts) // 2] * 1e3,
-                           "ONE isolated k_step launch after an L2 flush, its own event pair (~5 us of the figure is the pair), median of 40")
+                           "ONE isolated k_step launch after an L2 flush, its own event pair (~5 us of the figure is the pair), median of 40",
+                           "k_step")
     b.close()
     del acts, rew, done, flush, sink
 
@@ -480,7 +487,7 @@ def measure_roofline_points(torch, rmv, args, local):
     for key, env_id in (("n65536_quadrotor3d", ENV_ID), ("n65536_quadrotor3d_slungload", "quadrotor3d-slungload-v0")):
         n = 1 << 16
         b, acts, rew, done = make(env_id, n, 64)
-        e = entry(env_id, n, _time_many(torch, b, acts, rew, done, n, 4096, 0), "step stream, 64-step launches")
+        e = entry(env_id, n, _time_many(torch, b, acts, rew, done, n, 4096, 0), "step stream, 64-step launches", "k_step_stream")
         e["launch_per_step_us"] = _time_many(torch, b, acts, rew, done, n, 2048, 2)
         e["rollout_in_registers_us"] = _time_many(torch, b, acts, rew, done, n, 4096, 1)
         out[key] = e
@@ -587,41 +594,66 @@ def measure_extras(torch, rmv, args, local):
                          "mode": "one launch per step; float64 substeps in registers (compute-bound, not HBM-bound)"}
     b.close()
 
-    # BASELINE config 4: quadrotor2d-v0, N = 2^20, PPO2 rollout shape — obs rows [N,5] out, actions [N,2]
-    # ~ N(0,1) in (baselines' initial diagonal Gaussian), T = 128 steps into [T, N, ...] device buffers.
-    # "travelling": the rollout buffer carries the state (rmv_step_rows: read obs[t], write obs[t+1]);
-    # "in_place": tiled state in the handle + a row copy per step (rmv_step with obs rows).  Also for quadrotor3d.
+    # BASELINE config 4: quadrotor2d-v0, N = 2^20, PPO2 rollout shape — obs [N,5] in HBM, actions [N,2] ~ N(0,1)
+    # (baselines' initial diagonal Gaussian), one VecEnv.step per policy step, Monitor on (the VecEnv default).  Also for
+    # quadrotor3d.  (a) QuadVecEnv.step_tensor: what a device-resident PPO loop calls; the 3D kinds keep their state as
+    # the observation matrix (state_layout='rows'), so the step updates the obs tensor in place.  (b) RolloutBuffer:
+    # step t reads obs[t] and writes obs[t+1] of a [T+1, N, S] buffer.
     import gym_reinmav_b200.rollout as rollout
     for env_id, key in (("quadrotor2d-v0", "ppo2_rollout_shape_quadrotor2d"), (ENV_ID, "ppo2_rollout_shape_quadrotor3d")):
         n, T = 1 << 20, 128
-        Sd = {"quadrotor2d-v0": 5, ENV_ID: 10}[env_id]
-        for travelling in (False, True):
-            venv = rmv.QuadVecEnv(env_id, n, device=local, seed=SEED, monitor=False)
-            buf = rollout.RolloutBuffer(venv, T, travelling=travelling)
-            buf.actions.normal_()
-            if env_id == ENV_ID:
-                buf.actions.mul_(2.5).add_(5.0)          # around the middle of quadrotor3d's [0, 10) action box
-            policy = lambda obs, _it=iter(range(10 ** 9)): buf.action_views[next(_it) % T]      # pre-drawn actions: env-side cost only
-            buf.collect(policy)
+        Sd, Ad = {"quadrotor2d-v0": (5, 2), ENV_ID: (10, 4)}[env_id]
+        venv = rmv.QuadVecEnv(env_id, n, device=local, seed=SEED, monitor=True)
+        actions = torch.empty((T, n, Ad), dtype=torch.float32, device=dev).normal_()
+        if env_id == ENV_ID:
+            actions.mul_(2.5).add_(5.0)                  # around the middle of quadrotor3d's [0, 10) action box
+        views = [actions[t] for t in range(T)]
+        venv.reset_tensor()
+        for t in range(T):
+            venv.step_tensor(views[t])
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for t in range(T):
+                venv.step_tensor(views[t])
+            e1.record()
             torch.cuda.synchronize()
-            best = 1e30
-            for _ in range(3):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); buf.collect(policy); e1.record()
-                torch.cuda.synchronize()
-                best = min(best, e0.elapsed_time(e1) / T)
-            sps = n / (best * 1e-3)
-            nbytes = bytes_of[env_id] + (0 if travelling else 4 * Sd)
-            out[key + ("_travelling_state" if travelling else "")] = {
-                "env_id": env_id, "n_envs": n, "n_steps": T, "us_per_step": best * 1e3, "env_steps_per_s": sps,
-                "bytes_per_env_step": nbytes, "algorithmic_GBps": sps * nbytes / 1e9,
-                "frac_of_hbm_peak": sps * nbytes / 1e9 / peak,
-                "mode": ("one launch per step from Python (ctypes); state read from obs[t], written to obs[t+1] of a [T+1,N,%d] buffer "
-                         "(rmv_step_rows)" if travelling else
-                         "one launch per step from Python (ctypes); tiled state in place + obs rows written into obs[t+1] of a "
-                         "[T+1,N,%d] buffer (rmv_step)") % Sd}
-            venv.close()
-            del buf
+            best = min(best, e0.elapsed_time(e1) / T)
+        sps = n / (best * 1e-3)
+        rows = venv.state_layout == "rows"
+        nbytes = bytes_of[env_id] + (0 if rows else 4 * Sd) + 8          # + episode tracking (Monitor)
+        out[key] = {"env_id": env_id, "n_envs": n, "n_steps": T, "us_per_step": best * 1e3, "env_steps_per_s": sps,
+                    "bytes_per_env_step": nbytes, "algorithmic_GBps": sps * nbytes / 1e9, "frac_of_hbm_peak": sps * nbytes / 1e9 / peak,
+                    "kernel": venv.batch.last_kernel,
+                    "mode": "QuadVecEnv.step_tensor (one C-ABI call per step from Python), monitor=True, state_layout=%s" % venv.state_layout}
+        stats = venv.episode_stats()
+        out[key]["episodes_finished"] = stats["episodes"]
+        venv.close()
+        del venv
+        venv = rmv.QuadVecEnv(env_id, n, device=local, seed=SEED, monitor=True)
+        buf = rollout.RolloutBuffer(venv, T)
+        buf.actions.copy_(actions)
+        policy = lambda obs, _it=iter(range(10 ** 9)): buf.action_views[next(_it) % T]      # pre-drawn actions: env-side cost only
+        buf.collect(policy)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); buf.collect(policy); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / T)
+        sps = n / (best * 1e-3)
+        nbytes = bytes_of[env_id] + (0 if buf.travelling else 4 * Sd) + 8
+        out[key + "_rollout_buffer"] = {
+            "env_id": env_id, "n_envs": n, "n_steps": T, "us_per_step": best * 1e3, "env_steps_per_s": sps,
+            "bytes_per_env_step": nbytes, "algorithmic_GBps": sps * nbytes / 1e9, "frac_of_hbm_peak": sps * nbytes / 1e9 / peak,
+            "mode": "RolloutBuffer.collect: [T+1,N,%d] obs buffer, %s, monitor=True"
+                    % (Sd, "state travels through the buffer (rmv_step_rows: read obs[t], write obs[t+1])" if buf.travelling
+                       else "tiled state in place + obs rows written into obs[t+1] (rmv_step)")}
+        venv.close()
+        del buf, venv, actions, views
     return out
 
 

@@ -136,7 +136,8 @@ RMV_API int rmv_set_seed(rmv_env* env, uint64_t seed);
 RMV_API int rmv_get_time(const rmv_env* env, double* t);
 RMV_API int rmv_set_time(rmv_env* env, double t);
 
-/* Launch tuning (benchmarks / sweeps): vec = envs per thread (0 = auto, 1, 2, 4),
+/* Launch tuning (benchmarks / sweeps): vec = envs per thread (0 = auto, 1, 2, 4; for the step stream of quadrotor3d
+ * vec = 2 selects the two-envs-per-thread kernel on the packed float32 pipe, vec = 1 the one-env kernel),
  * block = threads per CTA of the one-env-per-thread step kernel (0 = auto, 128, 256, 512; vec > 1 always uses 128). */
 RMV_API int rmv_set_tuning(rmv_env* env, int vec, int block);
 /* the launch shape "auto" resolves to for a batch of n_envs of `kind` (device-free query): threads per CTA and whether the
@@ -220,7 +221,8 @@ RMV_API int rmv_step_rows(rmv_env* env, const float* rows_in_dev, const float* a
 /* T consecutive steps with auto-reset from a pre-generated action block (random-policy or
  * replayed rollouts).  act_dev is [T][A][act_ld] (SOA) or [T][n][A] (AOS); reward_dev / done_dev
  * are [T][out_ld] or NULL.  `mode`:
- *   RMV_MANY_STREAM   (0): the state makes the round trip through memory EVERY step (read from the state buffer,
+ *   RMV_MANY_STREAM   (0): (the default; falls back to RMV_MANY_LAUNCHES where that is faster: batches whose step
+ *               streams several hundred MB through HBM, rmv_stream_pays) the state makes the round trip through memory EVERY step (read from the state buffer,
  *               written back in place: 4(2S+A+1)+1 bytes per env-step, the traffic of T calls of rmv_step), but
  *               the T steps are ONE launch of the persistent step-stream kernel: every warp owns a fixed set of
  *               32-env units and walks (step, unit) in order, so a step depends on nothing but its own envs'
@@ -233,6 +235,17 @@ RMV_API int rmv_step_rows(rmv_env* env, const float* rows_in_dev, const float* a
 enum { RMV_MANY_STREAM = 0, RMV_MANY_ROLLOUT = 1, RMV_MANY_LAUNCHES = 2 };
 RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act_dev, int act_layout, int64_t act_ld,
                   float* reward_dev, uint8_t* done_dev, int64_t out_ld, int mode, void* stream);
+/* which kernel family the most recent step call of this handle launched (tests and benchmarks name the kernel they
+ * measured; -1 before the first step) */
+enum { RMV_VARIANT_STEP = 0,         /* k_step: one launch per step, tiled state                                  */
+       RMV_VARIANT_ROWS = 1,         /* k_step_rows: row-major state                                              */
+       RMV_VARIANT_TMA = 2,          /* k_step_tma: TMA bulk copies + mbarrier pipeline                           */
+       RMV_VARIANT_ROLLOUT = 3,      /* k_rollout: state in registers for T steps                                 */
+       RMV_VARIANT_STREAM = 4,       /* k_step_stream: persistent step stream, one env per thread                 */
+       RMV_VARIANT_STREAM_PAIR = 5   /* k_step_stream_pair: step stream, two envs per thread on the packed f32 pipe */ };
+RMV_API int rmv_last_variant(const rmv_env* env, int* variant);
+/* 1 if rmv_step_many(RMV_MANY_STREAM) runs the stream kernel for n_envs of `kind`, 0 if it issues launches (device-free) */
+RMV_API int rmv_stream_pays(int kind, int64_t n_envs);
 /* Tuning of the step-stream kernel (sweeps): warps_per_sm caps the resident warps per SM (0 = as many as fit);
  * block = threads per CTA (0 auto, 32, 64, 128 — a CTA is only a scheduling unit of this kernel).  Results are identical. */
 RMV_API int rmv_set_stream(rmv_env* env, int warps_per_sm, int block);

@@ -71,6 +71,7 @@ struct rmv_env {
   int64_t n = 0, ld = 0, env_id_offset = 0;
   uint64_t seed = 0;
   uint32_t flags = 0, step_index = 0;
+  int last_variant = -1;   // RMV_VARIANT_* of the most recent step launch (rmv_last_variant)
   bool rows = false;       // RMV_STATE_ROWS: state is [n_pad][S] rows, stepped in place by the row-state kernel
   double sim_time = 0.0;   // reinmav-v0: self.t (reinmav_env.py:73,119)
   rmv_params params{};
@@ -129,6 +130,7 @@ struct rmv_env {
 
 static int g_use_graph = (getenv("RMV_NO_GRAPH") == nullptr) ? 1 : 0;   // developer switch
 static int g_use_stream = (getenv("RMV_NO_STREAM") == nullptr) ? 1 : 0; // developer switch: rmv_step_many(mode 0) falls back to launches
+static int g_force_stream = (getenv("RMV_FORCE_STREAM") != nullptr) ? 1 : 0; // developer switch: the stream at every size (sweeps)
 static int g_ctas_cap = getenv("RMV_CTAS_PER_SM") ? atoi(getenv("RMV_CTAS_PER_SM")) : 0;
 static int enable_l2_window(rmv_env* e);
 static void disable_l2_window(rmv_env* e);
@@ -305,6 +307,12 @@ extern "C" RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
   RMV_REQUIRE(chunks >= 0 && chunks <= 1024, "chunks must be in [0, 1024] (0 = auto)");
   env->host_chunks = chunks;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_last_variant(const rmv_env* env, int* variant) {
+  RMV_REQUIRE(env != nullptr && variant != nullptr, "NULL argument");
+  *variant = env->last_variant;
   return RMV_OK;
 }
 
@@ -576,6 +584,21 @@ static bool default_prefetch(int kind, int64_t n) {
   return working_set_is_big(kind, n);
 }
 
+// Where the persistent step stream beats one launch per step (profiles/r2_sweep_stream_vs_launches.txt).  The stream
+// wins wherever launch boundaries matter — everything that is L2-resident or a little larger — and loses once a step
+// streams several hundred MB through HBM: its warps drift apart (that is the point of it), so DRAM sees thousands of
+// independent 5 KB accesses instead of one grid sweeping the array in address order (0.68 vs 1.0 of the copy bandwidth
+// at N = 2^23).  Above the threshold RMV_MANY_STREAM issues launches.
+static bool stream_pays(int kind, int64_t n) {
+  static const int64_t bytes[4] = {53, 85, 101, 149};
+  static const int64_t limit_mb[4] = {128, 48, 256, 256};
+  return kind >= 0 && kind < 4 && n * bytes[kind] <= (limit_mb[kind] << 20);
+}
+
+extern "C" RMV_API int rmv_stream_pays(int kind, int64_t n_envs) {
+  return (g_use_stream && stream_pays(kind, n_envs)) ? 1 : 0;
+}
+
 extern "C" RMV_API int rmv_launch_shape(int kind, int64_t n_envs, int* block, int* prefetch) {
   RMV_REQUIRE(kind >= 0 && kind < RMV_REINMAV, "kind %d has no one-env-per-thread step kernel", kind);
   RMV_REQUIRE(n_envs > 0, "n_envs must be positive");
@@ -734,8 +757,8 @@ static int g_stream_warps_override = getenv("RMV_STREAM_WARPS") ? atoi(getenv("R
 static int g_stream_block_override = getenv("RMV_STREAM_BLOCK") ? atoi(getenv("RMV_STREAM_BLOCK")) : 0;
 
 static void stream_shape_for(int64_t n, int sms, int resident_warps_per_sm, int cap_warps_per_sm, int forced_block,
-                             StreamShape* shape, unsigned* grid, unsigned* block) {
-  const uint32_t units = (uint32_t)((n + 31) / 32);
+                             StreamShape* shape, unsigned* grid, unsigned* block, uint32_t unit_envs = 32u) {
+  const uint32_t units = (uint32_t)((n + unit_envs - 1) / unit_envs);
   int per_sm = resident_warps_per_sm;
   if (cap_warps_per_sm > 0 && cap_warps_per_sm < per_sm) per_sm = cap_warps_per_sm;
   const uint32_t slots = (uint32_t)sms * (uint32_t)per_sm;
@@ -746,7 +769,7 @@ static void stream_shape_for(int64_t n, int sms, int resident_warps_per_sm, int 
   if (warps <= (uint32_t)sms * 24u) b = 32; else if (warps <= (uint32_t)sms * 48u) b = 64;
   if (forced_block == 32 || forced_block == 64 || forced_block == 128) b = (unsigned)forced_block;
   shape->units_per_warp = k; shape->warps = warps;
-  shape->limit = units * 32u; shape->env_stride = warps * 32u;
+  shape->limit = units * unit_envs; shape->env_stride = warps * unit_envs;
   *block = b;
   *grid = (warps * 32u + b - 1u) / b;
 }
@@ -799,9 +822,43 @@ static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_
   return cudaLaunchKernelEx(&cfg, k_step_stream<KIND, TRACK, PREF, CTRL>, args, shape);
 }
 
+// quadrotor3d, two envs per thread on the packed float32 pipe (k_step_stream_pair)
+static int g_stream_pair = getenv("RMV_STREAM_PAIR") ? atoi(getenv("RMV_STREAM_PAIR")) : -1;   // developer switch: -1 = the policy below
+static bool stream_pair_default(int64_t n) { (void)n; return false; }
+static cudaError_t launch_stream_pair(rmv_env* e, const StepArgs& args, cudaStream_t st) {
+  static int resident_of[kMaxDevices] = {}, sms_of[kMaxDevices] = {};
+  const int dev = current_device();
+  if (resident_of[dev] == 0) {
+    cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_stream_pair, 128, 0);
+    if (resident_of[dev] < 1) resident_of[dev] = 1;
+    if (sms_of[dev] < 1) sms_of[dev] = 1;
+  }
+  StreamShape shape; unsigned grid = 0, block = 0;
+  const int cap = e->stream_warps_per_sm > 0 ? e->stream_warps_per_sm : g_stream_warps_override;
+  const int fb = e->stream_block > 0 ? e->stream_block : g_stream_block_override;
+  stream_shape_for(args.n, sms_of[dev], resident_of[dev] * 4, cap, fb, &shape, &grid, &block, 64u);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_step_stream_pair, args, shape);
+}
+
 template <int KIND>
 static cudaError_t launch_stream_k(rmv_env* e, const StepArgs& args, cudaStream_t st, bool ctrl = false) {
   const bool track = args.ep_return != nullptr;
+  if constexpr (KIND == QUAD3D) {
+    const bool fits = !track && !ctrl && !args.act_soa && aligned(args.act, 16) && aligned(args.reward, 8) && aligned(args.done, 2) &&
+                      (args.out_ld % 2) == 0 && (args.act_step_stride % 4) == 0;
+    const bool want = e->vec == 2 || (e->vec == 0 && (g_stream_pair >= 0 ? g_stream_pair != 0 : stream_pair_default(args.n)));
+    if (fits && want) { e->last_variant = RMV_VARIANT_STREAM_PAIR; return launch_stream_pair(e, args, st); }
+  }
   if (ctrl) return track ? launch_stream_t<KIND, true, false, true>(e, args, st) : launch_stream_t<KIND, false, false, true>(e, args, st);
   const bool pref = e->prefetch >= 0 ? e->prefetch != 0 : default_prefetch(KIND, args.n);
   if (track) return pref ? launch_stream_t<KIND, true, true>(e, args, st) : launch_stream_t<KIND, true, false>(e, args, st);
@@ -913,6 +970,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
     RMV_REQUIRE(rew != nullptr && done != nullptr, "reward_dev and done_dev must not be NULL");
     float* const rows = e->state + c0 * e->S;
     a.rows_in = rows; a.obs = rows;
+    e->last_variant = RMV_VARIANT_ROWS;
     switch (e->kind) {
       case RMV_QUAD2D: err = launch_step_rows_k<QUAD2D>(e, a, st, fused_ctrl); break;
       case RMV_QUAD2D_SLUNG: err = launch_step_rows_k<QUAD2D_SLUNG>(e, a, st, fused_ctrl); break;
@@ -922,6 +980,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
     if (err == cudaSuccess && obs != nullptr && obs != rows)
       err = cudaMemcpyAsync(obs, rows, (size_t)cn * e->S * sizeof(float), cudaMemcpyDeviceToDevice, st);
   } else if (stream) {
+    e->last_variant = RMV_VARIANT_STREAM;          // (launch_stream_k<QUAD3D> may overwrite it with RMV_VARIANT_STREAM_PAIR)
     switch (e->kind) {
       case RMV_QUAD2D: err = launch_stream_k<QUAD2D>(e, a, st, fused_ctrl); break;
       case RMV_QUAD2D_SLUNG: err = launch_stream_k<QUAD2D_SLUNG>(e, a, st, fused_ctrl); break;
@@ -930,6 +989,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
     }
   } else if (fused_ctrl) {
     if (n_steps != 1) return fail(RMV_EINVAL, "internal: the fused control+step kernel is single-step");
+    e->last_variant = RMV_VARIANT_STEP;
     switch (e->kind) {
       case RMV_QUAD2D: err = launch_control_step_k<QUAD2D>(a, st); break;
       case RMV_QUAD2D_SLUNG: err = launch_control_step_k<QUAD2D_SLUNG>(a, st); break;
@@ -937,6 +997,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
       default: err = launch_control_step_k<QUAD3D_SLUNG>(a, st); break;
     }
   } else {
+    e->last_variant = n_steps > 1 ? RMV_VARIANT_ROLLOUT : ((e->use_tma && vec == 1 && !a.act_soa && aligned(a.act, 16)) ? RMV_VARIANT_TMA : RMV_VARIANT_STEP);
     switch (e->kind) {
       case RMV_QUAD2D: err = launch_step_k<QUAD2D>(e, a, vec, st); break;
       case RMV_QUAD2D_SLUNG: err = launch_step_k<QUAD2D_SLUNG>(e, a, vec, st); break;
@@ -1014,7 +1075,7 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
   float* const rew0 = reward_dev ? reward_dev : env->h_rew;
   uint8_t* const done0 = done_dev ? done_dev : env->h_done;
   const int64_t out_stride = reward_dev ? out_ld : 0, done_stride = done_dev ? out_ld : 0;
-  if (fused == RMV_MANY_STREAM && g_use_stream && n_steps >= 2) {
+  if (fused == RMV_MANY_STREAM && g_use_stream && n_steps >= 2 && (g_force_stream || stream_pays(env->kind, env->n))) {
     // one stride for both outputs: if only one of them is parked, the other one's scratch must be T rows as well
     if ((reward_dev == nullptr) != (done_dev == nullptr))
       return fail(RMV_EINVAL, "rmv_step_many(RMV_MANY_STREAM): pass both reward_dev and done_dev, or neither");
@@ -1208,7 +1269,7 @@ extern "C" RMV_API int rmv_control_step_many(rmv_env* env, int n_steps, const fl
   float* const rew0 = reward_dev ? reward_dev : env->h_rew;
   uint8_t* const done0 = done_dev ? done_dev : env->h_done;
   const int64_t stride = reward_dev ? out_ld : 0;
-  if (!env->rows && g_use_stream && n_steps >= 2)       // ONE launch: the closed loop runs inside the step stream
+  if (!env->rows && g_use_stream && n_steps >= 2 && (g_force_stream || stream_pays(env->kind, env->n)))   // ONE launch: the closed loop runs inside the step stream
     return launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, rew0, done0, stride, nullptr, 1, n_steps, st, 0, -1, true, true, &C, act_out_dev);
   for (int t = 0; t < n_steps; ++t) {
     int rc = launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, rew0 + (int64_t)t * stride, done0 + (int64_t)t * stride, env->n, nullptr, 1, 1,

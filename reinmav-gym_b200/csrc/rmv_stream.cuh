@@ -23,6 +23,7 @@
 // (tests/test_gpu_parity.py::test_step_stream_bitwise).
 #pragma once
 #include "rmv_kernels.cuh"
+#include "rmv_pair.cuh"
 
 namespace rmv {
 
@@ -184,6 +185,129 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
         return redraw_list[w][slot];
       });
       __syncthreads();                               // owners read these rows at the next step; the lists are free again
+    }
+  }
+}
+
+// ---- two envs per thread on the packed float32 pipe (quadrotor3d; rmv_pair.cuh) -----------------------------------
+// Same stream, unit = 64 envs per warp: lane l owns envs 2l, 2l+1 of the unit — 64-bit row accesses, two 128-bit action
+// rows, FFMA2 / FMUL2 / FADD2 arithmetic.  ~115 issued instructions per env-step instead of ~190 at the same number of
+// envs in flight per SM (8 CTAs x 4 warps x 64 envs).  Row-per-env actions, no episode tracking (the one-env kernel
+// serves those); reward / done buffers 8- / 2-byte aligned with an even out_ld (checked by the host).
+constexpr int kPairList = 128;        // per-warp re-draw list of the pair kernel: flushed when more than 64 entries are pending
+
+__global__ void __launch_bounds__(128, 8)
+k_step_stream_pair(const StepArgs a, const StreamShape shape) {
+  constexpr int KIND = QUAD3D;
+  constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
+  constexpr int NB = (S + 3) / 4;
+  __shared__ uint2 redraw_list[kStreamWarps][kPairList];
+  __shared__ uint32_t redraw_count[kStreamWarps];
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t gw = (blockIdx.x * blockDim.x + tid) >> 5;
+  const uint32_t n = (uint32_t)a.n;
+  const uint32_t limit = shape.limit;                                   // envs covered by existing 64-env units
+  const uint32_t W = shape.warps, K = shape.units_per_warp;
+  const uint32_t T = (uint32_t)a.n_steps;
+  if (tid < kStreamWarps) redraw_count[tid] = 0u;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __syncthreads();
+
+  uint2* const list = redraw_list[warp & (kStreamWarps - 1)];
+  const uint32_t e_first = (gw < W) ? (gw << 6) + 2u * lane : limit;
+  const uint32_t de = shape.env_stride;                                  // 64 * W (W % 4 == 0: whole tiles)
+  const size_t ds = (size_t)(de >> 7) * (S * kTile);
+  float* const sp_first = a.state + ((size_t)(e_first >> 7) * (S * kTile) + (e_first & (kTile - 1)));
+
+  const float* act_t = a.act;
+  float* rew_t = a.reward;
+  unsigned char* done_t = reinterpret_cast<unsigned char*>(a.done);
+  for (uint32_t t = 0; t < T; ++t, act_t += a.act_step_stride, rew_t += a.out_ld, done_t += a.out_ld) {
+    if (t + 1u == T) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    float* sp = sp_first;
+    uint32_t e = e_first, pending = 0u;
+    for (uint32_t j = 0; j < K; ++j, sp += ds, e += de) {
+      if (e < limit) {                             // warp-uniform: this unit exists
+        const bool act0 = e < n, act1 = e + 1u < n;
+        p2 s[S], act[A];
+#pragma unroll
+        for (int c = 0; c < S; ++c) s[c] = p2(*reinterpret_cast<const float2*>(sp + c * kTile));   // padded tiles: in bounds
+        {
+          const float4* const ap = reinterpret_cast<const float4*>(act_t + (size_t)(e * (uint32_t)A));
+          const float4 r0 = act0 ? __ldcs(ap) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          const float4 r1 = act1 ? __ldcs(ap + 1) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          act[0] = p2(r0.x, r1.x); act[1] = p2(r0.y, r1.y); act[2] = p2(r0.z, r1.z); act[3] = p2(r0.w, r1.w);
+        }
+        p2 pos_sq, vel_sq, n_rew;
+        quad3d_pair_step(a.P, s, act, pos_sq, vel_sq, n_rew);
+        const bool done0 = is_done(a.P, pos_sq.v.x, vel_sq.v.x) && act0;
+        const bool done1 = is_done(a.P, pos_sq.v.y, vel_sq.v.y) && act1;
+        const bool redraw0 = done0 && a.auto_reset != 0, redraw1 = done1 && a.auto_reset != 0;
+        float rew0 = -n_rew.v.x, rew1 = -n_rew.v.y;
+        uint32_t count0 = 0u, count1 = 0u;
+        if (done0 || done1) {                      // rare lane: the ever-done flag decides the terminal reward
+          if (done0) {
+            const uint32_t w = a.episode[e];
+            rew0 = reward_of(a.P, true, (w & kEverDone) != 0u, n_rew.v.x);
+            count0 = (w & ~kEverDone) + (a.auto_reset ? 1u : 0u);
+            a.episode[e] = count0 | kEverDone;
+          }
+          if (done1) {
+            const uint32_t w = a.episode[e + 1u];
+            rew1 = reward_of(a.P, true, (w & kEverDone) != 0u, n_rew.v.y);
+            count1 = (w & ~kEverDone) + (a.auto_reset ? 1u : 0u);
+            a.episode[e + 1u] = count1 | kEverDone;
+          }
+        }
+        if (act1) {                                // both envs exist
+          __stcs(reinterpret_cast<float2*>(rew_t + e), make_float2(scaled_reward(a.P, rew0), scaled_reward(a.P, rew1)));
+          __stcs(reinterpret_cast<uchar2*>(done_t + e), make_uchar2(done0 ? 1 : 0, done1 ? 1 : 0));
+        } else if (act0) {
+          __stcs(rew_t + e, scaled_reward(a.P, rew0));
+          __stcs(done_t + e, (unsigned char)(done0 ? 1 : 0));
+        }
+        if (!(redraw0 || redraw1)) {
+          if (act0) {                              // (a padding lane writes nothing)
+#pragma unroll
+            for (int c = 0; c < S; ++c) *reinterpret_cast<float2*>(sp + c * kTile) = s[c].v;
+          }
+        } else {
+          if (!redraw0 && act0) {
+#pragma unroll
+            for (int c = 0; c < S; ++c) sp[c * kTile] = s[c].v.x;
+          }
+          if (!redraw1 && act1) {
+#pragma unroll
+            for (int c = 0; c < S; ++c) sp[c * kTile + 1] = s[c].v.y;
+          }
+        }
+        const uint32_t m0 = __ballot_sync(0xffffffffu, redraw0), m1 = __ballot_sync(0xffffffffu, redraw1);
+        if ((m0 | m1) != 0u) {                     // warp-uniform
+          const uint32_t lt = (1u << lane) - 1u;
+          if (redraw0) list[pending + (uint32_t)__popc(m0 & lt)] = make_uint2(e, count0);
+          if (redraw1) list[pending + (uint32_t)__popc(m0) + (uint32_t)__popc(m1 & lt)] = make_uint2(e + 1u, count1);
+          pending += (uint32_t)(__popc(m0) + __popc(m1));
+          if (pending > 64u) {                     // a mass finish: the warp empties its own list right away
+            __syncwarp();
+            stream_redraw<KIND>(a, pending * NB, lane, 32u, [&](uint32_t slot) { return list[slot]; });
+            __syncwarp();
+            pending = 0u;
+          }
+        }
+      }
+    }
+    if (lane == 0u) redraw_count[warp & (kStreamWarps - 1)] = pending;
+    __syncthreads();
+    const uint32_t c0 = redraw_count[0], c1 = redraw_count[1], c2 = redraw_count[2], c3 = redraw_count[3];
+    const uint32_t total = c0 + c1 + c2 + c3;
+    if (total != 0u) {                               // CTA-uniform
+      stream_redraw<KIND>(a, total * NB, tid, blockDim.x, [&](uint32_t slot) {
+        uint32_t w = 0u;
+        if (slot >= c0) { slot -= c0; w = 1u; if (slot >= c1) { slot -= c1; w = 2u; if (slot >= c2) { slot -= c2; w = 3u; } } }
+        return redraw_list[w][slot];
+      });
+      __syncthreads();
     }
   }
 }

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("RMV_LIB", os.path.join(_HERE, "lib", "librmv.so"))
 QUAD2D, QUAD2D_SLUNG, QUAD3D, QUAD3D_SLUNG, REINMAV = 0, 1, 2, 3, 4
 ACT_AOS, ACT_SOA = 0, 1
 MANY_STREAM, MANY_ROLLOUT, MANY_LAUNCHES = 0, 1, 2
+VARIANTS = {-1: "none", 0: "k_step", 1: "k_step_rows", 2: "k_step_tma", 3: "k_rollout", 4: "k_step_stream", 5: "k_step_stream_pair"}
 TRACK_EPISODES = 1
 STATE_ROWS = 2
 EVER_DONE_BIT = 0x80000000
@@ -54,6 +55,8 @@ SIGNATURES = {
     "rmv_dims": (_i, [_vp, _pi, _pi, _pi64, _pi64]),
     "rmv_get_params": (_i, [_vp, ctypes.POINTER(Params)]),
     "rmv_set_seed": (_i, [_vp, _u64]),
+    "rmv_stream_pays": (_i, [_i, _i64]),
+    "rmv_last_variant": (_i, [_vp, _pi]),
     "rmv_get_time": (_i, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "rmv_set_time": (_i, [_vp, ctypes.c_double]),
     "rmv_set_tuning": (_i, [_vp, _i, _i]),

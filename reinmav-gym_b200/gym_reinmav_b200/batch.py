@@ -147,6 +147,13 @@ class QuadBatch:
         self.seed = int(seed)
         check(lib().rmv_set_seed(self._h, self.seed & 0xFFFFFFFFFFFFFFFF))
 
+    @property
+    def last_kernel(self):
+        """Name of the kernel family the most recent step call launched ("k_step_stream_pair", ...)."""
+        v = ctypes.c_int()
+        check(lib().rmv_last_variant(self._h, ctypes.byref(v)))
+        return _capi.VARIANTS.get(v.value, str(v.value))
+
     def set_tuning(self, vec=0, block=0):
         check(lib().rmv_set_tuning(self._h, int(vec), int(block)))
 
@@ -231,7 +238,9 @@ class QuadBatch:
         check(lib().rmv_step_many(self._h, int(n_steps), _ptr(actions, "float32", d, "actions"), layout, int(act_ld),
                                   _ptr(reward, "float32", d, "reward"), _ptr(done, "uint8", d, "done"),
                                   int(out_ld or self.num_envs), int(fused), _stream(stream, d)))
-        self.launches += int(n_steps) if int(fused) == _capi.MANY_LAUNCHES else 1
+        one = int(fused) == _capi.MANY_ROLLOUT or (int(fused) == _capi.MANY_STREAM and self.state_layout == "tiles" and self.kind < 4
+                                                   and int(n_steps) >= 2 and lib().rmv_stream_pays(self.kind, self.num_envs))
+        self.launches += 1 if one else int(n_steps)
 
     # ---------------------------------------------------------------- hot path (host buffers)
     def step_host(self, actions, reward, done, obs=None, auto_reset=True, stream=None):

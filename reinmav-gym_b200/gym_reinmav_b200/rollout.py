@@ -22,7 +22,8 @@ class RolloutBuffer:
     def __init__(self, venv, n_steps, travelling=None):
         self.venv, self.T = venv, int(n_steps)
         if travelling is None:
-            travelling = venv.batch.state_dim in (10, 16)          # quadrotor3d, quadrotor3d-slungload
+            # quadrotor3d, quadrotor3d-slungload — and any env that keeps its state as rows anyway
+            travelling = venv.batch.state_dim in (10, 16) or getattr(venv, "state_layout", "tiles") == "rows"
         self.travelling = bool(travelling) and venv.batch.action_dim > 0
         n, S, A = venv.num_envs, venv.batch.state_dim, venv.batch.action_dim
         dev = "cuda:%d" % venv.device

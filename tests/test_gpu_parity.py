@@ -269,6 +269,39 @@ def test_step_stream_bitwise(torch, rmv, env_id, case):
         assert abs(st0["return_sum"] - st1["return_sum"]) <= 1e-9 * max(1.0, abs(st0["return_sum"]))   # atomic double sums
 
 
+@pytest.mark.parametrize("n,cap,block", [(128 * 41 + 18, 0, 0), (20000 + 5, 1, 32), (20000 + 6, 2, 128), (17, 0, 0), (63, 0, 0),
+                                         ((1 << 19) + 77, 0, 0), ((1 << 20) + 2, 0, 0)])
+def test_step_stream_pair_bitwise(torch, rmv, n, cap, block):
+    """The two-envs-per-thread step stream on the packed float32 pipe (k_step_stream_pair: FFMA2 / FMUL2 / FADD2, 64-bit
+    row accesses; quadrotor3d) against T launches of the one-env-per-thread kernel: state, rewards, done flags and
+    episode words bit for bit — odd and even batch sizes (a lane with one env, a padding lane), less than one unit,
+    several units per warp, wide initial states (mass finish: the warp-local flush), two consecutive calls."""
+    env_id = "quadrotor3d-v0"
+    T, seed, dev = (12 if n > 100000 else 40), 8, "cuda:0"
+    start = np.random.RandomState(3).uniform(-3, 3, (n, 10)).astype(np.float32)
+    acts = torch.empty((T, n, 4), dtype=torch.float32, device=dev)
+    for t in range(T):
+        rmv.fill_uniform_actions(acts[t], n, 4, 0.0, 10.0, seed, step_index=t)
+    out = []
+    for mode, vec in ((2, 1), (0, 2)):
+        b = rmv.QuadBatch(env_id, n, seed=seed)
+        b.set_tuning(vec=vec)
+        b.set_stream(warps_per_sm=cap, block=block)
+        b.reset()
+        b.set_state(start)
+        ld = n + (n % 2)                              # even leading dimension: the pair kernel stores float2 / uchar2
+        rew = torch.zeros((2, T, ld), dtype=torch.float32, device=dev)
+        done = torch.zeros((2, T, ld), dtype=torch.uint8, device=dev)
+        for call in range(2):
+            b.step_many(T, acts, rew[call], done[call], out_ld=ld, layout=0, fused=mode)
+        torch.cuda.synchronize()
+        out.append((b.get_state(), rew[:, :, :n].cpu().numpy(), done[:, :, :n].cpu().numpy(), b.get_episode_words(), b.last_kernel))
+        b.close()
+    (s0, r0, d0, w0, k0), (s1, r1, d1, w1, k1) = out
+    assert d0[0, 0].mean() > 0.1 and (k0, k1) == ("k_step", "k_step_stream_pair")
+    assert np.array_equal(d0, d1) and same_bits(r0, r1) and same_bits(s0, s1) and np.array_equal(w0, w1)
+
+
 def test_step_stream_without_outputs_and_vs_model(torch, rmv):
     """reward_dev / done_dev may be NULL (only the state matters), and the stream equals the float32 model directly."""
     env_id, n, T, seed = "quadrotor3d-slungload-v0", 9000, 30, 2
