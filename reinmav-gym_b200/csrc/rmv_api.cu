@@ -591,7 +591,7 @@ static bool default_prefetch(int kind, int64_t n) {
 // at N = 2^23).  Above the threshold RMV_MANY_STREAM issues launches.
 static bool stream_pays(int kind, int64_t n) {
   static const int64_t bytes[4] = {53, 85, 101, 149};
-  static const int64_t limit_mb[4] = {128, 48, 256, 256};
+  static const int64_t limit_mb[4] = {256, 32, 256, 256};      // quadrotor2d-slungload gains up to N = 2^18 only
   return kind >= 0 && kind < 4 && n * bytes[kind] <= (limit_mb[kind] << 20);
 }
 
@@ -824,6 +824,8 @@ static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_
 
 // quadrotor3d, two envs per thread on the packed float32 pipe (k_step_stream_pair)
 static int g_stream_pair = getenv("RMV_STREAM_PAIR") ? atoi(getenv("RMV_STREAM_PAIR")) : -1;   // developer switch: -1 = the policy below
+// measured (profiles/r2_sweep_stream_pair.txt): 10.5 vs 10.1 us per step at N = 2^20, 3.15 vs 3.25 at N = 2^18, 1.67 vs 1.32
+// at N = 65536 — fewer issue slots (52 % busy instead of 72 %) but half the warps to hide latency with: opt-in (vec = 2)
 static bool stream_pair_default(int64_t n) { (void)n; return false; }
 static cudaError_t launch_stream_pair(rmv_env* e, const StepArgs& args, cudaStream_t st) {
   static int resident_of[kMaxDevices] = {}, sms_of[kMaxDevices] = {};
