@@ -310,6 +310,29 @@ RMV_API int rmv_gather_episodes(rmv_env* env, const int64_t* idx_host, int64_t k
 /* per-env return / length of the most recently finished episode, device pointers [ld] */
 RMV_API int rmv_episode_ptr(rmv_env* env, float** last_return_dev, uint32_t** last_length_dev);
 
+/* ---- VecNormalize on the device ------------------------------------------- */
+/* Running observation / return normalisation of baselines' `VecNormalize` — the wrapper the reference's launcher puts
+ * around a vec-env (gym_reinmav/run.py:91-92: for env_type 'mujoco'; an opt-in for the native envs).  Third-party
+ * algorithm (openai/baselines@90d6677, baselines/common/vec_env/vec_normalize.py + running_mean_std.py, not vendored):
+ * ret = ret*gamma + rew; ob_rms.update(obs); obs' = clip((obs - mean)/sqrt(var + eps), +-clip_obs); ret_rms.update(ret);
+ * rew' = clip(rew/sqrt(ret_var + eps), +-clip_rew); ret[done] = 0 — statistics in float64, two kernels per step, no host
+ * round trip.  An rmv_norm belongs to one device and one batch size; it is independent of any rmv_env. */
+typedef struct rmv_norm rmv_norm;
+RMV_API int rmv_norm_create(rmv_norm** out, int64_t n_envs, int obs_dim, int device, int norm_obs, int norm_ret,
+                            float clip_obs /*10*/, float clip_rew /*10*/, double gamma /*0.99*/, double epsilon /*1e-8*/);
+RMV_API int rmv_norm_destroy(rmv_norm* nm);
+/* VecNormalize.step_wait(): raw obs rows [n][S] / reward [n] / done [n] in, normalised obs_out [n][S] / reward_out [n]
+ * out (obs_dev and obs_out_dev both NULL: rewards only).  update == 0 freezes the statistics (evaluation). */
+RMV_API int rmv_norm_step(rmv_norm* nm, const float* obs_dev, const float* reward_dev, const uint8_t* done_dev,
+                          float* obs_out_dev, float* reward_out_dev, int update, void* stream);
+/* VecNormalize.reset(): returns cleared, the reset observations enter the statistics and are normalised */
+RMV_API int rmv_norm_reset(rmv_norm* nm, const float* obs_dev, float* obs_out_dev, int update, void* stream);
+/* the running statistics (checkpoint / restore / logging); ob_mean, ob_var: obs_dim doubles.  Both synchronise `stream`. */
+RMV_API int rmv_norm_get(rmv_norm* nm, double* ob_mean, double* ob_var, double* ob_count, double* ret_mean, double* ret_var,
+                         double* ret_count, void* stream);
+RMV_API int rmv_norm_set(rmv_norm* nm, const double* ob_mean, const double* ob_var, double ob_count, double ret_mean,
+                         double ret_var, double ret_count, void* stream);
+
 /* ---- pinned host memory helpers ------------------------------------------------------------ */
 RMV_API int rmv_host_alloc(void** out, size_t bytes);
 RMV_API int rmv_host_free(void* p);

@@ -15,6 +15,7 @@
 #include "rmv_control.cuh"
 #include "rmv_step_tma.cuh"
 #include "rmv_stream.cuh"
+#include "rmv_norm.cuh"
 #include "rmv_reinmav.cuh"
 
 using namespace rmv;
@@ -1385,6 +1386,133 @@ extern "C" RMV_API int rmv_episode_ptr(rmv_env* env, float** last_return_dev, ui
   RMV_REQUIRE(env->flags & RMV_TRACK_EPISODES, "handle was created without RMV_TRACK_EPISODES");
   if (last_return_dev) *last_return_dev = env->last_return;
   if (last_length_dev) *last_length_dev = env->last_length;
+  return RMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// VecNormalize on the device (rmv_norm.cuh)
+// ------------------------------------------------------------------------------------------
+struct rmv_norm {
+  int device = 0, S = 0;
+  int64_t n = 0;
+  int norm_obs = 1, norm_ret = 1;
+  float clip_obs = 10.0f, clip_rew = 10.0f;
+  double gamma = 0.99, epsilon = 1e-8;
+  double* ret = nullptr;       // [n]
+  double* stats = nullptr;     // [2][kNormStats]
+  double* sums = nullptr;      // [2][kNormSums]
+  uint64_t step = 0;           // parity selects the current halves
+};
+
+static void norm_host_defaults(double* st) {
+  for (int c = 0; c <= kNormMaxDim; ++c) { st[c] = 0.0; st[(kNormMaxDim + 1) + c] = 1.0; }   // RunningMeanStd: mean 0, var 1
+  st[2 * (kNormMaxDim + 1)] = 1e-4; st[2 * (kNormMaxDim + 1) + 1] = 1e-4;                      // count = epsilon = 1e-4
+}
+
+extern "C" RMV_API int rmv_norm_create(rmv_norm** out, int64_t n_envs, int obs_dim, int device, int norm_obs, int norm_ret,
+                                       float clip_obs, float clip_rew, double gamma, double epsilon) {
+  RMV_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  RMV_REQUIRE(n_envs > 0 && obs_dim > 0 && obs_dim <= kNormMaxDim, "n_envs must be positive and obs_dim in [1, %d]", kNormMaxDim);
+  RMV_ON_DEVICE(device);
+  rmv_norm* nm = new (std::nothrow) rmv_norm();
+  if (!nm) return fail(RMV_ENOMEM, "host allocation failed");
+  nm->device = device; nm->S = obs_dim; nm->n = n_envs; nm->norm_obs = norm_obs ? 1 : 0; nm->norm_ret = norm_ret ? 1 : 0;
+  nm->clip_obs = clip_obs; nm->clip_rew = clip_rew; nm->gamma = gamma; nm->epsilon = epsilon;
+  cudaError_t err = alloc_zero(&nm->ret, (size_t)n_envs);
+  if (err == cudaSuccess) err = alloc_zero(&nm->stats, (size_t)2 * kNormStats);
+  if (err == cudaSuccess) err = alloc_zero(&nm->sums, (size_t)2 * kNormSums);
+  if (err == cudaSuccess) {
+    double st[kNormStats];
+    norm_host_defaults(st);
+    err = cudaMemcpy(nm->stats, st, sizeof(st), cudaMemcpyHostToDevice);
+  }
+  if (err == cudaSuccess) err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    cudaFree(nm->ret); cudaFree(nm->stats); cudaFree(nm->sums);
+    delete nm;
+    return fail(err == cudaErrorMemoryAllocation ? RMV_ENOMEM : RMV_ECUDA, "rmv_norm_create: %s", cudaGetErrorString(err));
+  }
+  *out = nm;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_norm_destroy(rmv_norm* nm) {
+  if (!nm) return RMV_OK;
+  {
+    RMV_ON_DEVICE(nm->device);
+    cudaDeviceSynchronize();
+    cudaFree(nm->ret); cudaFree(nm->stats); cudaFree(nm->sums);
+  }
+  delete nm;
+  return RMV_OK;
+}
+
+static int norm_launch(rmv_norm* nm, const float* obs, const float* rew, const uint8_t* done, float* obs_out, float* rew_out,
+                       int update, cudaStream_t st) {
+  NormArgs a;
+  const int cur = (int)(nm->step & 1u);
+  a.obs = obs; a.reward = rew; a.done = done; a.obs_out = obs_out; a.reward_out = rew_out; a.ret = nm->ret;
+  a.stats_cur = nm->stats + cur * kNormStats; a.stats_next = nm->stats + (cur ^ 1) * kNormStats;
+  a.sums_cur = nm->sums + cur * kNormSums; a.sums_next = nm->sums + (cur ^ 1) * kNormSums;
+  a.n = nm->n; a.S = nm->S; a.norm_obs = nm->norm_obs; a.norm_ret = nm->norm_ret; a.update = update ? 1 : 0;
+  a.clip_obs = nm->clip_obs; a.clip_rew = nm->clip_rew; a.gamma = nm->gamma; a.epsilon = nm->epsilon;
+  unsigned grid = blocks_for(nm->n, 256);
+  if (grid > 148u * 8u) grid = 148u * 8u;
+  k_norm_moments<<<grid, 256, 0, st>>>(a);
+  k_norm_apply<<<blocks_for(nm->n, 256), 256, 0, st>>>(a);
+  RMV_CUDA(cudaGetLastError());
+  nm->step += 1;
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_norm_step(rmv_norm* nm, const float* obs_dev, const float* reward_dev, const uint8_t* done_dev,
+                                     float* obs_out_dev, float* reward_out_dev, int update, void* stream) {
+  RMV_REQUIRE(nm != nullptr && reward_dev != nullptr && done_dev != nullptr && reward_out_dev != nullptr, "NULL argument");
+  RMV_REQUIRE((obs_dev == nullptr) == (obs_out_dev == nullptr), "pass both obs_dev and obs_out_dev, or neither");
+  RMV_ON_DEVICE(nm->device);
+  return norm_launch(nm, obs_dev, reward_dev, done_dev, obs_out_dev, reward_out_dev, update, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" RMV_API int rmv_norm_reset(rmv_norm* nm, const float* obs_dev, float* obs_out_dev, int update, void* stream) {
+  RMV_REQUIRE(nm != nullptr && obs_dev != nullptr && obs_out_dev != nullptr, "NULL argument");
+  RMV_ON_DEVICE(nm->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RMV_CUDA(cudaMemsetAsync(nm->ret, 0, (size_t)nm->n * sizeof(double), st));       // self.ret = np.zeros(self.num_envs)
+  return norm_launch(nm, obs_dev, nullptr, nullptr, obs_out_dev, nullptr, update, st);
+}
+
+extern "C" RMV_API int rmv_norm_get(rmv_norm* nm, double* ob_mean, double* ob_var, double* ob_count, double* ret_mean,
+                                    double* ret_var, double* ret_count, void* stream) {
+  RMV_REQUIRE(nm != nullptr, "nm is NULL");
+  RMV_ON_DEVICE(nm->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double h[kNormStats];
+  RMV_CUDA(cudaMemcpyAsync(h, nm->stats + (nm->step & 1u) * kNormStats, sizeof(h), cudaMemcpyDeviceToHost, st));
+  RMV_CUDA(cudaStreamSynchronize(st));
+  for (int c = 0; c < nm->S; ++c) {
+    if (ob_mean) ob_mean[c] = h[c];
+    if (ob_var) ob_var[c] = h[(kNormMaxDim + 1) + c];
+  }
+  if (ob_count) *ob_count = h[2 * (kNormMaxDim + 1)];
+  if (ret_mean) *ret_mean = h[nm->S];
+  if (ret_var) *ret_var = h[(kNormMaxDim + 1) + nm->S];
+  if (ret_count) *ret_count = h[2 * (kNormMaxDim + 1) + 1];
+  return RMV_OK;
+}
+
+extern "C" RMV_API int rmv_norm_set(rmv_norm* nm, const double* ob_mean, const double* ob_var, double ob_count, double ret_mean,
+                                    double ret_var, double ret_count, void* stream) {
+  RMV_REQUIRE(nm != nullptr && ob_mean != nullptr && ob_var != nullptr, "NULL argument");
+  RMV_ON_DEVICE(nm->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double h[kNormStats];
+  norm_host_defaults(h);
+  for (int c = 0; c < nm->S; ++c) { h[c] = ob_mean[c]; h[(kNormMaxDim + 1) + c] = ob_var[c]; }
+  h[nm->S] = ret_mean; h[(kNormMaxDim + 1) + nm->S] = ret_var;
+  h[2 * (kNormMaxDim + 1)] = ob_count; h[2 * (kNormMaxDim + 1) + 1] = ret_count;
+  RMV_CUDA(cudaStreamSynchronize(st));
+  RMV_CUDA(cudaMemcpy(nm->stats + (nm->step & 1u) * kNormStats, h, sizeof(h), cudaMemcpyHostToDevice));
   return RMV_OK;
 }
 

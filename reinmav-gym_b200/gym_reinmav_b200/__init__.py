@@ -21,7 +21,13 @@ def RolloutBuffer(*args, **kwargs):
     from .rollout import RolloutBuffer as _RB
     return _RB(*args, **kwargs)
 
-__version__ = "0.1.0"
+def VecNormalize(*args, **kwargs):
+    """baselines' VecNormalize on the device (run.py:91-92; imports torch lazily)."""
+    from .vec_normalize import VecNormalize as _VN
+    return _VN(*args, **kwargs)
+
+
+__version__ = "0.2.0"
 
 ENTRY_POINTS = {
     "quadrotor2d-v0": "gym_reinmav_b200.envs.native:Quadrotor2D",

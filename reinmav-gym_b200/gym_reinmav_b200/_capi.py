@@ -39,7 +39,7 @@ class Params(ctypes.Structure):
 
 _vp, _i, _i64, _u64, _u32, _f = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64,
                                  ctypes.c_uint32, ctypes.c_float)
-_pi, _pi64, _pf = ctypes.POINTER(_i), ctypes.POINTER(_i64), ctypes.POINTER(_f)
+_pi, _pi64, _pf, _pd = ctypes.POINTER(_i), ctypes.POINTER(_i64), ctypes.POINTER(_f), ctypes.POINTER(ctypes.c_double)
 
 # name -> (restype, argtypes).  Every symbol include/rmv.h declares must be listed here;
 # tests/test_capi_symbols.py checks the two against each other.
@@ -86,6 +86,12 @@ SIGNATURES = {
     "rmv_episode_stats": (_i, [_vp, ctypes.POINTER(ctypes.c_double), _vp]),
     "rmv_gather_episodes": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "rmv_episode_ptr": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "rmv_norm_create": (_i, [ctypes.POINTER(_vp), _i64, _i, _i, _i, _i, _f, _f, ctypes.c_double, ctypes.c_double]),
+    "rmv_norm_destroy": (_i, [_vp]),
+    "rmv_norm_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "rmv_norm_reset": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "rmv_norm_get": (_i, [_vp, _pd, _pd, _pd, _pd, _pd, _pd, _vp]),
+    "rmv_norm_set": (_i, [_vp, _pd, _pd, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp]),
     "rmv_host_alloc": (_i, [ctypes.POINTER(_vp), ctypes.c_size_t]),
     "rmv_host_free": (_i, [_vp]),
 }
