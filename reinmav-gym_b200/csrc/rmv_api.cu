@@ -100,6 +100,9 @@ struct rmv_env {
   // pipeline of the *_host entry points (lazy)
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t pipe_kernel[3] = {nullptr, nullptr, nullptr};   // after the last step kernel queued on pipe[i]
+  cudaStream_t pipe_small = nullptr;                          // reward / done leave on their own stream, once per call
+  cudaEvent_t pipe_small_done = nullptr;
   cudaEvent_t pipe_start = nullptr;
   int host_chunks = 0;      // 0 = auto
   // tuning
@@ -130,6 +133,7 @@ struct rmv_env {
 };
 
 static int g_use_graph = (getenv("RMV_NO_GRAPH") == nullptr) ? 1 : 0;   // developer switch
+static int g_host_batch_small = getenv("RMV_HOST_BATCH_SMALL") ? atoi(getenv("RMV_HOST_BATCH_SMALL")) : 1;   // developer switch (A/B)
 static int g_use_stream = (getenv("RMV_NO_STREAM") == nullptr) ? 1 : 0; // developer switch: rmv_step_many(mode 0) falls back to launches
 static int g_force_stream = (getenv("RMV_FORCE_STREAM") != nullptr) ? 1 : 0; // developer switch: the stream at every size (sweeps)
 static int g_ctas_cap = getenv("RMV_CTAS_PER_SM") ? atoi(getenv("RMV_CTAS_PER_SM")) : 0;
@@ -215,7 +219,10 @@ static void free_all(rmv_env* e) {
   for (int i = 0; i < 3; ++i) {
     if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]);
     if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]);
+    if (e->pipe_kernel[i]) cudaEventDestroy(e->pipe_kernel[i]);
   }
+  if (e->pipe_small) cudaStreamDestroy(e->pipe_small);
+  if (e->pipe_small_done) cudaEventDestroy(e->pipe_small_done);
   if (e->pipe_start) cudaEventDestroy(e->pipe_start);
   for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
@@ -1162,7 +1169,10 @@ static int ensure_pipe(rmv_env* e) {
   for (int i = 0; i < 3; ++i) {
     if (!e->pipe[i]) RMV_CUDA(cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking));
     if (!e->pipe_done[i]) RMV_CUDA(cudaEventCreateWithFlags(&e->pipe_done[i], cudaEventDisableTiming));
+    if (!e->pipe_kernel[i]) RMV_CUDA(cudaEventCreateWithFlags(&e->pipe_kernel[i], cudaEventDisableTiming));
   }
+  if (!e->pipe_small) RMV_CUDA(cudaStreamCreateWithFlags(&e->pipe_small, cudaStreamNonBlocking));
+  if (!e->pipe_small_done) RMV_CUDA(cudaEventCreateWithFlags(&e->pipe_small_done, cudaEventDisableTiming));
   if (!e->pipe_start) RMV_CUDA(cudaEventCreateWithFlags(&e->pipe_start, cudaEventDisableTiming));
   return RMV_OK;
 }
@@ -1197,6 +1207,12 @@ extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float*
   if (rc) return rc;
   RMV_CUDA(cudaEventRecord(env->pipe_start, st));          // everything queued on the caller's stream comes first
   for (int i = 0; i < 3; ++i) RMV_CUDA(cudaStreamWaitEvent(env->pipe[i], env->pipe_start, 0));
+  RMV_CUDA(cudaStreamWaitEvent(env->pipe_small, env->pipe_start, 0));
+  // The observation rows are the bulk (4S of the 4S + 5 bytes per env going back): they leave chunk by chunk behind their
+  // kernel.  Rewards and done flags leave ONCE per call on a stream of their own, as soon as the last kernel has run
+  // (the kernels are done long before the observation copies are): 2 small DMA transfers instead of 2 per chunk, and
+  // their set-up overlaps the bulk copies instead of sitting between them.
+  const bool batch_small = g_host_batch_small != 0 && obs_host != nullptr;
   int k = 0;
   for (int64_t c0 = 0; c0 < n; c0 += per, ++k) {
     const int64_t cn = (n - c0 < per) ? n - c0 : per;
@@ -1205,16 +1221,27 @@ extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float*
     rc = launch_step(env, env->h_act + c0 * A, RMV_ACT_AOS, 0, 0, env->h_rew + c0, env->h_done + c0, cn,
                      obs_dev ? obs_dev + c0 * S : nullptr, auto_reset, 1, ps, c0, cn, false);
     if (rc) return rc;
+    if (batch_small) RMV_CUDA(cudaEventRecord(env->pipe_kernel[k % 3], ps));
     if (obs_host) RMV_CUDA(cudaMemcpyAsync(obs_host + c0 * S, obs_src + c0 * S, (size_t)cn * S * sizeof(float), cudaMemcpyDeviceToHost, ps));
-    if (reward_host) RMV_CUDA(cudaMemcpyAsync(reward_host + c0, env->h_rew + c0, (size_t)cn * sizeof(float), cudaMemcpyDeviceToHost, ps));
-    if (done_host) RMV_CUDA(cudaMemcpyAsync(done_host + c0, env->h_done + c0, (size_t)cn, cudaMemcpyDeviceToHost, ps));
+    if (!batch_small) {
+      if (reward_host) RMV_CUDA(cudaMemcpyAsync(reward_host + c0, env->h_rew + c0, (size_t)cn * sizeof(float), cudaMemcpyDeviceToHost, ps));
+      if (done_host) RMV_CUDA(cudaMemcpyAsync(done_host + c0, env->h_done + c0, (size_t)cn, cudaMemcpyDeviceToHost, ps));
+    }
   }
   env->step_index += 1u;
+  if (batch_small) {
+    for (int i = 0; i < 3 && i < k; ++i) RMV_CUDA(cudaStreamWaitEvent(env->pipe_small, env->pipe_kernel[i], 0));
+    if (reward_host) RMV_CUDA(cudaMemcpyAsync(reward_host, env->h_rew, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, env->pipe_small));
+    if (done_host) RMV_CUDA(cudaMemcpyAsync(done_host, env->h_done, (size_t)n, cudaMemcpyDeviceToHost, env->pipe_small));
+    RMV_CUDA(cudaEventRecord(env->pipe_small_done, env->pipe_small));
+    RMV_CUDA(cudaStreamWaitEvent(st, env->pipe_small_done, 0));
+  }
   for (int i = 0; i < 3; ++i) {
     RMV_CUDA(cudaEventRecord(env->pipe_done[i], env->pipe[i]));
     RMV_CUDA(cudaStreamWaitEvent(st, env->pipe_done[i], 0));   // later work on the caller's stream sees the new state
   }
   for (int i = 0; i < 3; ++i) RMV_CUDA(cudaStreamSynchronize(env->pipe[i]));
+  if (batch_small) RMV_CUDA(cudaStreamSynchronize(env->pipe_small));
   return RMV_OK;
 }
 
