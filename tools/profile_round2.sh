@@ -22,15 +22,15 @@ cap stream_q2dslung_n16 k_step_stream 2 $SW --envs quadrotor2d-slungload-v0 --n 
 RMV_FORCE_STREAM=1 cap stream_q3d_n23_forced k_step_stream 1 $SW --envs quadrotor3d-v0 --n 8388608 --fused 0 --steps 8 --ring 8
 cap stream_pair_q3d_n20 k_step_stream_pair 2 python tools/sweep.py --vec 2 --layout aos --envs quadrotor3d-v0 --n 1048576 --fused 0 --steps 16 --ring 16
 # one launch per step: the HBM-bound point and the slung-load kinds
-cap step_q3d_n23 "k_step<" 12 $SW --envs quadrotor3d-v0 --n 8388608 --fused 2 --steps 8 --ring 8
-cap step_q3dslung_n20 "k_step<" 30 $SW --envs quadrotor3d-slungload-v0 --n 1048576 --fused 2 --steps 16 --ring 16
-cap step_q3dslung_n23 "k_step<" 12 $SW --envs quadrotor3d-slungload-v0 --n 8388608 --fused 2 --steps 8 --ring 8
-cap step_q2dslung_n20 "k_step<" 30 $SW --envs quadrotor2d-slungload-v0 --n 1048576 --fused 2 --steps 16 --ring 16
-cap step_q2dslung_n23 "k_step<" 12 $SW --envs quadrotor2d-slungload-v0 --n 8388608 --fused 2 --steps 8 --ring 8
+cap step_q3d_n23 "^k_step$" 12 $SW --envs quadrotor3d-v0 --n 8388608 --fused 2 --steps 8 --ring 8
+cap step_q3dslung_n20 "^k_step$" 30 $SW --envs quadrotor3d-slungload-v0 --n 1048576 --fused 2 --steps 16 --ring 16
+cap step_q3dslung_n23 "^k_step$" 12 $SW --envs quadrotor3d-slungload-v0 --n 8388608 --fused 2 --steps 8 --ring 8
+cap step_q2dslung_n20 "^k_step$" 30 $SW --envs quadrotor2d-slungload-v0 --n 1048576 --fused 2 --steps 16 --ring 16
+cap step_q2dslung_n23 "^k_step$" 12 $SW --envs quadrotor2d-slungload-v0 --n 8388608 --fused 2 --steps 8 --ring 8
 # the other kernels
 cap control_q3d_n20 k_control 3 python tools/probe_misc.py control 1048576 quadrotor3d-v0
 cap control_q2d_n20 k_control 3 python tools/probe_misc.py control 1048576 quadrotor2d-v0
-cap control_step_q3d_n20 "k_step<" 3 python tools/probe_misc.py control_step 1048576 quadrotor3d-v0
+cap control_step_q3d_n20 "^k_step$" 3 python tools/probe_misc.py control_step 1048576 quadrotor3d-v0
 cap rollout_q3d_n20 k_rollout 2 python tools/probe_misc.py rollout 1048576 quadrotor3d-v0
 cap rows_track_q3d_n20 k_step_rows 8 python tools/probe_misc.py rows_track 1048576 quadrotor3d-v0
 cap reinmav_n20 k_reinmav_step 3 python tools/probe_misc.py reinmav 1048576
