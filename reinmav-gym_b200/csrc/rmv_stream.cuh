@@ -132,7 +132,12 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
         const bool redraw = done && a.auto_reset != 0;
         float rew = -n_rew;
         uint32_t count = 0u;
-        if (done) {
+        // two thirds of the units hold no finished env: one vote lets those warps BRANCH around the bookkeeping instead of
+        // issuing it predicated-off (the compiler's choice for a plain `if (done)`)
+        const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
+        if (done_mask != 0u) {                       // warp-uniform; the barrier keeps the compiler from predicating the block
+          __syncwarp();
+          if (done) {
           // rare lane: the ever-done flag decides the terminal reward (quadrotor3d.py:112-122)
           const uint32_t w = PREF ? word : a.episode[e];
           rew = reward_of(a.P, true, (w & kEverDone) != 0u, n_rew);
@@ -148,6 +153,7 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
             a.ep_start[e] = now;
             ep_ret = -rew;                          // becomes 0 after the "+ rew" below
           }
+          }
         }
         if (active) {
           __stcs(rew_t + e, scaled_reward(a.P, rew));
@@ -158,8 +164,8 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
             for (int c = 0; c < S; ++c) sp[c * kTile] = s[c];
           }
         }
-        // finished envs go to the warp's list (ballot + prefix popcount: no atomics)
-        const uint32_t mask = __ballot_sync(0xffffffffu, redraw);
+        // finished envs go to the warp's list (prefix popcount of the vote: no atomics)
+        const uint32_t mask = a.auto_reset ? done_mask : 0u;
         if (mask != 0u) {                            // warp-uniform
           if (redraw) list[pending + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = make_uint2(e, count);
           pending += (uint32_t)__popc(mask);
