@@ -68,7 +68,7 @@ class VecNormalize:
         obs, rew, done = self.step_tensor(self._act)
         self._act = None
         done_h = done.cpu().numpy().astype(bool)
-        infos = SparseInfos(self.num_envs, self.venv._finished(done_h) if self.venv.monitor else {})
+        infos = self.venv._finished(done_h) if self.venv.monitor else SparseInfos(self.num_envs)
         return obs.cpu().numpy(), rew.cpu().numpy(), done_h, infos
 
     def step(self, actions):

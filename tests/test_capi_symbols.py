@@ -69,6 +69,13 @@ def test_sparse_infos():
     assert [i.get("episode") for i in infos].count(None) == 4
     with pytest.raises(IndexError):
         infos[5]
+    # the lazy form the VecEnv builds: arrays of finished envs, dicts only for what is read
+    lazy = SparseInfos(8, idx=np.array([1, 6]), returns=np.array([-2.5, 4.0], np.float32), lengths=np.array([9, 3], np.uint32), t=0.25)
+    assert len(lazy) == 8 and lazy[0] == {} and lazy[6] == {"episode": {"r": 4.0, "l": 3, "t": 0.25}} and lazy[-7]["episode"]["l"] == 9
+    assert [bool(i) for i in lazy] == [False, True, False, False, False, False, True, False]
+    assert lazy.episodes() == {1: {"r": -2.5, "l": 9, "t": 0.25}, 6: {"r": 4.0, "l": 3, "t": 0.25}}
+    assert list(lazy.finished_indices()) == [1, 6] and lazy[1:3] == [lazy[1], {}]
+    assert len(SparseInfos(3)) == 3 and SparseInfos(3)[2] == {} and list(SparseInfos(2)) == [{}, {}]
 
 
 def test_undersized_buffers_are_refused_before_the_abi():
@@ -128,3 +135,34 @@ def test_auto_launch_shape_policy(capi):
     assert shape(capi.QUAD3D_SLUNG, small) == (128, 1) and shape(capi.QUAD3D_SLUNG, big) == (128, 1)
     assert shape(capi.QUAD3D_SLUNG, 1 << 16) == (128, 0)
     assert lib.rmv_launch_shape(capi.REINMAV, small, None, None) != 0
+
+
+def test_step_stream_shape_and_policy(capi):
+    """Device-free queries of the persistent step stream (DESIGN.md §3 "The step stream"): every warp owns the same number
+    of 32-env units and all of them are co-resident; small batches use one-warp CTAs; batches whose step streams several
+    hundred MB through HBM keep one launch per step."""
+    import ctypes
+    import os
+    lib = capi.lib()
+
+    def shape(n, sms=148, resident=64):
+        k, w, g, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert lib.rmv_stream_shape(n, sms, resident, ctypes.byref(k), ctypes.byref(w), ctypes.byref(g), ctypes.byref(b)) == 0
+        return k.value, w.value, g.value, b.value
+    assert shape(1 << 20) == (4, 8192, 2048, 128)            # 8192 warps x 4 units on 148 x 64 slots
+    assert shape(1 << 16) == (1, 2048, 2048, 32)             # one unit per warp, 32-thread CTAs spread over the SMs
+    assert shape(1 << 23) == (28, 9364, 2341, 128)
+    k, w, g, b = shape(17)
+    assert (k, w) == (1, 4) and g * b >= w * 32
+    for n in (1, 31, 33, 4095, 70001, (1 << 19) + 77):
+        k, w, g, b = shape(n)
+        units = (n + 31) // 32
+        assert w % 4 == 0 and k * w >= units and (k - 1) * w < units + 4 and g * b >= w * 32 and w <= 148 * 64 + 3
+    assert lib.rmv_stream_shape(0, 148, 64, None, None, None, None) != 0
+    if os.environ.get("RMV_NO_STREAM"):
+        pytest.skip("developer override set")
+    assert lib.rmv_stream_pays(capi.QUAD3D, 1 << 20) == 1 and lib.rmv_stream_pays(capi.QUAD3D, 1 << 21) == 1
+    assert lib.rmv_stream_pays(capi.QUAD3D, 1 << 22) == 0 and lib.rmv_stream_pays(capi.QUAD3D, 1 << 23) == 0
+    assert lib.rmv_stream_pays(capi.QUAD2D_SLUNG, 1 << 18) == 1 and lib.rmv_stream_pays(capi.QUAD2D_SLUNG, 1 << 20) == 0
+    assert lib.rmv_stream_pays(capi.QUAD2D, 1 << 22) == 1 and lib.rmv_stream_pays(capi.QUAD3D_SLUNG, 1 << 20) == 1
+    assert lib.rmv_stream_pays(capi.REINMAV, 1 << 10) == 0
