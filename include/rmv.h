@@ -159,9 +159,8 @@ RMV_API int rmv_set_prefetch(rmv_env* env, int mode);
  * streams do not fit L2 (+10-13 % measured); launches that also write observation rows do not use the window.
  * Results are identical. */
 RMV_API int rmv_set_l2_persist(rmv_env* env, int mode);
-/* number of equal chunks rmv_step_host pipelines a batch through (H2D | kernel | D2H overlap); 0 = auto: one chunk below
- * 65536 envs, else chunks that grow geometrically (n/32, n/32, n/16, ... n/2) so that the result copies — the critical
- * path — start after 1/32 of the input has arrived */
+/* number of chunks rmv_step_host pipelines a batch through (H2D | kernel | D2H overlap); 0 = auto
+ * (8 for n >= 65536, else 1) */
 RMV_API int rmv_set_host_chunks(rmv_env* env, int chunks);
 
 /* ---- state access (parity tests, checkpoint/resume, zero-copy views) --------------------- */

@@ -134,7 +134,6 @@ struct rmv_env {
 
 static int g_use_graph = (getenv("RMV_NO_GRAPH") == nullptr) ? 1 : 0;   // developer switch
 static int g_host_batch_small = getenv("RMV_HOST_BATCH_SMALL") ? atoi(getenv("RMV_HOST_BATCH_SMALL")) : 1;   // developer switch (A/B)
-static int g_host_geometric = getenv("RMV_HOST_GEOMETRIC") ? atoi(getenv("RMV_HOST_GEOMETRIC")) : 1;        // developer switch (A/B)
 static int g_use_stream = (getenv("RMV_NO_STREAM") == nullptr) ? 1 : 0; // developer switch: rmv_step_many(mode 0) falls back to launches
 static int g_force_stream = (getenv("RMV_FORCE_STREAM") != nullptr) ? 1 : 0; // developer switch: the stream at every size (sweeps)
 static int g_ctas_cap = getenv("RMV_CTAS_PER_SM") ? atoi(getenv("RMV_CTAS_PER_SM")) : 0;
@@ -1187,16 +1186,11 @@ extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float*
   if (rc) return rc;
   const int64_t n = env->n;
   const int S = env->S, A = env->A;
-  // Chunking.  The device -> host copies are the critical path (4S + 5 bytes per env going back against 4A coming in), and
-  // they cannot start before the first chunk's actions have arrived and its kernel has run: the pipeline's fill.  Auto
-  // (host_chunks == 0) therefore grows the chunks geometrically — n/32, n/32, n/16, n/8, n/4, n/2 — so the first result
-  // copy starts after ~1/32 of the input, and every later chunk's input (half the bytes per env) has landed before the
-  // result copy in front of it is through.  host_chunks > 0 cuts the batch into that many equal chunks.
-  int chunks = env->host_chunks > 0 ? env->host_chunks : (n >= (1 << 16) ? (g_host_geometric ? 6 : 8) : 1);
+  // Chunking: 8 equal chunks for large batches.  (Chunks that grow geometrically — n/32, n/32, n/16, ... n/2, to start the
+  // result copies earlier — measured no better: 1.02 against 1.00 ms per step at N = 2^20, profiles/README.md r2.)
+  int chunks = env->host_chunks > 0 ? env->host_chunks : (n >= (1 << 16) ? 8 : 1);
   if (env->A == 0) chunks = 1;
-  const bool geometric = env->host_chunks == 0 && chunks > 1 && g_host_geometric != 0;
-  int64_t per = geometric ? ((n + 31) / 32 + 1023) / 1024 * 1024
-                          : ((n + chunks - 1) / chunks + 1023) / 1024 * 1024;      // whole tiles, aligned for every vector width
+  int64_t per = ((n + chunks - 1) / chunks + 1023) / 1024 * 1024;      // whole tiles, aligned for every vector width
   if (per >= n) chunks = 1;
   // observation rows leave from the staging copy the kernel writes, or — on a row-state handle — from the state itself
   float* const obs_dev = env->rows ? nullptr : (obs_host ? env->h_obs : nullptr);
@@ -1222,9 +1216,8 @@ extern "C" RMV_API int rmv_step_host(rmv_env* env, const float* act_host, float*
   // their set-up overlaps the bulk copies instead of sitting between them.
   const bool batch_small = g_host_batch_small != 0 && obs_host != nullptr;
   int k = 0;
-  for (int64_t c0 = 0, cn = 0; c0 < n; c0 += cn, ++k) {
-    if (geometric && k >= 2) per *= 2;
-    cn = (n - c0 < per) ? n - c0 : per;
+  for (int64_t c0 = 0; c0 < n; c0 += per, ++k) {
+    const int64_t cn = (n - c0 < per) ? n - c0 : per;
     cudaStream_t ps = env->pipe[k % 3];
     RMV_CUDA(cudaMemcpyAsync(env->h_act + c0 * A, act_host + c0 * A, (size_t)cn * A * sizeof(float), cudaMemcpyHostToDevice, ps));
     rc = launch_step(env, env->h_act + c0 * A, RMV_ACT_AOS, 0, 0, env->h_rew + c0, env->h_done + c0, cn,
