@@ -247,8 +247,10 @@ RMV_API int rmv_last_variant(const rmv_env* env, int* variant);
 /* 1 if rmv_step_many(RMV_MANY_STREAM) runs the stream kernel for n_envs of `kind`, 0 if it issues launches (device-free) */
 RMV_API int rmv_stream_pays(int kind, int64_t n_envs);
 /* Tuning of the step-stream kernel (sweeps): warps_per_sm caps the resident warps per SM (0 = as many as fit);
- * block = threads per CTA (0 auto, 32, 64, 128 — a CTA is only a scheduling unit of this kernel).  Results are identical. */
-RMV_API int rmv_set_stream(rmv_env* env, int warps_per_sm, int block);
+ * block = threads per CTA (0 auto, 32, 64, 128 — a CTA is only a scheduling unit of this kernel); action_prefetch = fetch
+ * the warp's NEXT action row while the current unit is computed (-1 auto: on for small batches, 0, 1; row-per-env actions
+ * only).  Results are identical. */
+RMV_API int rmv_set_stream(rmv_env* env, int warps_per_sm, int block, int action_prefetch);
 /* the shape the stream kernel takes for n_envs on a device with `sms` SMs and room for `resident_warps_per_sm` of its
  * warps per SM (device-free query): every warp owns units_per_warp 32-env units (the last few one less), `warps`
  * warps (a multiple of 4) own work, launched as grid x block threads. */

@@ -115,6 +115,7 @@ struct rmv_env {
   int use_tma = 0;         // 1: TMA-pipelined persistent step kernel where it applies
   int stream_warps_per_sm = 0;   // 0 = as many as fit; else cap on resident warps per SM (sweeps)
   int stream_block = 0;    // 0 = auto; else 32, 64 or 128 threads per CTA of the stream kernel
+  int stream_apre = -1;    // -1 auto, 0 / 1: fetch the warp's next action while the current unit is computed
   // rmv_step_many(fused = 0): the K single-step launches of a repeated call are captured once in a CUDA graph and replayed
   struct StepGraph {
     int n_steps = 0, layout = 0;
@@ -345,8 +346,10 @@ extern "C" RMV_API int rmv_set_kernel(rmv_env* env, int use_tma, int ctas_per_sm
   return RMV_OK;
 }
 
-extern "C" RMV_API int rmv_set_stream(rmv_env* env, int warps_per_sm, int block) {
+extern "C" RMV_API int rmv_set_stream(rmv_env* env, int warps_per_sm, int block, int action_prefetch) {
   RMV_REQUIRE(env != nullptr, "env is NULL");
+  RMV_REQUIRE(action_prefetch >= -1 && action_prefetch <= 1, "action_prefetch must be -1 (auto), 0 or 1");
+  env->stream_apre = action_prefetch;
   RMV_REQUIRE(warps_per_sm >= 0 && warps_per_sm <= 64, "warps_per_sm must be in [0, 64] (0 = as many as fit)");
   RMV_REQUIRE(block == 0 || block == 32 || block == 64 || block == 128, "block must be 0 (auto), 32, 64 or 128");
   env->stream_warps_per_sm = warps_per_sm; env->stream_block = block;
@@ -794,13 +797,15 @@ extern "C" RMV_API int rmv_stream_shape(int64_t n_envs, int sms, int resident_wa
   return RMV_OK;
 }
 
-template <int KIND, bool TRACK, bool PREF, bool CTRL = false>
+static int g_stream_apre = getenv("RMV_STREAM_APRE") ? atoi(getenv("RMV_STREAM_APRE")) : -1;   // developer switch: -1 = by shape
+
+template <int KIND, bool TRACK, bool PREF, bool CTRL = false, bool APRE = false>
 static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_t st) {
   static int resident_of[kMaxDevices] = {}, sms_of[kMaxDevices] = {};      // per instantiation and per device
   const int dev = current_device();
   if (resident_of[dev] == 0) {
     cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_stream<KIND, TRACK, PREF, CTRL>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_stream<KIND, TRACK, PREF, CTRL, APRE>, 128, 0);
     if (resident_of[dev] < 1) resident_of[dev] = 1;
     if (sms_of[dev] < 1) sms_of[dev] = 1;
   }
@@ -827,7 +832,7 @@ static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, k_step_stream<KIND, TRACK, PREF, CTRL>, args, shape);
+  return cudaLaunchKernelEx(&cfg, k_step_stream<KIND, TRACK, PREF, CTRL, APRE>, args, shape);
 }
 
 // quadrotor3d, two envs per thread on the packed float32 pipe (k_step_stream_pair)
@@ -871,6 +876,14 @@ static cudaError_t launch_stream_k(rmv_env* e, const StepArgs& args, cudaStream_
   }
   if (ctrl) return track ? launch_stream_t<KIND, true, false, true>(e, args, st) : launch_stream_t<KIND, false, false, true>(e, args, st);
   const bool pref = e->prefetch >= 0 ? e->prefetch != 0 : default_prefetch(KIND, args.n);
+  // action prefetch (APRE): row-per-env actions, at most two units per warp (small batches: occupancy is not the constraint)
+  bool apre = !args.act_soa && args.n <= (int64_t)148 * 2048 * 2;
+  if (g_stream_apre >= 0) apre = !args.act_soa && g_stream_apre != 0;
+  if (e->stream_apre >= 0) apre = !args.act_soa && e->stream_apre != 0;
+  if (apre) {
+    if (track) return pref ? launch_stream_t<KIND, true, true, false, true>(e, args, st) : launch_stream_t<KIND, true, false, false, true>(e, args, st);
+    return pref ? launch_stream_t<KIND, false, true, false, true>(e, args, st) : launch_stream_t<KIND, false, false, false, true>(e, args, st);
+  }
   if (track) return pref ? launch_stream_t<KIND, true, true>(e, args, st) : launch_stream_t<KIND, true, false>(e, args, st);
   return pref ? launch_stream_t<KIND, false, true>(e, args, st) : launch_stream_t<KIND, false, false>(e, args, st);
 }

@@ -64,8 +64,13 @@ __device__ __forceinline__ void stream_redraw(const StepArgs& a, uint32_t pairs,
   }
 }
 
-template <int KIND, bool TRACK, bool PREF, bool CTRL = false>
-__global__ void __launch_bounds__(128, CTRL ? 8 : stream_min_ctas(KIND, TRACK))
+// APRE (row-per-env actions only): the action of the warp's NEXT work item — its next unit of this step, or its first
+// unit of the next step — is fetched while the current unit is computed.  Actions stream from HBM (nothing else in a
+// unit does at L2-resident sizes), so at small batches, where a warp has one unit and little company on its SM, that
+// load is the longest wait of every step; the state cannot run ahead the same way (with one unit per warp the next item
+// reads what this one writes).  Costs A registers: used where occupancy is not the constraint (k <= 2).
+template <int KIND, bool TRACK, bool PREF, bool CTRL = false, bool APRE = false>
+__global__ void __launch_bounds__(128, CTRL ? 8 : (APRE ? 12 : stream_min_ctas(KIND, TRACK)))
 k_step_stream(const StepArgs a, const StreamShape shape) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   constexpr int NB = (S + 3) / 4;
@@ -98,6 +103,14 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
   float* rew_t = a.reward;
   unsigned char* done_t = reinterpret_cast<unsigned char*>(a.done);
   uint32_t now = a.step_index;
+  float act_next[A];
+  if constexpr (APRE) {                              // the first item's action
+    if (e_first < n) load_contig_stream<A>(act_t + (size_t)(e_first * (uint32_t)A), act_next);
+    else {
+#pragma unroll
+      for (int c = 0; c < A; ++c) act_next[c] = 0.0f;
+    }
+  }
   for (uint32_t t = 0; t < T; ++t, act_t += a.act_step_stride, rew_t += a.out_ld, done_t += a.out_ld) {
     if (t + 1u == T) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next launch may become resident as we drain
     ++now;
@@ -116,6 +129,14 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
         if constexpr (CTRL) {                        // closed loop: the reference's controller on the state just loaded
           control_law<KIND>(a.C, s, act);
           if (a.act_out && active) store_action_row<A>(a.act_out + (size_t)t * a.act_step_stride + (size_t)(e * (uint32_t)A), act);
+        } else if constexpr (APRE) {
+#pragma unroll
+          for (int c = 0; c < A; ++c) act[c] = act_next[c];
+          // next item: this warp's next unit of this step if it exists, else its first unit of the next step
+          const bool same_step = (j + 1u < K) && (e + de < limit);
+          const uint32_t en = same_step ? e + de : e_first;
+          const float* const an = same_step ? act_t : act_t + a.act_step_stride;
+          if ((same_step || t + 1u < T) && en < n) load_contig_stream<A>(an + (size_t)(en * (uint32_t)A), act_next);
         } else if (a.act_soa) {
 #pragma unroll
           for (int c = 0; c < A; ++c) act[c] = active ? __ldcs(act_t + (size_t)c * a.act_ld + e) : 0.0f;

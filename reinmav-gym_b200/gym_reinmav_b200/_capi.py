@@ -74,7 +74,7 @@ SIGNATURES = {
     "rmv_step": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp]),
     "rmv_step_rows": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _vp]),
     "rmv_step_many": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp, _i64, _i, _vp]),
-    "rmv_set_stream": (_i, [_vp, _i, _i]),
+    "rmv_set_stream": (_i, [_vp, _i, _i, _i]),
     "rmv_stream_shape": (_i, [_i64, _i, _i, _pi, _pi, _pi, _pi]),
     "rmv_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rmv_reset_host": (_i, [_vp, _vp, _vp]),

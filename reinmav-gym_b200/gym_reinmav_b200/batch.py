@@ -180,9 +180,9 @@ class QuadBatch:
         """L2 access-policy window on the state (state stays L2-resident between steps): -1 auto, 0 off, 1 on."""
         check(lib().rmv_set_l2_persist(self._h, int(mode)))
 
-    def set_stream(self, warps_per_sm=0, block=0):
+    def set_stream(self, warps_per_sm=0, block=0, action_prefetch=-1):
         """Tuning of the step-stream kernel behind ``step_many(fused=0)``; results are identical."""
-        check(lib().rmv_set_stream(self._h, int(warps_per_sm), int(block)))
+        check(lib().rmv_set_stream(self._h, int(warps_per_sm), int(block), int(action_prefetch)))
 
     def set_host_chunks(self, chunks=0):
         check(lib().rmv_set_host_chunks(self._h, int(chunks)))

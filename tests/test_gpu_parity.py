@@ -212,12 +212,15 @@ def test_fused_rollout_equals_single_steps(torch, rmv, env_id, vec):
 
 
 STREAM_CASES = [
-    # n, warps_per_sm cap, block, track, layout      (148 SMs: cap 1 -> 148 warps own everything)
-    (128 * 41 + 18, 0, 0, True, "aos"),              # one unit per warp, ragged last unit, small-batch CTA size
-    (20000 + 5, 1, 32, False, "soa"),                # 5 units per warp (the last few warps own 4), 1-warp CTAs
-    (20000 + 5, 2, 128, True, "aos"),                # 3 units per warp
-    (17, 0, 0, False, "aos"),                        # less than one unit
-    ((1 << 19) + 77, 0, 0, False, "aos"),            # more units than resident warps: k = 2 at full occupancy
+    # n, warps_per_sm cap, block, track, layout, action prefetch     (148 SMs: cap 1 -> 148 warps own everything)
+    (128 * 41 + 18, 0, 0, True, "aos", -1),          # one unit per warp, ragged last unit, small-batch CTA size, auto (prefetch on)
+    (128 * 41 + 18, 0, 0, False, "aos", 0),          # the same without the action prefetch
+    (20000 + 5, 1, 32, False, "soa", -1),            # 5 units per warp (the last few warps own 4), 1-warp CTAs
+    (20000 + 5, 2, 128, True, "aos", 1),             # 3 units per warp, next action from the next unit / the next step
+    (20000 + 5, 2, 128, True, "aos", 0),
+    (17, 0, 0, False, "aos", 1),                     # less than one unit
+    ((1 << 19) + 77, 0, 0, False, "aos", -1),        # more units than resident warps: k >= 2 at full occupancy
+    ((1 << 19) + 77, 0, 0, False, "aos", 0),
 ]
 
 
@@ -229,7 +232,7 @@ def test_step_stream_bitwise(torch, rmv, env_id, case):
     kernel — state, rewards, done flags, episode words and episode statistics bit for bit; two consecutive calls (the
     second starts from the first one's state), wide initial states (a third of the envs finish at once: the per-warp
     re-draw list overflows and is flushed mid-step), every ownership shape."""
-    n, cap, block, track, layout = STREAM_CASES[case]
+    n, cap, block, track, layout, apre = STREAM_CASES[case]
     kind = KIND_OF_ID[env_id]
     S, A = STATE_DIM[kind], ACTION_DIM[kind]
     lo, hi = ACTION_BOUNDS[kind]
@@ -250,7 +253,7 @@ def test_step_stream_bitwise(torch, rmv, env_id, case):
     out = []
     for mode in (2, 0):                           # RMV_MANY_LAUNCHES, RMV_MANY_STREAM
         b = rmv.QuadBatch(env_id, n, seed=seed, track_episodes=track)
-        b.set_stream(warps_per_sm=cap, block=block)
+        b.set_stream(warps_per_sm=cap, block=block, action_prefetch=apre)
         b.reset()
         b.set_state(start)
         rew = torch.empty((2, T, n), dtype=torch.float32, device=dev)

@@ -16,12 +16,12 @@ BOUNDS = {"quadrotor2d-v0": (-10, 10), "quadrotor2d-slungload-v0": (-10, 10), "q
 
 
 def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, ctas=0, obs=0, track=0, l2=0, rows=0,
-             warps=0, sblock=0):
+             warps=0, sblock=0, apre=-1):
     dev = "cuda:0"
     b = rmv.QuadBatch(env_id, n, seed=0, track_episodes=bool(track))
     b.set_tuning(vec=vec, block=block)
     b.set_kernel(tma=bool(tma), ctas_per_sm=ctas)
-    b.set_stream(warps_per_sm=warps, block=sblock)
+    b.set_stream(warps_per_sm=warps, block=sblock, action_prefetch=apre)
     if l2:
         try:
             b.set_l2_persist(1)
@@ -102,6 +102,7 @@ def main():
     ap.add_argument("--layout", default="soa,aos")
     ap.add_argument("--fused", default="0", help="comma list of rmv_step_many modes: 0 = step stream, 1 = rollout in registers, 2 = one launch per step")
     ap.add_argument("--warps", default="0", help="comma list: step-stream resident warps per SM cap (0 = all that fit)")
+    ap.add_argument("--apre", default="-1", help="comma list: step-stream action prefetch (-1 auto, 0, 1)")
     ap.add_argument("--sblock", default="0", help="comma list: step-stream threads per CTA (0 auto, 32, 64, 128)")
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--ring", type=int, default=16)
@@ -123,11 +124,12 @@ def main():
                             ring = max(2, min(args.ring, int(6e9 // (n * 4 * 6))))
                             for tma in (int(x) for x in args.tma.split(",")):
                                 for ctas in (int(x) for x in args.ctas.split(",")) if tma else (0,):
-                                    stream_cfgs = [(w_, sb_) for w_ in (int(x) for x in args.warps.split(","))
-                                                   for sb_ in (int(x) for x in args.sblock.split(","))] if fused == 0 else [(0, 0)]
-                                    for warps, sblock in stream_cfgs:
-                                        us, sps, gbs, frac = time_cfg(env_id, n, vec, block, layout, fused, args.steps, ring, args.peak, tma, ctas, args.obs, args.track, args.l2, args.rows, warps, sblock)
-                                        print("%-26s %9d %3d %5d %4s %5d %9.2f %11.4g %9.1f %6.3f  tma=%d ctas=%d obs=%d track=%d l2=%d rows=%d warps=%d sblock=%d" % (env_id, n, vec, block, layout, fused, us, sps, gbs, frac, tma, ctas, args.obs, args.track, args.l2, args.rows, warps, sblock), flush=True)
+                                    stream_cfgs = [(w_, sb_, ap_) for w_ in (int(x) for x in args.warps.split(","))
+                                                   for sb_ in (int(x) for x in args.sblock.split(","))
+                                                   for ap_ in (int(x) for x in args.apre.split(","))] if fused == 0 else [(0, 0, -1)]
+                                    for warps, sblock, apre in stream_cfgs:
+                                        us, sps, gbs, frac = time_cfg(env_id, n, vec, block, layout, fused, args.steps, ring, args.peak, tma, ctas, args.obs, args.track, args.l2, args.rows, warps, sblock, apre)
+                                        print("%-26s %9d %3d %5d %4s %5d %9.2f %11.4g %9.1f %6.3f  tma=%d ctas=%d obs=%d track=%d l2=%d rows=%d warps=%d sblock=%d apre=%d" % (env_id, n, vec, block, layout, fused, us, sps, gbs, frac, tma, ctas, args.obs, args.track, args.l2, args.rows, warps, sblock, apre), flush=True)
 
 
 if __name__ == "__main__":
