@@ -876,8 +876,9 @@ static cudaError_t launch_stream_k(rmv_env* e, const StepArgs& args, cudaStream_
   }
   if (ctrl) return track ? launch_stream_t<KIND, true, false, true>(e, args, st) : launch_stream_t<KIND, false, false, true>(e, args, st);
   const bool pref = e->prefetch >= 0 ? e->prefetch != 0 : default_prefetch(KIND, args.n);
-  // action prefetch (APRE): row-per-env actions, at most two units per warp (small batches: occupancy is not the constraint)
-  bool apre = !args.act_soa && args.n <= (int64_t)148 * 2048 * 2;
+  // action prefetch (APRE): row-per-env actions, small batches (one unit per warp, at most 32 warps per SM: the action row is
+  // the one load of a unit that comes from HBM, and nothing hides it there) — profiles/r2_sweep_stream_apre.txt
+  bool apre = !args.act_soa && args.n <= (int64_t)148 * 32 * 32;
   if (g_stream_apre >= 0) apre = !args.act_soa && g_stream_apre != 0;
   if (e->stream_apre >= 0) apre = !args.act_soa && e->stream_apre != 0;
   if (apre) {

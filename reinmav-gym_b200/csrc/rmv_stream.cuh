@@ -37,11 +37,12 @@ struct StreamShape {
 constexpr int kStreamWarps = 4;       // warps per CTA at most (the launch may use fewer: a CTA is only a scheduling unit)
 constexpr int kStreamList = 64;       // per-warp re-draw list: flushed when more than 32 entries are pending
 
-constexpr int stream_min_ctas(int kind, bool track) {
-  // CTAs of 128 threads per SM: 16 = 2048 threads (<= 32 registers), 12 = 1536 (<= 40), 10 = 1280 (<= 48)
-  if (kind == QUAD3D_SLUNG) return 10;
-  if (kind == QUAD2D_SLUNG) return 12;
-  return track ? 12 : 16;
+constexpr int stream_min_ctas(int kind, bool track, bool apre = false) {
+  // CTAs of 128 threads per SM: 16 = 2048 threads (<= 32 registers), 12 = 1536 (<= 40), 10 = 1280 (<= 48), 8 = 1024 (<= 64).
+  // The action prefetch keeps A more values live: one step down (it is used where occupancy is not the constraint).
+  const int base = (kind == QUAD3D_SLUNG) ? 10 : (kind == QUAD2D_SLUNG ? 12 : (track ? 12 : 16));
+  if (!apre) return base;
+  return base == 16 ? 12 : (base == 12 ? 10 : 8);
 }
 
 // re-draw `pairs / NB` finished envs: pair i = (entry i / NB, Philox block i % NB), pairs idx0, idx0 + stride, ...
@@ -70,7 +71,7 @@ __device__ __forceinline__ void stream_redraw(const StepArgs& a, uint32_t pairs,
 // load is the longest wait of every step; the state cannot run ahead the same way (with one unit per warp the next item
 // reads what this one writes).  Costs A registers: used where occupancy is not the constraint (k <= 2).
 template <int KIND, bool TRACK, bool PREF, bool CTRL = false, bool APRE = false>
-__global__ void __launch_bounds__(128, CTRL ? 8 : (APRE ? 12 : stream_min_ctas(KIND, TRACK)))
+__global__ void __launch_bounds__(128, CTRL ? 8 : stream_min_ctas(KIND, TRACK, APRE))
 k_step_stream(const StepArgs a, const StreamShape shape) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   constexpr int NB = (S + 3) / 4;
