@@ -8,6 +8,7 @@
 // hold 1e-5 against the reference over the 20 000 substeps of its own 4 s test trajectory.
 #pragma once
 #include "rmv_kernels.cuh"
+#include "rmv_f64.cuh"
 
 namespace rmv {
 
@@ -25,78 +26,98 @@ struct ReinmavArgs {
 constexpr int kReinmavS = 13;
 constexpr int kReinmavMaxSub = 64;     // np.arange(t, t + 0.01, 1/5000) has 50 or 51 elements
 
+constexpr double kRmArm = 0.0860, kRmMass = 0.1800, kRmGrav = 9.8100, kRmMaxF = 3.5316;   // reinmav_env.py:55-59 (MIN_F = 0)
+#define RMV_REINMAV_GAINS const double kRmKp[3] = {10.0, 10.0, 35.0}, kRmKd[3] = {5.0, 5.0, 22.0}   /* controller gains (:311-312) */
+constexpr double kRmKpRot = 100.0, kRmKdRot = 0.1;                                // (:313-314)
+constexpr double kRmMix = 0.5 / kRmArm;                                           // moment -> thrust difference (:204-212)
+
 // What every env shares at one substep: the quintic reference trajectory (trj_gen, reinmav_env.py:128-136) and
 // sin/cos of the desired yaw (controller, :306-337) depend on the clock only, so a CTA evaluates them once per
-// substep into shared memory instead of every thread doing it 50 times.
+// substep into shared memory instead of every thread doing it 50 times — together with every product of a gain and a
+// reference value, so that a thread's share of the PD laws is one fused multiply-add per state component:
+//   ddr_i = d_acc + kd_i (d_vel - v_i) + kp_i (d_pos - x_i)            = acc0[i] - kd_i v_i - kp_i x_i
+//   k mx  = k (100 (phi_des - phi) - 0.1 p),  phi_des = (ddr_0 sp - ddr_1 cp) / g
+//                                                                       = ddr_0 sp_k - ddr_1 cp_k - 100 k phi - 0.1 k p
+//   mz    = 100 (d_pos - psi) + 0.1 (d_vel - r)                        = mz0 - 100 psi - 0.1 r
+// (k = 0.5 / arm, the motor-mixing factor; sp_k = 100 k sin(psi_des) / g).  The regrouping moves results at the
+// 1e-16 level (see reinmav_derivative).
 struct ReinmavRef {
-  double d_pos, d_vel, d_acc, sp, cp;
+  double acc0[3], sp_k, cp_k, mz0;
 };
 __device__ __forceinline__ ReinmavRef reinmav_reference(double t) {
   ReinmavRef r;
+  RMV_REINMAV_GAINS;
   const double tau = fmax(0.0, fmin(t, 4.0)) / 4.0;
   const double tau2 = tau * tau, tau3 = tau2 * tau, tau4 = tau3 * tau, tau5 = tau4 * tau;
-  r.d_pos = 10.0 * tau3 - 15.0 * tau4 + 6.0 * tau5;
-  r.d_vel = (30 / 4.0) * tau2 - (60 / 4.0) * tau3 + (30 / 4.0) * tau4;
-  r.d_acc = (60 / 16.0) * tau - (180 / 16.0) * tau2 + (120 / 16.0) * tau3;
-  sincos(r.d_pos, &r.sp, &r.cp);                             // psi_des = desired yaw = d_pos
+  const double d_pos = 10.0 * tau3 - 15.0 * tau4 + 6.0 * tau5;
+  const double d_vel = (30 / 4.0) * tau2 - (60 / 4.0) * tau3 + (30 / 4.0) * tau4;
+  const double d_acc = (60 / 16.0) * tau - (180 / 16.0) * tau2 + (120 / 16.0) * tau3;
+  double sp, cp;
+  sincos(d_pos, &sp, &cp);                                   // psi_des = desired yaw = d_pos
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r.acc0[i] = d_acc + kRmKd[i] * d_vel + kRmKp[i] * d_pos;
+  r.sp_k = kRmKpRot * kRmMix * (1 / kRmGrav * sp);
+  r.cp_k = kRmKpRot * kRmMix * (1 / kRmGrav * cp);
+  r.mz0 = kRmKpRot * d_pos + kRmKdRot * d_vel;
   return r;
 }
 
+// The arithmetic below is the reference's, regrouped and contracted by hand into fused multiply-adds (the library is
+// compiled with --fmad=false for the float32 step kernels, and this kernel is bound by the FP64 pipe: a DMUL + DADD
+// pair costs twice a DFMA).  That changes results at the 1e-16 level; reinmav-v0 is held to 1e-5 against the
+// reference and 2e-6 against the float64 oracle with the same float32 storage rule (tests/test_reinmav.py).
 __device__ __forceinline__ void reinmav_derivative(const double (&s)[13], const ReinmavRef& ref, const double (&invI)[9],
                                                    double (&ds)[13]) {
-  constexpr double ARM = 0.0860, MASS = 0.1800, GRAV = 9.8100, MIN_F = 0.0, MAX_F = 3.5316;   // reinmav_env.py:55-59
+  RMV_REINMAV_GAINS;
   constexpr double I00 = 0.00025, I02 = 2.55e-06, I11 = 0.000232, I20 = 2.55e-06, I22 = 0.0003738;   // :60-62
   const double qw = s[6], qx = s[7], qy = s[8], qz = s[9], p = s[10], q = s[11], r = s[12];
   // quat2mat (:267-290); only the entries the controller and the force projection read
-  const double nq = qw * qw + qx * qx + qy * qy + qz * qz;
+  const double nq = ::fma(qz, qz, ::fma(qy, qy, ::fma(qx, qx, qw * qw)));
   double R02 = 0.0, R10 = 0.0, R11 = 1.0, R12 = 0.0, R20 = 0.0, R21 = 0.0, R22 = 1.0;
   if (nq > 2.220446049250313e-16) {
-    const double sc = 2.0 / nq;
+    const double sc = normal_range(nq) ? div_newton(2.0, nq) : 2.0 / nq;
     const double X = qx * sc, Y = qy * sc, Z = qz * sc;
-    const double wX = qw * X, wY = qw * Y, wZ = qw * Z, xX = qx * X, xY = qx * Y, xZ = qx * Z;
-    const double yY = qy * Y, yZ = qy * Z, zZ = qz * Z;
-    R02 = xZ + wY;
-    R10 = xY + wZ; R11 = 1.0 - (xX + zZ); R12 = yZ - wX;
-    R20 = xZ - wY; R21 = yZ + wX; R22 = 1.0 - (xX + yY);
+    const double xX = qx * X, xY = qx * Y, xZ = qx * Z, yZ = qy * Z;
+    R02 = ::fma(qw, Y, xZ);
+    R10 = ::fma(qw, Z, xY); R11 = 1.0 - ::fma(qz, Z, xX); R12 = ::fma(-qw, X, yZ);
+    R20 = ::fma(-qw, Y, xZ); R21 = ::fma(qw, X, yZ); R22 = 1.0 - ::fma(qy, Y, xX);
   }
   // RotToRPY (:341-346): phi = asin(R12), psi = atan2(-R10/cos(phi), R11/cos(phi)), theta = atan2(-R02/cos(phi),
   // R22/cos(phi)).  cos(asin(x)) = sqrt(1 - x^2) > 0 for |x| < 1, and atan2 is invariant under a common positive
   // factor, so the two divisions and the cosine are not evaluated (differences at the 1e-16 level, far inside the
-  // stated 1e-5; at |R12| = 1 the reference itself divides by zero).
-  const double phi = asin(R12);
-  const double psi = atan2(-R10, R11);
-  const double theta = atan2(-R02, R22);
-  // controller (:306-337)
-  const double kp[3] = {10.0, 10.0, 35.0}, kd[3] = {5.0, 5.0, 22.0};
+  // stated 1e-5; at |R12| = 1 the reference itself divides by zero).  asin_f64 / atan2_f64 (rmv_f64.cuh): double
+  // accuracy at a quarter of the library versions' FP64 instructions.
+  const double phi = asin_f64(R12);
+  const double psi = atan2_f64(-R10, R11);
+  const double theta = atan2_f64(-R02, R22);
+  // controller (:306-337) and motor mixing + clamp (:204-216)
   double ddr[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) ddr[i] = ref.d_acc + kd[i] * (ref.d_vel - s[3 + i]) + kp[i] * (ref.d_pos - s[i]);
-  const double u1 = MASS * (GRAV + ddr[2]);
-  const double phi_des = 1 / GRAV * (ddr[0] * ref.sp - ddr[1] * ref.cp);
-  const double theta_des = 1 / GRAV * (ddr[0] * ref.cp + ddr[1] * ref.sp);
-  const double mx = 100.0 * (phi_des - phi) - 0.1 * p;
-  const double my = 100.0 * (theta_des - theta) - 0.1 * q;
-  const double mz = 100.0 * (ref.d_pos - psi) + 0.1 * (ref.d_vel - r);
-  // motor mixing + clamp (:204-216)
-  const double k = 0.5 / ARM;
-  double T[4] = {0.25 * u1 - k * my, 0.25 * u1 + k * mx, 0.25 * u1 + k * my, 0.25 * u1 - k * mx};
+  for (int i = 0; i < 3; ++i) ddr[i] = ::fma(-kRmKp[i], s[i], ::fma(-kRmKd[i], s[3 + i], ref.acc0[i]));
+  const double u4 = ::fma(0.25 * kRmMass, ddr[2], 0.25 * kRmMass * kRmGrav);             // u1 / 4, u1 = m (g + ddr_z)
+  const double kmx = ::fma(-kRmKpRot * kRmMix, phi, ::fma(-kRmKdRot * kRmMix, p, ::fma(ddr[0], ref.sp_k, -(ddr[1] * ref.cp_k))));
+  const double kmy = ::fma(-kRmKpRot * kRmMix, theta, ::fma(-kRmKdRot * kRmMix, q, ::fma(ddr[0], ref.cp_k, ddr[1] * ref.sp_k)));
+  const double mz = ::fma(-kRmKpRot, psi, ::fma(-kRmKdRot, r, ref.mz0));
+  double T[4] = {u4 - kmy, u4 + kmx, u4 + kmy, u4 - kmx};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) T[i] = fmax(fmin(T[i], MAX_F / 4.0), MIN_F / 4.0);
-  const double force = T[0] + T[1] + T[2] + T[3];
-  const double mom[3] = {ARM * T[1] - ARM * T[3], -ARM * T[0] + ARM * T[2], mz};
+  for (int i = 0; i < 4; ++i) T[i] = clamp_zero_to(T[i], kRmMaxF / 4.0);      // np.clip(T, MIN_F / 4 = 0, MAX_F / 4)
+  const double fm = (1.0 / kRmMass) * (T[0] + T[1] + T[2] + T[3]);                        // force / mass
   ds[0] = s[3]; ds[1] = s[4]; ds[2] = s[5];
-  ds[3] = 1.0 / MASS * (R20 * force);
-  ds[4] = 1.0 / MASS * (R21 * force);
-  ds[5] = 1.0 / MASS * (R22 * force - MASS * GRAV);
-  const double err = 1 - nq;
-  ds[6] = -0.5 * (-p * qx - q * qy - r * qz) + 2.0 * err * qw;
-  ds[7] = -0.5 * (p * qw - r * qy + q * qz) + 2.0 * err * qx;
-  ds[8] = -0.5 * (q * qw + r * qx - p * qz) + 2.0 * err * qy;
-  ds[9] = -0.5 * (r * qw - q * qx + p * qy) + 2.0 * err * qz;
-  const double Iw[3] = {I00 * p + I02 * r, I11 * q, I20 * p + I22 * r};
-  const double rhs[3] = {mom[0] - (q * Iw[2] - r * Iw[1]), mom[1] - (r * Iw[0] - p * Iw[2]), mom[2] - (p * Iw[1] - q * Iw[0])};
+  ds[3] = R20 * fm;
+  ds[4] = R21 * fm;
+  ds[5] = ::fma(R22, fm, -kRmGrav);
+  const double err2 = 2.0 * (1 - nq), hp = 0.5 * p, hq = 0.5 * q, hr = 0.5 * r;
+  ds[6] = ::fma(hr, qz, ::fma(hq, qy, ::fma(hp, qx, err2 * qw)));
+  ds[7] = ::fma(-hq, qz, ::fma(hr, qy, ::fma(-hp, qw, err2 * qx)));
+  ds[8] = ::fma(hp, qz, ::fma(-hr, qx, ::fma(-hq, qw, err2 * qy)));
+  ds[9] = ::fma(-hp, qy, ::fma(hq, qx, ::fma(-hr, qw, err2 * qz)));
+  const double Iw[3] = {::fma(I02, r, I00 * p), I11 * q, ::fma(I22, r, I20 * p)};
+  // moments minus omega x (I omega)
+  const double rhs[3] = {::fma(-q, Iw[2], ::fma(r, Iw[1], kRmArm * (T[1] - T[3]))),
+                         ::fma(-r, Iw[0], ::fma(p, Iw[2], kRmArm * (T[2] - T[0]))),
+                         ::fma(-p, Iw[1], ::fma(q, Iw[0], mz))};
 #pragma unroll
-  for (int i = 0; i < 3; ++i) ds[10 + i] = invI[3 * i] * rhs[0] + invI[3 * i + 1] * rhs[1] + invI[3 * i + 2] * rhs[2];
+  for (int i = 0; i < 3; ++i) ds[10 + i] = ::fma(invI[3 * i + 2], rhs[2], ::fma(invI[3 * i + 1], rhs[1], invI[3 * i] * rhs[0]));
 }
 
 __global__ void __launch_bounds__(128) k_reinmav_step(const ReinmavArgs a) {
@@ -115,7 +136,7 @@ __global__ void __launch_bounds__(128) k_reinmav_step(const ReinmavArgs a) {
   for (int i = 0; i < a.n_sub; ++i) {
     reinmav_derivative(s, ref[i], invI, ds);
 #pragma unroll
-    for (int c = 0; c < 13; ++c) s[c] = s[c] + h * ds[c];
+    for (int c = 0; c < 13; ++c) s[c] = ::fma(h, ds[c], s[c]);
   }
 #pragma unroll
   for (int c = 0; c < 13; ++c) {

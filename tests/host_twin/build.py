@@ -9,8 +9,9 @@ OUT = os.path.join(HERE, "libtwin.so")
 
 def build(force=False):
     src = os.path.join(HERE, "twin.cpp")
-    hdr = os.path.join(ROOT, "reinmav-gym_b200", "csrc", "rmv_math.cuh")
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    csrc = os.path.join(ROOT, "reinmav-gym_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, h) for h in ("rmv_math.cuh", "rmv_f64.cuh")]
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
         return OUT
     cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
            "-x", "c++", src, "-I", os.path.join(ROOT, "reinmav-gym_b200", "csrc"),

@@ -3,6 +3,7 @@
 // equals the NumPy float32 model (oracle/batch.py, dtype=float32) bit for bit.
 // Built by tests/host_twin/build.py with  g++ -O2 -ffp-contract=off -fno-fast-math.
 #include "rmv_math.cuh"
+#include "rmv_f64.cuh"
 #include "rmv.h"
 #include <string.h>
 
@@ -115,4 +116,12 @@ extern "C" int twin_control(int kind, const float* ctrl, long n, const float* s_
     default: return -1;
   }
   return 0;
+}
+
+// float64 asin / atan2 of k_reinmav_step (rmv_f64.cuh)
+extern "C" void twin_atan2_f64(long n, const double* y, const double* x, double* out) {
+  for (long i = 0; i < n; ++i) out[i] = atan2_f64(y[i], x[i]);
+}
+extern "C" void twin_asin_f64(long n, const double* x, double* out) {
+  for (long i = 0; i < n; ++i) out[i] = asin_f64(x[i]);
 }

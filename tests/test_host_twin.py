@@ -161,3 +161,38 @@ def test_control_law_bitwise_and_within_1e5_of_float64(host_twin, env_id):
         # states in 2e5 land above 1e-5 (worst 3.8e-5).  That is float32 itself, not the pinned atan2 (<= 2.8e-7).
         assert err[finite].max() <= 1e-4, err[finite].max()
         assert np.quantile(err[finite], 0.9999) <= 5e-6 and (err[finite] > 1e-5).sum() <= 4
+
+
+def test_float64_asin_atan2_of_reinmav_match_libm(host_twin):
+    """rmv_f64.cuh (the Euler angles of k_reinmav_step, reinmav_env.py:341-346): a few 1e-16 from NumPy's libm over
+    every octant, the pi/8 split, the |x| = 1/2 switch of asin, signed zeros, infinities and NaN."""
+    rng = np.random.RandomState(3)
+    n = 400000
+    ang = rng.uniform(-np.pi, np.pi, n)
+    rad = 10.0 ** rng.uniform(-6, 6, n)
+    y, x = rad * np.sin(ang), rad * np.cos(ang)
+    edge = [0.0, -0.0, 1.0, -1.0, np.sqrt(2) - 1, 1 - np.sqrt(2), 1e-300, -1e-300, 5e-324, 1e300, np.inf, -np.inf, np.nan]
+    ey, ex = np.meshgrid(edge, edge)
+    y, x = np.concatenate([y, ey.ravel(), np.tan(np.pi / 8) * np.abs(x[:1000])]), np.concatenate([x, ex.ravel(), np.abs(x[:1000])])
+    out = np.empty_like(y)
+    host_twin.twin_atan2_f64(ctypes.c_long(len(y)), _p(y), _p(x), _p(out))
+    with np.errstate(all="ignore"):
+        ref = np.arctan2(y, x)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.array_equal(np.signbit(out[ok]), np.signbit(ref[ok]))
+    assert np.abs(out[ok] - ref[ok]).max() <= 4.5e-16            # one ulp at pi
+    rel = np.abs(out[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-300)
+    assert rel.max() <= 4 * np.finfo(np.float64).eps
+
+    v = np.concatenate([rng.uniform(-1, 1, n), rng.uniform(-0.5, 0.5, n), 10.0 ** rng.uniform(-12, 0, 1000),
+                        [0.0, -0.0, 0.5, -0.5, np.nextafter(0.5, 1), 1.0, -1.0, 1.0000001, np.nan, 1e-310]])
+    out = np.empty_like(v)
+    host_twin.twin_asin_f64(ctypes.c_long(len(v)), _p(v), _p(out))
+    with np.errstate(all="ignore"):
+        ref = np.arcsin(v)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.array_equal(np.signbit(out[ok]), np.signbit(ref[ok]))
+    rel = np.abs(out[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-300)
+    assert rel.max() <= 4 * np.finfo(np.float64).eps

@@ -107,3 +107,35 @@ def test_many_envs_and_step_many():
     assert np.abs(a.get_state() - s_ref).max() < 2e-6
     a.close()
     b.close()
+
+
+@pytest.mark.gpu
+def test_every_attitude_octant_against_the_oracle():
+    """Attitudes over all of SO(3): both atan2 of RotToRPY see every octant and the pi/8 split, asin both of its
+    ranges (|R12| above 1/2 takes the library path of rmv_f64.cuh).  Near gimbal lock the reference divides by
+    cos(phi) ~ 0 and amplifies its own rounding, so those envs are held to the looser bound only."""
+    import torch
+    import gym_reinmav_b200 as rmv
+    n = 20000
+    rng = np.random.RandomState(5)
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    init = np.concatenate([rng.uniform(-0.5, 0.5, (n, 3)), rng.uniform(-1, 1, (n, 3)), q, rng.uniform(-2, 2, (n, 3))], axis=1)
+    init = init.astype(np.float32)
+    b = rmv.QuadBatch("reinmav-v0", n)
+    b.set_state(init)
+    o = ReinmavBatch(n, state=init.astype(np.float64))
+    qw, qx, qy, qz = init[:, 6].astype(np.float64), init[:, 7].astype(np.float64), init[:, 8].astype(np.float64), init[:, 9].astype(np.float64)
+    r12 = 2 * (qy * qz - qw * qx) / (qw * qw + qx * qx + qy * qy + qz * qz)
+    assert (np.abs(r12) > 0.5).sum() > n // 4 and (np.abs(r12) <= 0.5).sum() > n // 4
+    rew = torch.empty(n, device="cuda:0")
+    done = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+    for t in range(3):
+        b.step(None, rew, done)
+        s_ref, _, _ = o.step(round_to_float32=True)
+    diff = np.abs(b.get_state().astype(np.float64) - s_ref).max(axis=1)
+    scale = np.maximum(1.0, np.abs(s_ref).max(axis=1))                 # body rates reach tens of rad/s under saturated motors
+    regular = np.abs(r12) < 0.99
+    assert (diff[regular] / scale[regular]).max() <= 2e-6
+    assert (diff / scale).max() <= 1e-4
+    b.close()
