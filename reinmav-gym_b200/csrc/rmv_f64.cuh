@@ -8,7 +8,7 @@
 //   atan2(y, x)  octant reduction on |x|, |y| plus the pi/8 split  atan(m/M) = pi/4 + atan((m - M)/(m + M)),  both
 //                applied BEFORE the one division, so the polynomial only sees |t| <= tan(pi/8): 10 terms in t^2
 //   asin(x)      |x| < 1/2: x + x^3 P(x^2), 12 terms; beyond (roll above 30 degrees) the library's asin
-//   the division MUFU.RCP64H seed, two Newton steps, one residual correction (7 FP64 ops, no slow path)
+//   the division MUFU.RCP64H seed, one Newton step, one residual correction (5 FP64 ops, no slow path)
 // Coefficients: Chebyshev-node interpolants of (f(sqrt u)/sqrt u - 1)/u computed at 50 digits, rounded to double.
 // Host build (tests/host_twin): same code with an exact division.
 #pragma once
@@ -27,7 +27,15 @@ namespace rmv {
 #if defined(__CUDACC__)
 __device__ __noinline__ double atan2_library(double y, double x) { return ::atan2(y, x); }
 __device__ __noinline__ double asin_library(double x) { return ::asin(x); }
+__device__ __noinline__ double div_library(double n, double d) { return n / d; }
 #endif
+RMV_F64_HD double div_rare(double n, double d) {
+#if defined(__CUDA_ARCH__)
+  return div_library(n, d);
+#else
+  return n / d;
+#endif
+}
 RMV_F64_HD double atan2_rare(double y, double x) {
 #if defined(__CUDA_ARCH__)
   return atan2_library(y, x);
@@ -60,12 +68,9 @@ RMV_F64_HD double div_newton(double n, double d) {
 #if defined(__CUDA_ARCH__)
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = ::fma(-d, r, 1.0);
-  r = ::fma(r, e, r);
-  e = ::fma(-d, r, 1.0);
-  r = ::fma(r, e, r);
+  r = ::fma(r, ::fma(-d, r, 1.0), r);              // seed is good to 2^-19.9 (tools/f64_check.cu): 2^-39.8 after one Newton step
   const double q = n * r;
-  return ::fma(::fma(-d, q, n), r, q);
+  return ::fma(::fma(-d, q, n), r, q);             // the residual correction squares that again: within one ulp of n / d
 #else
   return n / d;
 #endif
@@ -116,12 +121,17 @@ RMV_F64_HD double clamp_zero_to(double v, double hi) {
 RMV_F64_TABLE double kOctantBase[8] = {0.0, 0x1.921fb54442d18p-1, 0x1.921fb54442d18p+0, 0x1.921fb54442d18p-1,
                                        0x1.921fb54442d18p+1, 0x1.2d97c7f3321d2p+1, 0x1.921fb54442d18p+0, 0x1.2d97c7f3321d2p+1};
 
-RMV_F64_HD double atan2_f64(double y, double x) {
+// atan2 for max(|x|, |y|) in the normal range
+RMV_F64_HD bool atan2_fast_ok(double y, double x) {
+  const double ax = ::fabs(x), ay = ::fabs(y);
+  return normal_range(gt_nonneg(ay, ax) ? ay : ax);                // false for zeros, subnormals, inf, NaN (NaN orders above inf)
+}
+RMV_F64_TABLE double kTanPi8 = 0x1.a827999fcef32p-2;
+RMV_F64_HD double atan2_core(double y, double x) {
   const double ax = ::fabs(x), ay = ::fabs(y);
   const bool swap = gt_nonneg(ay, ax);
   const double big = swap ? ay : ax, small = swap ? ax : ay;
-  if (!normal_range(big)) return atan2_rare(y, x);                 // zeros, subnormals, inf, NaN: the library's rules
-  const bool upper = gt_nonneg(small, 0x1.a827999fcef32p-2 * big);  // beyond pi/8: measure from pi/4
+  const bool upper = gt_nonneg(small, kTanPi8 * big);  // beyond pi/8: measure from pi/4
   const bool xneg = ::signbit(x);
   const double num = upper ? small - big : small;
   const double den = upper ? small + big : big;
@@ -130,14 +140,19 @@ RMV_F64_HD double atan2_f64(double y, double x) {
   const double a = atan_small(swap != xneg ? -t : t) + kOctantBase[(xneg ? 4 : 0) + (swap ? 2 : 0) + (upper ? 1 : 0)];
   return ::copysign(a, y);
 }
+RMV_F64_HD double atan2_f64(double y, double x) {
+  return atan2_fast_ok(y, x) ? atan2_core(y, x) : atan2_rare(y, x);   // rare: the library's rules
+}
 
-RMV_F64_HD double asin_f64(double x) {
-  if (!gt_nonneg(0.5, ::fabs(x))) return asin_rare(x);             // |x| >= 1/2 or NaN
+// asin for |x| < 1/2
+RMV_F64_HD bool asin_fast_ok(double x) { return gt_nonneg(0.5, ::fabs(x)); }   // false for NaN too
+RMV_F64_HD double asin_core(double x) {
   const double u = x * x;
   double p = kAsinCoef[11];
 #pragma unroll
   for (int k = 10; k >= 0; --k) p = ::fma(p, u, kAsinCoef[k]);
   return ::fma(x * u, p, x);
 }
+RMV_F64_HD double asin_f64(double x) { return asin_fast_ok(x) ? asin_core(x) : asin_rare(x); }
 
 }  // namespace rmv

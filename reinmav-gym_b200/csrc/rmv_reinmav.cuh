@@ -30,6 +30,17 @@ constexpr double kRmArm = 0.0860, kRmMass = 0.1800, kRmGrav = 9.8100, kRmMaxF = 
 #define RMV_REINMAV_GAINS const double kRmKp[3] = {10.0, 10.0, 35.0}, kRmKd[3] = {5.0, 5.0, 22.0}   /* controller gains (:311-312) */
 constexpr double kRmKpRot = 100.0, kRmKdRot = 0.1;                                // (:313-314)
 constexpr double kRmMix = 0.5 / kRmArm;                                           // moment -> thrust difference (:204-212)
+constexpr double kRmI00 = 0.00025, kRmI02 = 2.55e-06, kRmI11 = 0.000232, kRmI20 = 2.55e-06, kRmI22 = 0.0003738;   // (:60-62)
+
+// The constants of a substep that are not exact in 32 bits.  In the constant bank an FP64 instruction reads them as an
+// operand; written as literals each use costs two uniform-register moves inside the substep loop.
+struct ReinmavConst {
+  double quarter_mass, quarter_weight, neg_rot_p, neg_rot_d, neg_kd_rot, thrust_cap, inv_mass, neg_grav, arm;
+  double i00, i02, i11, i20, i22, h;
+};
+__constant__ ReinmavConst kRmC = {0.25 * kRmMass, 0.25 * kRmMass * kRmGrav, -kRmKpRot * kRmMix, -kRmKdRot * kRmMix, -kRmKdRot,
+                                  kRmMaxF / 4.0, 1.0 / kRmMass, -kRmGrav, kRmArm,
+                                  kRmI00, kRmI02, kRmI11, kRmI20, kRmI22, 1.0 / 5000};
 
 // What every env shares at one substep: the quintic reference trajectory (trj_gen, reinmav_env.py:128-136) and
 // sin/cos of the desired yaw (controller, :306-337) depend on the clock only, so a CTA evaluates them once per
@@ -69,13 +80,12 @@ __device__ __forceinline__ ReinmavRef reinmav_reference(double t) {
 __device__ __forceinline__ void reinmav_derivative(const double (&s)[13], const ReinmavRef& ref, const double (&invI)[9],
                                                    double (&ds)[13]) {
   RMV_REINMAV_GAINS;
-  constexpr double I00 = 0.00025, I02 = 2.55e-06, I11 = 0.000232, I20 = 2.55e-06, I22 = 0.0003738;   // :60-62
   const double qw = s[6], qx = s[7], qy = s[8], qz = s[9], p = s[10], q = s[11], r = s[12];
   // quat2mat (:267-290); only the entries the controller and the force projection read
   const double nq = ::fma(qz, qz, ::fma(qy, qy, ::fma(qx, qx, qw * qw)));
   double R02 = 0.0, R10 = 0.0, R11 = 1.0, R12 = 0.0, R20 = 0.0, R21 = 0.0, R22 = 1.0;
-  if (nq > 2.220446049250313e-16) {
-    const double sc = normal_range(nq) ? div_newton(2.0, nq) : 2.0 / nq;
+  if (nq > 2.220446049250313e-16) {                          // np.finfo(float).eps (:271); false for NaN
+    const double sc = normal_range(nq) ? div_newton(2.0, nq) : div_rare(2.0, nq);
     const double X = qx * sc, Y = qy * sc, Z = qz * sc;
     const double xX = qx * X, xY = qx * Y, xZ = qx * Z, yZ = qy * Z;
     R02 = ::fma(qw, Y, xZ);
@@ -87,40 +97,45 @@ __device__ __forceinline__ void reinmav_derivative(const double (&s)[13], const 
   // factor, so the two divisions and the cosine are not evaluated (differences at the 1e-16 level, far inside the
   // stated 1e-5; at |R12| = 1 the reference itself divides by zero).  asin_f64 / atan2_f64 (rmv_f64.cuh): double
   // accuracy at a quarter of the library versions' FP64 instructions.
-  const double phi = asin_f64(R12);
-  const double psi = atan2_f64(-R10, R11);
-  const double theta = atan2_f64(-R02, R22);
+  double phi, psi, theta;
+  if (asin_fast_ok(R12) & atan2_fast_ok(-R10, R11) & atan2_fast_ok(-R02, R22)) {          // one branch for the three
+    phi = asin_core(R12); psi = atan2_core(-R10, R11); theta = atan2_core(-R02, R22);
+  } else {
+    phi = asin_f64(R12); psi = atan2_f64(-R10, R11); theta = atan2_f64(-R02, R22);
+  }
   // controller (:306-337) and motor mixing + clamp (:204-216)
   double ddr[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) ddr[i] = ::fma(-kRmKp[i], s[i], ::fma(-kRmKd[i], s[3 + i], ref.acc0[i]));
-  const double u4 = ::fma(0.25 * kRmMass, ddr[2], 0.25 * kRmMass * kRmGrav);             // u1 / 4, u1 = m (g + ddr_z)
-  const double kmx = ::fma(-kRmKpRot * kRmMix, phi, ::fma(-kRmKdRot * kRmMix, p, ::fma(ddr[0], ref.sp_k, -(ddr[1] * ref.cp_k))));
-  const double kmy = ::fma(-kRmKpRot * kRmMix, theta, ::fma(-kRmKdRot * kRmMix, q, ::fma(ddr[0], ref.cp_k, ddr[1] * ref.sp_k)));
-  const double mz = ::fma(-kRmKpRot, psi, ::fma(-kRmKdRot, r, ref.mz0));
+  const double u4 = ::fma(kRmC.quarter_mass, ddr[2], kRmC.quarter_weight);             // u1 / 4, u1 = m (g + ddr_z)
+  const double kmx = ::fma(kRmC.neg_rot_p, phi, ::fma(kRmC.neg_rot_d, p, ::fma(ddr[0], ref.sp_k, -(ddr[1] * ref.cp_k))));
+  const double kmy = ::fma(kRmC.neg_rot_p, theta, ::fma(kRmC.neg_rot_d, q, ::fma(ddr[0], ref.cp_k, ddr[1] * ref.sp_k)));
+  const double mz = ::fma(-kRmKpRot, psi, ::fma(kRmC.neg_kd_rot, r, ref.mz0));
   double T[4] = {u4 - kmy, u4 + kmx, u4 + kmy, u4 - kmx};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) T[i] = clamp_zero_to(T[i], kRmMaxF / 4.0);      // np.clip(T, MIN_F / 4 = 0, MAX_F / 4)
-  const double fm = (1.0 / kRmMass) * (T[0] + T[1] + T[2] + T[3]);                        // force / mass
+  for (int i = 0; i < 4; ++i) T[i] = clamp_zero_to(T[i], kRmC.thrust_cap);      // np.clip(T, MIN_F / 4 = 0, MAX_F / 4)
+  const double fm = kRmC.inv_mass * (T[0] + T[1] + T[2] + T[3]);                        // force / mass
   ds[0] = s[3]; ds[1] = s[4]; ds[2] = s[5];
   ds[3] = R20 * fm;
   ds[4] = R21 * fm;
-  ds[5] = ::fma(R22, fm, -kRmGrav);
+  ds[5] = ::fma(R22, fm, kRmC.neg_grav);
   const double err2 = 2.0 * (1 - nq), hp = 0.5 * p, hq = 0.5 * q, hr = 0.5 * r;
   ds[6] = ::fma(hr, qz, ::fma(hq, qy, ::fma(hp, qx, err2 * qw)));
   ds[7] = ::fma(-hq, qz, ::fma(hr, qy, ::fma(-hp, qw, err2 * qx)));
   ds[8] = ::fma(hp, qz, ::fma(-hr, qx, ::fma(-hq, qw, err2 * qy)));
   ds[9] = ::fma(-hp, qy, ::fma(hq, qx, ::fma(-hr, qw, err2 * qz)));
-  const double Iw[3] = {::fma(I02, r, I00 * p), I11 * q, ::fma(I22, r, I20 * p)};
+  const double Iw[3] = {::fma(kRmC.i02, r, kRmC.i00 * p), kRmC.i11 * q, ::fma(kRmC.i22, r, kRmC.i20 * p)};
   // moments minus omega x (I omega)
-  const double rhs[3] = {::fma(-q, Iw[2], ::fma(r, Iw[1], kRmArm * (T[1] - T[3]))),
-                         ::fma(-r, Iw[0], ::fma(p, Iw[2], kRmArm * (T[2] - T[0]))),
+  const double rhs[3] = {::fma(-q, Iw[2], ::fma(r, Iw[1], kRmC.arm * (T[1] - T[3]))),
+                         ::fma(-r, Iw[0], ::fma(p, Iw[2], kRmC.arm * (T[2] - T[0]))),
                          ::fma(-p, Iw[1], ::fma(q, Iw[0], mz))};
-#pragma unroll
-  for (int i = 0; i < 3; ++i) ds[10 + i] = ::fma(invI[3 * i + 2], rhs[2], ::fma(invI[3 * i + 1], rhs[1], invI[3 * i] * rhs[0]));
+  // I^-1 rhs: the pitch axis decouples ([[a,0,c],[0,e,0],[g,0,i]] and its inverse share the zeros, exact on the host side)
+  ds[10] = ::fma(invI[2], rhs[2], invI[0] * rhs[0]);
+  ds[11] = invI[4] * rhs[1];
+  ds[12] = ::fma(invI[8], rhs[2], invI[6] * rhs[0]);
 }
 
-__global__ void __launch_bounds__(128) k_reinmav_step(const ReinmavArgs a) {
+__global__ void __launch_bounds__(128, 7) k_reinmav_step(const ReinmavArgs a) {
   __shared__ ReinmavRef ref[kReinmavMaxSub];
   if ((int)threadIdx.x < a.n_sub) ref[threadIdx.x] = reinmav_reference(a.t0 + (double)threadIdx.x * a.delta);
   __syncthreads();
@@ -132,7 +147,7 @@ __global__ void __launch_bounds__(128) k_reinmav_step(const ReinmavArgs a) {
   for (int c = 0; c < 13; ++c) s[c] = (double)row[c * kTile];
 #pragma unroll
   for (int i = 0; i < 9; ++i) invI[i] = a.inv_inertia[i];
-  const double h = 1.0 / 5000;
+  const double h = kRmC.h;                                   // 1/5000 (:91)
   for (int i = 0; i < a.n_sub; ++i) {
     reinmav_derivative(s, ref[i], invI, ds);
 #pragma unroll
