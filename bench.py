@@ -630,6 +630,31 @@ def measure_extras(torch, rmv, args, local):
                     "mode": "QuadVecEnv.step_tensor (one C-ABI call per step from Python), monitor=True, state_layout=%s" % venv.state_layout}
         stats = venv.episode_stats()
         out[key]["episodes_finished"] = stats["episodes"]
+        if env_id == ENV_ID:
+            # the same loop under VecNormalize (run.py:91-92): two more kernels per step (rmv_norm.cuh), running statistics
+            # in HBM; bytes = the step's + 4(2S + 2) + 1 + 16 (obs in / out, reward in / out, done, the float64 return)
+            norm = rmv.VecNormalize(venv)
+            norm.reset_tensor()
+            for t in range(16):
+                norm.step_tensor(views[t])
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for t in range(T):
+                    norm.step_tensor(views[t])
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) / T)
+            nb2 = nbytes + 4 * (2 * Sd + 2) + 1 + 16
+            out["vecnormalize_quadrotor3d"] = {
+                "env_id": env_id, "n_envs": n, "n_steps": T, "us_per_step": best * 1e3, "env_steps_per_s": n / (best * 1e-3),
+                "bytes_per_env_step": nb2, "algorithmic_GBps": n / (best * 1e-3) * nb2 / 1e9,
+                "frac_of_hbm_peak": n / (best * 1e-3) * nb2 / 1e9 / peak,
+                "mode": "VecNormalize(QuadVecEnv).step_tensor: env step + k_norm_moments + k_norm_apply, statistics updated every step"}
+            norm.close()                                  # closes venv too
+            del norm
         venv.close()
         del venv
         venv = rmv.QuadVecEnv(env_id, n, device=local, seed=SEED, monitor=True)

@@ -1443,7 +1443,7 @@ struct rmv_norm {
   double gamma = 0.99, epsilon = 1e-8;
   double* ret = nullptr;       // [n]
   double* stats = nullptr;     // [2][kNormStats]
-  double* sums = nullptr;      // [2][kNormSums]
+  double* sums = nullptr;      // [2][kNormSumsAll]
   uint64_t step = 0;           // parity selects the current halves
 };
 
@@ -1464,7 +1464,7 @@ extern "C" RMV_API int rmv_norm_create(rmv_norm** out, int64_t n_envs, int obs_d
   nm->clip_obs = clip_obs; nm->clip_rew = clip_rew; nm->gamma = gamma; nm->epsilon = epsilon;
   cudaError_t err = alloc_zero(&nm->ret, (size_t)n_envs);
   if (err == cudaSuccess) err = alloc_zero(&nm->stats, (size_t)2 * kNormStats);
-  if (err == cudaSuccess) err = alloc_zero(&nm->sums, (size_t)2 * kNormSums);
+  if (err == cudaSuccess) err = alloc_zero(&nm->sums, (size_t)2 * kNormSumsAll);
   if (err == cudaSuccess) {
     double st[kNormStats];
     norm_host_defaults(st);
@@ -1497,13 +1497,40 @@ static int norm_launch(rmv_norm* nm, const float* obs, const float* rew, const u
   const int cur = (int)(nm->step & 1u);
   a.obs = obs; a.reward = rew; a.done = done; a.obs_out = obs_out; a.reward_out = rew_out; a.ret = nm->ret;
   a.stats_cur = nm->stats + cur * kNormStats; a.stats_next = nm->stats + (cur ^ 1) * kNormStats;
-  a.sums_cur = nm->sums + cur * kNormSums; a.sums_next = nm->sums + (cur ^ 1) * kNormSums;
+  a.sums_cur = nm->sums + cur * kNormSumsAll; a.sums_next = nm->sums + (cur ^ 1) * kNormSumsAll;
   a.n = nm->n; a.S = nm->S; a.norm_obs = nm->norm_obs; a.norm_ret = nm->norm_ret; a.update = update ? 1 : 0;
   a.clip_obs = nm->clip_obs; a.clip_rew = nm->clip_rew; a.gamma = nm->gamma; a.epsilon = nm->epsilon;
-  unsigned grid = blocks_for(nm->n, 256);
-  if (grid > 148u * 8u) grid = 148u * 8u;
-  k_norm_moments<<<grid, 256, 0, st>>>(a);
-  k_norm_apply<<<blocks_for(nm->n, 256), 256, 0, st>>>(a);
+  // flat float4 walk when both matrices allow it; ONE wave of CTAs, a multiple of S of them so that a thread's lanes keep
+  // their components
+  const bool vec4 = aligned(obs, 16) && aligned(obs_out, 16);
+  static int wave_of[kMaxDevices][2] = {};
+  int& wave = wave_of[nm->device][vec4 ? 1 : 0];
+  if (wave == 0) {
+    int sms = 1, r0 = 1, r1 = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, nm->device);
+    if (vec4) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r0, k_norm_moments<4>, kNormBlock, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r1, k_norm_apply<4>, kNormBlock, 0);
+    } else {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r0, k_norm_moments<1>, kNormBlock, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r1, k_norm_apply<1>, kNormBlock, 0);
+    }
+    wave = std::max(1, sms) * std::max(1, std::min(r0, r1));
+  }
+  const int64_t work = vec4 ? (nm->n * nm->S + 3) / 4 : nm->n * nm->S;
+  int64_t want = (std::max<int64_t>(work, nm->n) + kNormBlock - 1) / kNormBlock;
+  unsigned grid;
+  if (want >= wave) grid = (unsigned)std::max<int64_t>(nm->S, (int64_t)wave / nm->S * nm->S);
+  else grid = (unsigned)((want + nm->S - 1) / nm->S * nm->S);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kNormBlock); cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  if (vec4) { RMV_CUDA(cudaLaunchKernelEx(&cfg, k_norm_moments<4>, a)); RMV_CUDA(cudaLaunchKernelEx(&cfg, k_norm_apply<4>, a)); }
+  else { RMV_CUDA(cudaLaunchKernelEx(&cfg, k_norm_moments<1>, a)); RMV_CUDA(cudaLaunchKernelEx(&cfg, k_norm_apply<1>, a)); }
   RMV_CUDA(cudaGetLastError());
   nm->step += 1;
   return RMV_OK;

@@ -80,3 +80,37 @@ def test_device_vecnormalize_matches_the_restated_baselines_algorithm(env_id):
     h_obs, h_rew, h_done, infos = venv.step(rng.uniform(lo, hi, size=(n, A)).astype(np.float32))
     assert h_obs.shape == (n, S) and h_obs.dtype == np.float32 and h_rew.shape == (n,) and h_done.dtype == bool and len(infos) == n
     venv.close(); other.close()
+
+
+@pytest.mark.gpu
+def test_norm_step_with_unaligned_matrices_takes_the_scalar_walk():
+    """rmv_norm_step walks the observation matrix four floats at a time when both matrices are 16-byte aligned and one at
+    a time otherwise: both walks against the oracle, on a batch whose n * S is not a multiple of 4."""
+    import ctypes
+    import torch
+    from gym_reinmav_b200._capi import check, lib
+    n, S = 1237, 9
+    results = []
+    for offset in (0, 1):                                       # offset 1 float: 4-byte aligned only
+        h = ctypes.c_void_p()
+        check(lib().rmv_norm_create(ctypes.byref(h), n, S, 0, 1, 1, 10.0, 10.0, 0.99, 1e-8))
+        o = VecNormalizeOracle(n, S, gamma=0.99)
+        buf_in = torch.zeros(n * S + 4, dtype=torch.float32, device="cuda:0")
+        buf_out = torch.zeros(n * S + 4, dtype=torch.float32, device="cuda:0")
+        rew_out = torch.zeros(n, dtype=torch.float32, device="cuda:0")
+        obs_in, obs_out = buf_in[offset:offset + n * S].view(n, S), buf_out[offset:offset + n * S].view(n, S)
+        assert obs_in.data_ptr() % 16 == 4 * offset
+        rs = np.random.RandomState(9)
+        for t in range(6):
+            x = rs.normal(2.0, 3.0, size=(n, S)).astype(np.float32)
+            r = rs.normal(-1.0, 2.0, size=n).astype(np.float32)
+            d = rs.uniform(size=n) < 0.1
+            obs_in.copy_(torch.as_tensor(x))
+            rew, done = torch.as_tensor(r, device="cuda:0"), torch.as_tensor(d.astype(np.uint8), device="cuda:0")
+            check(lib().rmv_norm_step(h, obs_in.data_ptr(), rew.data_ptr(), done.data_ptr(), obs_out.data_ptr(), rew_out.data_ptr(), 1, None))
+            w_obs, w_rew = o.step(x.astype(np.float64), r.astype(np.float64), d)
+            assert np.abs(obs_out.cpu().numpy() - w_obs).max() <= 2e-5 and np.abs(rew_out.cpu().numpy() - w_rew).max() <= 2e-5
+        assert float(buf_out[:offset].abs().sum()) == 0.0 and float(buf_out[offset + n * S:].abs().sum()) == 0.0   # nothing outside
+        results.append(obs_out.cpu().numpy().copy())
+        check(lib().rmv_norm_destroy(h))
+    assert np.abs(results[0] - results[1]).max() <= 1e-6

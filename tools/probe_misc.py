@@ -1,7 +1,9 @@
 """Launches the kernels that are not reachable through tools/sweep.py a few times each, for ncu captures:
 k_control, the fused control+step kernel, k_rollout, k_reinmav_step, the row-state kernel with Monitor on.
 
-    python tools/probe_misc.py <control|control_step|rollout|rows_track|reinmav> [n_envs] [env_id]
+    python tools/probe_misc.py <control|control_step|rollout|rows_track|reinmav|vecnorm> [n_envs] [env_id]
+
+vecnorm also prints the time of VecNormalize(QuadVecEnv).step_tensor against the bare venv.step_tensor.
 """
 import os
 import sys
@@ -21,6 +23,28 @@ if what == "reinmav":
     done = torch.empty(n, dtype=torch.uint8, device=dev)
     for _ in range(6):
         b.step(None, rew, done)
+elif what == "vecnorm":
+    env_id = sys.argv[3] if len(sys.argv) > 3 else "quadrotor3d-v0"
+    lo, hi = {"quadrotor3d-v0": (0, 10)}.get(env_id, (-10, 10))
+    for wrap in (False, True):
+        venv = rmv.make_vec_env(env_id, "native", n, 0)
+        env = rmv.VecNormalize(venv) if wrap else venv
+        env.reset_tensor() if wrap else venv.reset()
+        A = venv.action_space.shape[0]
+        acts = torch.empty((16, n, A), dtype=torch.float32, device=dev)
+        for t in range(16):
+            rmv.fill_uniform_actions(acts[t], n, A, lo, hi, 0, step_index=t)
+        for t in range(8):
+            env.step_tensor(acts[t])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(128):
+            env.step_tensor(acts[t % 16])
+        e1.record()
+        torch.cuda.synchronize()
+        print("%s %s n=%d  %.2f us/step" % (env_id, "VecNormalize(venv).step_tensor" if wrap else "venv.step_tensor", n, e0.elapsed_time(e1) / 128 * 1e3))
+        env.close()
 else:
     env_id = sys.argv[3] if len(sys.argv) > 3 else "quadrotor3d-v0"
     rows = what == "rows_track"
