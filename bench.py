@@ -151,7 +151,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.fh.close()
-        sm, smax, reasons, busy = [], [], set(), []
+        sm, smax, reasons, busy, watts = [], [], set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in open(self.path):
             f = [x.strip() for x in ln.split(",")]
@@ -162,6 +162,10 @@ class ClockSampler:
             except ValueError:
                 continue
             sm.append(clk); smax.append(mx); busy.append(util > 0)
+            try:
+                watts.append(float(f[3]))
+            except ValueError:
+                pass
             for name, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -169,7 +173,8 @@ class ClockSampler:
         under = [c for c, b in zip(sm, busy) if b] or sm
         if under:
             under.sort()
-            out.update(sm_mhz=under[len(under) // 2], sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(under))
+            out.update(sm_mhz=under[len(under) // 2], sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(under),
+                       sm_min_mhz=under[0], power_w_max=max(watts) if watts else None)
         return out
 
 
