@@ -26,6 +26,8 @@
 // The first version read one row per thread (stride-S addresses, 10 cache-line requests per load) and issued two FP64
 // atomics per warp and component on 2 (S + 1) addresses: 222 us per step at N = 2^20, S = 10 against 15 us for the env
 // step itself; this version 32 us (k_norm_moments 12.9 + k_norm_apply 20.1 under ncu, profiles/README.md r2c).
+// One wave of CTAs is the fastest grid: 2 / 4 / 8 waves measured 49.6 / 59.9 / 82.4 us per VecNormalize step against 47.4
+// (every CTA repeats the reduction epilogue and the statistics prologue).
 // Algorithmic bytes: 4(2S + 2) + 1 + 16 per env-step (obs in/out, reward in/out, done, the float64 return).
 #pragma once
 #include <cuda_runtime.h>
