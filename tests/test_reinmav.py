@@ -139,3 +139,52 @@ def test_every_attitude_octant_against_the_oracle():
     assert (diff[regular] / scale[regular]).max() <= 2e-6
     assert (diff / scale).max() <= 1e-4
     b.close()
+
+
+@pytest.mark.gpu
+def test_history_for_plot_state_follows_the_reference_bookkeeping(golden):
+    """The reference's own test ends with ``env.plot_state()`` (test/test_reinmav.py:24), which draws the history
+    ``step()`` keeps (reinmav_env.py:119-124): cum_t, cum_state = stateToQd(state), cum_desired_state = trj_gen(t + dt)."""
+    import gym_reinmav_b200 as rmv
+    from oracle.reinmav64 import quat_to_matrix, trajectory
+    env = rmv.make("reinmav-v0")
+    assert env.cum_t == [0.0] and env.cum_state.shape == (12,) and env.cum_state[:6].tolist() == [0.0] * 6
+    states = [env.step()[0] for _ in range(25)]
+    assert np.allclose(env.cum_t, np.arange(26) * 0.01, atol=1e-12)
+    assert env.cum_state.shape == (26, 12) and env.cum_desired_state.shape == (26, 11)
+    for k, s in enumerate(states, start=1):
+        qd = env.cum_state[k]
+        assert np.array_equal(qd[:6], s[:6]) and np.array_equal(qd[9:], s[10:13])
+        R = quat_to_matrix(s[6], s[7], s[8], s[9])
+        phi = np.arcsin(R[1][2])
+        want = (phi, np.arctan2(-R[0][2] / np.cos(phi), R[2][2] / np.cos(phi)), np.arctan2(-R[1][0] / np.cos(phi), R[1][1] / np.cos(phi)))
+        assert np.allclose(qd[6:9], want, rtol=0, atol=1e-12)
+        pos, vel, acc = trajectory(k * 0.01)
+        assert np.allclose(env.cum_desired_state[k], [pos] * 3 + [vel] * 3 + [acc] * 3 + [pos, vel], rtol=0, atol=1e-12)
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            env.plot_state()
+    env.close()
+
+
+@pytest.mark.reference
+def test_history_helpers_equal_the_reference_class():
+    """stateToQd / trj_gen of the N = 1 view against the reference's own ReinmavEnv (run from /root/reference under the
+    shim), on random states and over the history its step() keeps."""
+    from oracle.make_golden_reinmav import load_reinmav_class
+    from gym_reinmav_b200.envs.native import ReinmavEnv
+    ref = load_reinmav_class()()
+    rng = np.random.RandomState(11)
+    for _ in range(200):
+        s = rng.normal(size=13)
+        s[6:10] /= np.linalg.norm(s[6:10]) * rng.uniform(0.8, 1.2)
+        np.testing.assert_allclose(ReinmavEnv.stateToQd(s), ref.stateToQd(s), rtol=0, atol=1e-12)
+    for t in (-1.0, 0.0, 0.37, 1.3, 3.999, 4.0, 7.0):
+        np.testing.assert_allclose(ReinmavEnv.trj_gen(t), ref.trj_gen(t), rtol=0, atol=1e-15)
+    for _ in range(3):
+        ref.step()
+    assert len(ref.cum_t) == 4 and np.asarray(ref.cum_state).shape == (4, 12) and np.asarray(ref.cum_desired_state).shape == (4, 11)
+    np.testing.assert_allclose(ref.cum_desired_state[3], ReinmavEnv.trj_gen(0.03), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(ref.cum_state[3], ReinmavEnv.stateToQd(np.asarray(ref.state, dtype=float).reshape(-1)), rtol=0, atol=1e-12)
