@@ -50,6 +50,18 @@ class NativeQuadEnv(_EnvBase):
             self.load_mass, self.tether_length = p.load_mass, p.tether_len
         self.observation_space, self.action_space = make_spaces(self.KIND)
         self.viewer = None
+        # viewer handles of the reference classes (quadrotor2d.py:57-59, quadrotor3d_slungload.py:62-72): never populated here
+        # (render() is a no-op), present so that code reading them finds what the reference has before its first render()
+        self.x_range = 1.0
+        if planar:
+            self.quadtrans = self.reftrans = None
+            if self.KIND == _capi.QUAD2D_SLUNG:
+                self.loadtrans = None
+        elif self.KIND != _capi.REINMAV:
+            for name in ("quad1", "quad2", "rotor1", "rotor2", "rotor3", "rotor4", "velocity", "ref"):
+                setattr(self, "render_" + name, None)
+            if self.KIND == _capi.QUAD3D_SLUNG:
+                self.render_load = self.render_tether = None
         self._seed_value = self._fresh_seed() if seed is None else int(seed)
         self._batch = QuadBatch(self.KIND, 1, device=device, seed=self._seed_value)
         self._act = np.zeros((1, max(self._batch.action_dim, 1)), dtype=np.float32)

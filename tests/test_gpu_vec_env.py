@@ -97,6 +97,11 @@ def test_single_env_view(rmv, env_id):
     assert env.dt == np.float32(0.01) and env.mass == 1.0 and env.g[-1] == -np.float32(9.8)
     assert env.observation_space.shape == (S,) and env.action_space.shape == (A,)
     assert env.steps_beyond_done is None
+    # the viewer handles the reference classes carry before their first render() (quadrotor2d.py:57-59 and twins)
+    handles = {5: ["quadtrans", "reftrans"], 9: ["quadtrans", "reftrans", "loadtrans"],
+               10: ["render_" + k for k in ("quad1", "quad2", "rotor1", "rotor2", "rotor3", "rotor4", "velocity", "ref")]}
+    handles[16] = handles[10] + ["render_load", "render_tether"]
+    assert env.x_range == 1.0 and env.viewer is None and all(getattr(env, h) is None for h in handles[S])
     assert env.seed(123) == [123]
     obs = env.reset()
     assert obs.shape == (S,) and obs.dtype == np.float64 and (np.abs(obs) <= 1).all()
