@@ -73,13 +73,19 @@ def _need(x, count, what):
         raise ValueError("%s holds %d elements, %d needed" % (what, have, count))
 
 
+_TORCH_CUDA = None          # torch, once it is imported and reports a CUDA device (asked once: this sits on the per-step path)
+
+
 def _stream(stream, device):
     if stream is None:
-        import sys
-        torch = sys.modules.get("torch")
-        if torch is not None and torch.cuda.is_available():
-            return torch.cuda.current_stream(device).cuda_stream
-        return None
+        global _TORCH_CUDA
+        if _TORCH_CUDA is None:
+            import sys
+            torch = sys.modules.get("torch")
+            if torch is None or not torch.cuda.is_available():
+                return None
+            _TORCH_CUDA = torch
+        return _TORCH_CUDA.cuda.current_stream(device).cuda_stream
     if isinstance(stream, int):
         return stream or None
     return stream.cuda_stream                        # torch.cuda.Stream

@@ -229,6 +229,8 @@ class QuadVecEnv:
             self._t = dict(obs=obs, state=state,
                            rew=torch.empty((n,), dtype=torch.float32, device=dev),
                            done=torch.empty((n,), dtype=torch.uint8, device=dev))
+            for k in ("obs", "rew", "done"):
+                self._t[k + "_ptr"] = self._t[k].data_ptr()
         return self._t
 
     def reset_tensor(self):
@@ -241,7 +243,8 @@ class QuadVecEnv:
         reward [N], done [N] uint8) as tensors aliasing internal buffers."""
         t = self._tensors()
         rows = self.state_layout == "rows"          # the step updates t["obs"] (= the state) in place: nothing to copy
-        self.batch.step(actions, t["rew"], t["done"], obs=t["obs"] if (want_obs and not rows) else None, auto_reset=True)
+        # the internal buffers go down as the raw addresses validated when they were made: only `actions` is checked per call
+        self.batch.step(actions, t["rew_ptr"], t["done_ptr"], obs=t["obs_ptr"] if (want_obs and not rows) else None, auto_reset=True)
         return (t["obs"] if want_obs else None), t["rew"], t["done"]
 
     def control_tensor(self, ref_pos=None, ref_vel=None):
