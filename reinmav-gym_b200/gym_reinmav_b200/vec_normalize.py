@@ -33,6 +33,7 @@ class VecNormalize:
         dev = "cuda:%d" % self.device
         self._obs = torch.empty((self.num_envs, S), dtype=torch.float32, device=dev)
         self._rew = torch.empty((self.num_envs,), dtype=torch.float32, device=dev)
+        self._obs_ptr, self._rew_ptr = self._obs.data_ptr(), self._rew.data_ptr()
         self._act = None
         self.closed = False
 
@@ -46,8 +47,8 @@ class VecNormalize:
     def step_tensor(self, actions):
         """(normalised obs [N,S], normalised reward [N], done [N] uint8) — tensors aliasing internal buffers."""
         raw, rew, done = self.venv.step_tensor(actions)
-        check(lib().rmv_norm_step(self._h, _ptr(raw, "float32", self.device, "obs"), _ptr(rew, "float32", self.device, "reward"),
-                                  _ptr(done, "uint8", self.device, "done"), _ptr(self._obs), _ptr(self._rew),
+        t = self.venv._tensors()                       # the env's own buffers: addresses validated when they were made
+        check(lib().rmv_norm_step(self._h, t["obs_ptr"], t["rew_ptr"], t["done_ptr"], self._obs_ptr, self._rew_ptr,
                                   1 if self.training else 0, _stream(None, self.device)))
         return self._obs, self._rew, done
 
