@@ -241,10 +241,12 @@ enum { RMV_VARIANT_STEP = 0,         /* k_step: one launch per step, tiled state
        RMV_VARIANT_ROWS = 1,         /* k_step_rows: row-major state                                              */
        RMV_VARIANT_TMA = 2,          /* k_step_tma: TMA bulk copies + mbarrier pipeline                           */
        RMV_VARIANT_ROLLOUT = 3,      /* k_rollout: state in registers for T steps                                 */
-       RMV_VARIANT_STREAM = 4,       /* k_step_stream: persistent step stream, one env per thread                 */
+       RMV_VARIANT_STREAM = 4,       /* k_step_stream: persistent step stream, one env per thread (tiles or rows) */
        RMV_VARIANT_STREAM_PAIR = 5   /* k_step_stream_pair: step stream, two envs per thread on the packed f32 pipe */ };
 RMV_API int rmv_last_variant(const rmv_env* env, int* variant);
-/* 1 if rmv_step_many(RMV_MANY_STREAM) runs the stream kernel for n_envs of `kind`, 0 if it issues launches (device-free) */
+/* 1 if rmv_step_many(RMV_MANY_STREAM) runs the stream kernel for n_envs of `kind`, 0 if it issues launches (device-free).
+ * For tiled handles; an RMV_STATE_ROWS handle keeps the stream up to 64 MB of algorithmic bytes per step (its rows pass
+ * through shared memory both ways) — rmv_last_variant tells what a call launched. */
 RMV_API int rmv_stream_pays(int kind, int64_t n_envs);
 /* Tuning of the step-stream kernel (sweeps): warps_per_sm caps the resident warps per SM (0 = as many as fit);
  * block = threads per CTA (0 auto, 32, 64, 128 — a CTA is only a scheduling unit of this kernel); action_prefetch = fetch
@@ -284,7 +286,7 @@ RMV_API int rmv_control(rmv_env* env, const float* ref_pos, const float* ref_vel
 RMV_API int rmv_control_step(rmv_env* env, const float* ref_pos, const float* ref_vel, float* act_out_dev,
                              float* reward_dev, uint8_t* done_dev, float* obs_aos_dev, int auto_reset, void* stream);
 /* T closed-loop steps with reset-on-done (the 400-step loop of test/test_quadrotor3d.py:16-22): one launch of the step
- * stream (one launch per step on an RMV_STATE_ROWS handle).  act_out_dev NULL or [T][n][A]; reward_dev / done_dev both
+ * stream where it pays (rmv_stream_pays), else one launch per step.  act_out_dev NULL or [T][n][A]; reward_dev / done_dev both
  * NULL or [T][out_ld]. */
 RMV_API int rmv_control_step_many(rmv_env* env, int n_steps, const float* ref_pos, const float* ref_vel, float* act_out_dev,
                                   float* reward_dev, uint8_t* done_dev, int64_t out_ld, void* stream);

@@ -606,6 +606,16 @@ static bool stream_pays(int kind, int64_t n) {
   return kind >= 0 && kind < 4 && n * bytes[kind] <= (limit_mb[kind] << 20);
 }
 
+// Row-state handles: the unit's rows go through shared memory both ways, which costs the stream more than it costs the
+// row-state kernel once the launch boundary stops mattering — measured (profiles/r2c_sweep_rows_stream.txt): 1.66 against
+// 3.14 us per quadrotor3d step at N = 65536, 3.79 / 5.60 at 2^18, 13.1 / 13.6 at 2^20 (15.5 / 15.1 with episode tracking);
+// quadrotor3d-slungload 6.75 / 7.98 at 2^18 but 27.5 / 24.3 at 2^20; quadrotor2d 9.49 / 10.45 at 2^20 (55 MB per step).
+static bool stream_pays_for(const rmv_env* e) {
+  static const int64_t bytes[4] = {53, 85, 101, 149};
+  if (!stream_pays(e->kind, e->n)) return false;
+  return !e->rows || e->n * bytes[e->kind] <= ((int64_t)64 << 20);
+}
+
 extern "C" RMV_API int rmv_stream_pays(int kind, int64_t n_envs) {
   return (g_use_stream && stream_pays(kind, n_envs)) ? 1 : 0;
 }
@@ -799,13 +809,13 @@ extern "C" RMV_API int rmv_stream_shape(int64_t n_envs, int sms, int resident_wa
 
 static int g_stream_apre = getenv("RMV_STREAM_APRE") ? atoi(getenv("RMV_STREAM_APRE")) : -1;   // developer switch: -1 = by shape
 
-template <int KIND, bool TRACK, bool PREF, bool CTRL = false, bool APRE = false>
+template <int KIND, bool TRACK, bool PREF, bool CTRL = false, bool APRE = false, bool ROWS = false>
 static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_t st) {
   static int resident_of[kMaxDevices] = {}, sms_of[kMaxDevices] = {};      // per instantiation and per device
   const int dev = current_device();
   if (resident_of[dev] == 0) {
     cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_stream<KIND, TRACK, PREF, CTRL, APRE>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_of[dev], k_step_stream<KIND, TRACK, PREF, CTRL, APRE, ROWS>, 128, 0);
     if (resident_of[dev] < 1) resident_of[dev] = 1;
     if (sms_of[dev] < 1) sms_of[dev] = 1;
   }
@@ -832,7 +842,7 @@ static cudaError_t launch_stream_t(rmv_env* e, const StepArgs& args, cudaStream_
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, k_step_stream<KIND, TRACK, PREF, CTRL, APRE>, args, shape);
+  return cudaLaunchKernelEx(&cfg, k_step_stream<KIND, TRACK, PREF, CTRL, APRE, ROWS>, args, shape);
 }
 
 // quadrotor3d, two envs per thread on the packed float32 pipe (k_step_stream_pair)
@@ -868,6 +878,12 @@ static cudaError_t launch_stream_pair(rmv_env* e, const StepArgs& args, cudaStre
 template <int KIND>
 static cudaError_t launch_stream_k(rmv_env* e, const StepArgs& args, cudaStream_t st, bool ctrl = false) {
   const bool track = args.ep_return != nullptr;
+  if (e->rows) {                                   // row-state handle: the stream with the row transposes (no prefetch variants)
+    if (ctrl) return track ? launch_stream_t<KIND, true, false, true, false, true>(e, args, st)
+                           : launch_stream_t<KIND, false, false, true, false, true>(e, args, st);
+    return track ? launch_stream_t<KIND, true, false, false, false, true>(e, args, st)
+                 : launch_stream_t<KIND, false, false, false, false, true>(e, args, st);
+  }
   if constexpr (KIND == QUAD3D) {
     const bool fits = !track && !ctrl && !args.act_soa && aligned(args.act, 16) && aligned(args.reward, 8) && aligned(args.done, 2) &&
                       (args.out_ld % 2) == 0 && (args.act_step_stride % 4) == 0;
@@ -988,9 +1004,9 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
   a.rows_in = nullptr;
   const bool fused_ctrl = ctrl != nullptr;
   cudaError_t err;
-  if (e->rows) {
+  if (e->rows && !stream) {
     // RMV_STATE_ROWS: the state buffer is the [n][S] observation matrix; the row-state kernel updates it in place
-    if (n_steps != 1 || stream) return fail(RMV_EINVAL, "internal: multi-step launch on a row-state handle");
+    if (n_steps != 1) return fail(RMV_EINVAL, "internal: multi-step launch of the row-state kernel");
     RMV_REQUIRE(rew != nullptr && done != nullptr, "reward_dev and done_dev must not be NULL");
     float* const rows = e->state + c0 * e->S;
     a.rows_in = rows; a.obs = rows;
@@ -1003,7 +1019,7 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
     }
     if (err == cudaSuccess && obs != nullptr && obs != rows)
       err = cudaMemcpyAsync(obs, rows, (size_t)cn * e->S * sizeof(float), cudaMemcpyDeviceToDevice, st);
-  } else if (stream) {
+  } else if (stream) {                             // (a row-state handle too: a.state = e->state + c0 * S either way)
     e->last_variant = RMV_VARIANT_STREAM;          // (launch_stream_k<QUAD3D> may overwrite it with RMV_VARIANT_STREAM_PAIR)
     switch (e->kind) {
       case RMV_QUAD2D: err = launch_stream_k<QUAD2D>(e, a, st, fused_ctrl); break;
@@ -1089,7 +1105,7 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
     return launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, reward_dev, done_dev, out_ld, nullptr, 0, n_steps, st);
   const int64_t stride = (act_layout == RMV_ACT_SOA) ? (int64_t)env->A * act_ld : env->n * env->A;
   RMV_REQUIRE(fused >= 0 && fused <= 2, "mode must be RMV_MANY_STREAM (0), RMV_MANY_ROLLOUT (1) or RMV_MANY_LAUNCHES (2)");
-  if (env->rows) fused = RMV_MANY_LAUNCHES;       // row-state handles: one launch of the row-state kernel per step
+  if (env->rows && fused == RMV_MANY_ROLLOUT) fused = RMV_MANY_LAUNCHES;   // the rollout kernel reads tiles: row-state handles take launches there
   if (fused == RMV_MANY_ROLLOUT)
     return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st);
   if (!reward_dev || !done_dev) {                 // the step kernels always write both: park a missing one in scratch
@@ -1099,7 +1115,7 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
   float* const rew0 = reward_dev ? reward_dev : env->h_rew;
   uint8_t* const done0 = done_dev ? done_dev : env->h_done;
   const int64_t out_stride = reward_dev ? out_ld : 0, done_stride = done_dev ? out_ld : 0;
-  if (fused == RMV_MANY_STREAM && g_use_stream && n_steps >= 2 && (g_force_stream || stream_pays(env->kind, env->n))) {
+  if (fused == RMV_MANY_STREAM && g_use_stream && n_steps >= 2 && (g_force_stream || stream_pays_for(env))) {
     // one stride for both outputs: if only one of them is parked, the other one's scratch must be T rows as well
     if ((reward_dev == nullptr) != (done_dev == nullptr))
       return fail(RMV_EINVAL, "rmv_step_many(RMV_MANY_STREAM): pass both reward_dev and done_dev, or neither");
@@ -1315,7 +1331,7 @@ extern "C" RMV_API int rmv_control_step_many(rmv_env* env, int n_steps, const fl
   float* const rew0 = reward_dev ? reward_dev : env->h_rew;
   uint8_t* const done0 = done_dev ? done_dev : env->h_done;
   const int64_t stride = reward_dev ? out_ld : 0;
-  if (!env->rows && g_use_stream && n_steps >= 2 && (g_force_stream || stream_pays(env->kind, env->n)))   // ONE launch: the closed loop runs inside the step stream
+  if (g_use_stream && n_steps >= 2 && (g_force_stream || stream_pays_for(env)))   // ONE launch: the closed loop runs inside the step stream
     return launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, rew0, done0, stride, nullptr, 1, n_steps, st, 0, -1, true, true, &C, act_out_dev);
   for (int t = 0; t < n_steps; ++t) {
     int rc = launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, rew0 + (int64_t)t * stride, done0 + (int64_t)t * stride, env->n, nullptr, 1, 1,

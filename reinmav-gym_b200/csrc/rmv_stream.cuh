@@ -47,7 +47,7 @@ constexpr int stream_min_ctas(int kind, bool track, bool apre = false) {
 
 // re-draw `pairs / NB` finished envs: pair i = (entry i / NB, Philox block i % NB), pairs idx0, idx0 + stride, ...
 // `item_of(slot)` returns (env index inside the launch, new reset count) of list entry `slot`.
-template <int KIND, typename ItemOf>
+template <int KIND, bool ROWS = false, typename ItemOf>
 __device__ __forceinline__ void stream_redraw(const StepArgs& a, uint32_t pairs, uint32_t idx0, uint32_t stride, ItemOf item_of) {
   constexpr int S = Dims<KIND>::S;
   constexpr int NB = (S + 3) / 4;
@@ -58,10 +58,17 @@ __device__ __forceinline__ void stream_redraw(const StepArgs& a, uint32_t pairs,
     const uint64_t id = (uint64_t)a.env_id_offset + er;
     uint32_t w4[4];
     philox4x32_10_ks((uint32_t)id, (uint32_t)(id >> 32), item.y, ((STREAM_RESET_BASE + (uint32_t)KIND) << 8) | b, a.ks, w4);
-    float* const row = a.state + ((size_t)(er >> 7) * (S * kTile) + (er & (kTile - 1))) + 4 * b * kTile;
+    if constexpr (ROWS) {                              // row-state handle: a.state is the [n_pad][S] observation matrix
+      float* const row = a.state + (size_t)er * S + 4 * b;
 #pragma unroll
-    for (int l = 0; l < 4; ++l)
-      if (S % 4 == 0 || 4 * b + l < S) row[l * kTile] = uniform_pm1(w4[l]);
+      for (int l = 0; l < 4; ++l)
+        if (S % 4 == 0 || 4 * b + l < S) row[l] = uniform_pm1(w4[l]);
+    } else {
+      float* const row = a.state + ((size_t)(er >> 7) * (S * kTile) + (er & (kTile - 1))) + 4 * b * kTile;
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (S % 4 == 0 || 4 * b + l < S) row[l * kTile] = uniform_pm1(w4[l]);
+    }
   }
 }
 
@@ -70,13 +77,20 @@ __device__ __forceinline__ void stream_redraw(const StepArgs& a, uint32_t pairs,
 // unit does at L2-resident sizes), so at small batches, where a warp has one unit and little company on its SM, that
 // load is the longest wait of every step; the state cannot run ahead the same way (with one unit per warp the next item
 // reads what this one writes).  Costs A registers: used where occupancy is not the constraint (k <= 2).
-template <int KIND, bool TRACK, bool PREF, bool CTRL = false, bool APRE = false>
+//
+// ROWS (RMV_STATE_ROWS handles): a.state is the [n_pad][S] observation matrix.  A unit's 32 rows are 32 * S contiguous floats:
+// they come in with S coalesced requests through the warp's shared tile and leave the same way (the row-state kernel's
+// transposes, rmv_kernels.cuh); a finished env's row is stored like the others and overwritten by the re-draw, which the
+// CTA barrier (or, in a mass finish, the warp barrier) orders behind it.
+template <int KIND, bool TRACK, bool PREF, bool CTRL = false, bool APRE = false, bool ROWS = false>
 __global__ void __launch_bounds__(128, CTRL ? 8 : stream_min_ctas(KIND, TRACK, APRE))
 k_step_stream(const StepArgs a, const StreamShape shape) {
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   constexpr int NB = (S + 3) / 4;
+  constexpr int SP = row_pitch<S>();
   __shared__ uint2 redraw_list[kStreamWarps][kStreamList];
   __shared__ uint32_t redraw_count[kStreamWarps];
+  __shared__ __align__(16) float row_tile[ROWS ? kStreamWarps * 32 * SP : 4];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t gw = (blockIdx.x * blockDim.x + tid) >> 5;
@@ -95,8 +109,10 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
   uint2* const list = redraw_list[warp & (kStreamWarps - 1)];
   const uint32_t e_first = (gw < W) ? (gw << 5) + lane : limit;          // warps without work start past the end
   const uint32_t de = shape.env_stride;                                  // envs between two units of this warp
-  const size_t ds = (size_t)(de >> 7) * (S * kTile);                     // the same distance in the tiled state (W % 4 == 0)
-  float* const sp_first = a.state + ((size_t)(e_first >> 7) * (S * kTile) + (e_first & (kTile - 1)));
+  const size_t ds = ROWS ? (size_t)de * S : (size_t)(de >> 7) * (S * kTile);   // the same distance in the state buffer (W % 4 == 0)
+  float* const sp_first = ROWS ? a.state + ((size_t)(e_first - lane) * S + lane)       // element `lane` of the unit's 32 * S floats
+                               : a.state + ((size_t)(e_first >> 7) * (S * kTile) + (e_first & (kTile - 1)));
+  float* const my_tile = row_tile + (ROWS ? (warp & (kStreamWarps - 1)) * 32 * SP : 0);
 
   // per-step base pointers: uniform, advanced by a constant per step (the host always passes reward / done buffers:
   // a caller's NULL is parked in scratch with out_ld = 0)
@@ -123,8 +139,14 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
         float s[S], act[A];
         uint32_t word = 0u, ep_started = 0u;
         float ep_ret = 0.0f;
+        if constexpr (ROWS) {                                           // the rows are padded to whole tiles too: in bounds
+          rows_to_tile<S, false>(sp, my_tile, lane, 32u);
+          __syncwarp();
+          row_from_smem<S>(my_tile + lane * SP, s);
+        } else {
 #pragma unroll
-        for (int c = 0; c < S; ++c) s[c] = sp[c * kTile];               // tiles (and the per-env arrays) are padded: in bounds
+          for (int c = 0; c < S; ++c) s[c] = sp[c * kTile];             // tiles (and the per-env arrays) are padded: in bounds
+        }
         if (PREF) word = a.episode[e];
         if (TRACK) { ep_ret = a.ep_return[e]; ep_started = a.ep_start[e]; }
         if constexpr (CTRL) {                        // closed loop: the reference's controller on the state just loaded
@@ -181,10 +203,18 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
           __stcs(rew_t + e, scaled_reward(a.P, rew));
           __stcs(done_t + e, (unsigned char)(done ? 1 : 0));
           if (TRACK) a.ep_return[e] = ep_ret + rew;
-          if (!redraw) {
+          if constexpr (!ROWS) {
+            if (!redraw) {
 #pragma unroll
-            for (int c = 0; c < S; ++c) sp[c * kTile] = s[c];
+              for (int c = 0; c < S; ++c) sp[c * kTile] = s[c];
+            }
           }
+        }
+        if constexpr (ROWS) {                        // all 32 rows of the unit, coalesced (plain stores: the next step reads them)
+          row_to_smem<S>(my_tile + lane * SP, s);
+          __syncwarp();
+          tile_to_rows<S, false, false>(my_tile, sp, lane, 32u);
+          __syncwarp();                              // the tile is free for the next unit; the rows are ordered before a warp-level re-draw
         }
         // finished envs go to the warp's list (prefix popcount of the vote: no atomics)
         const uint32_t mask = a.auto_reset ? done_mask : 0u;
@@ -193,7 +223,7 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
           pending += (uint32_t)__popc(mask);
           if (pending > 32u) {                       // a mass finish: the warp empties its own list right away
             __syncwarp();
-            stream_redraw<KIND>(a, pending * NB, lane, 32u, [&](uint32_t slot) { return list[slot]; });
+            stream_redraw<KIND, ROWS>(a, pending * NB, lane, 32u, [&](uint32_t slot) { return list[slot]; });
             __syncwarp();
             pending = 0u;
           }
@@ -207,7 +237,7 @@ k_step_stream(const StepArgs a, const StreamShape shape) {
     const uint32_t c0 = redraw_count[0], c1 = redraw_count[1], c2 = redraw_count[2], c3 = redraw_count[3];
     const uint32_t total = c0 + c1 + c2 + c3;
     if (total != 0u) {                               // CTA-uniform
-      stream_redraw<KIND>(a, total * NB, tid, blockDim.x, [&](uint32_t slot) {
+      stream_redraw<KIND, ROWS>(a, total * NB, tid, blockDim.x, [&](uint32_t slot) {
         uint32_t w = 0u;
         if (slot >= c0) { slot -= c0; w = 1u; if (slot >= c1) { slot -= c1; w = 2u; if (slot >= c2) { slot -= c2; w = 3u; } } }
         return redraw_list[w][slot];

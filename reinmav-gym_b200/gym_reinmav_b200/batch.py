@@ -160,6 +160,11 @@ class QuadBatch:
         check(lib().rmv_last_variant(self._h, ctypes.byref(v)))
         return _capi.VARIANTS.get(v.value, str(v.value))
 
+    def _one_launch(self):
+        """Whether the multi-step call just made was ONE kernel launch (the library decides: step stream / rollout kernel
+        against one launch per step, by kind, batch size and state layout)."""
+        return self.last_kernel in ("k_step_stream", "k_step_stream_pair", "k_rollout")
+
     def set_tuning(self, vec=0, block=0):
         check(lib().rmv_set_tuning(self._h, int(vec), int(block)))
 
@@ -244,9 +249,7 @@ class QuadBatch:
         check(lib().rmv_step_many(self._h, int(n_steps), _ptr(actions, "float32", d, "actions"), layout, int(act_ld),
                                   _ptr(reward, "float32", d, "reward"), _ptr(done, "uint8", d, "done"),
                                   int(out_ld or self.num_envs), int(fused), _stream(stream, d)))
-        one = int(fused) == _capi.MANY_ROLLOUT or (int(fused) == _capi.MANY_STREAM and self.state_layout == "tiles" and self.kind < 4
-                                                   and int(n_steps) >= 2 and lib().rmv_stream_pays(self.kind, self.num_envs))
-        self.launches += 1 if one else int(n_steps)
+        self.launches += 1 if self._one_launch() else int(n_steps)
 
     # ---------------------------------------------------------------- hot path (host buffers)
     def step_host(self, actions, reward, done, obs=None, auto_reset=True, stream=None):
@@ -293,7 +296,7 @@ class QuadBatch:
         check(lib().rmv_control_step_many(self._h, int(n_steps), self._ref(ref_pos), self._ref(ref_vel),
                                           _ptr(actions_out, "float32", d, "actions_out"), _ptr(reward, "float32", d, "reward"),
                                           _ptr(done, "uint8", d, "done"), int(out_ld or n), _stream(stream, d)))
-        self.launches += 1 if self.state_layout == "tiles" else int(n_steps)
+        self.launches += 1 if self._one_launch() else int(n_steps)
 
     def control_host(self, actions, ref_pos=None, ref_vel=None, stream=None):
         check(lib().rmv_control_host(self._h, self._ref(ref_pos), self._ref(ref_vel),

@@ -272,6 +272,71 @@ def test_step_stream_bitwise(torch, rmv, env_id, case):
         assert abs(st0["return_sum"] - st1["return_sum"]) <= 1e-9 * max(1.0, abs(st0["return_sum"]))   # atomic double sums
 
 
+ROW_STREAM_CASES = [(128 * 41 + 18, 0, 0, True, "aos"), (20000 + 5, 1, 32, False, "soa"), (20000 + 5, 2, 128, True, "aos"),
+                    (17, 0, 0, False, "aos"), ((1 << 19) + 77, 0, 0, True, "aos")]
+
+
+@pytest.mark.parametrize("case", range(len(ROW_STREAM_CASES)))
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_step_stream_on_row_state_handles_bitwise(torch, rmv, env_id, case):
+    """The step stream on a RMV_STATE_ROWS handle (the unit's 32 rows go through the warp's shared tile both ways, a
+    finished env's row is stored and then overwritten by the re-draw) against T launches on a tiled handle: state,
+    rewards, done flags, episode words and statistics bit for bit, mass finishes included; then the closed loop
+    (rmv_control_step_many) the same way, actions included."""
+    n, cap, block, track, layout = ROW_STREAM_CASES[case]
+    kind = KIND_OF_ID[env_id]
+    S, A = STATE_DIM[kind], ACTION_DIM[kind]
+    lo, hi = ACTION_BOUNDS[kind]
+    T, seed = (10 if n > 100000 else 36), 21
+    start = np.random.RandomState(5).uniform(-3, 3, (n, S)).astype(np.float32)
+    dev = "cuda:0"
+    ld = ((n + 127) // 128) * 128
+    if layout == "aos":
+        acts = torch.empty((T, n, A), dtype=torch.float32, device=dev)
+        for t in range(T):
+            rmv.fill_uniform_actions(acts[t], n, A, lo, hi, seed, step_index=t)
+        kw = dict(layout=0)
+    else:
+        acts = torch.zeros((T, A, ld), dtype=torch.float32, device=dev)
+        for t in range(T):
+            rmv.fill_uniform_actions(acts[t], n, A, lo, hi, seed, step_index=t, layout=1, act_ld=ld)
+        kw = dict(layout=1, act_ld=ld)
+    out = []
+    for state_layout, mode in (("tiles", 2), ("rows", 0)):
+        b = rmv.QuadBatch(env_id, n, seed=seed, track_episodes=track, state_layout=state_layout)
+        b.set_stream(warps_per_sm=cap, block=block)
+        b.reset()
+        b.set_state(start)
+        rew = torch.empty((3, T, n), dtype=torch.float32, device=dev)
+        done = torch.empty((3, T, n), dtype=torch.uint8, device=dev)
+        ctl = torch.zeros((T, n, A), dtype=torch.float32, device=dev)
+        launches0 = b.launches
+        for call in range(2):
+            b.step_many(T, acts, rew[call], done[call], out_ld=n, fused=mode, **kw)
+        if state_layout == "rows":
+            # the library keeps one launch per step on a row-state handle above 64 MB per step (rmv_api.cu: stream_pays_for)
+            big = n * (4 * (2 * S + A + 1) + 1) > (64 << 20) or not rmv._capi.lib().rmv_stream_pays(kind, n)
+            assert b.last_kernel == ("k_step_rows" if big else "k_step_stream")
+            assert b.launches - launches0 == (2 * T if big else 2)
+            rows = torch.as_tensor(b.state_view(), device=dev)[:n].cpu().numpy()
+            assert same_bits(rows, b.get_state())
+        if mode == 0:
+            b.control_step_many(T, rew[2], done[2], out_ld=n, actions_out=ctl)
+        else:
+            for t in range(T):
+                b.control_step(rew[2, t], done[2, t], actions_out=ctl[t])
+        torch.cuda.synchronize()
+        out.append((b.get_state(), rew.cpu().numpy(), done.cpu().numpy(), b.get_episode_words(), ctl.cpu().numpy(),
+                    b.episode_stats() if track else None))
+        b.close()
+    (s0, r0, d0, w0, c0, st0), (s1, r1, d1, w1, c1, st1) = out
+    assert d0[0, 0].mean() > 0.1 or n < 100              # the mass-finish case really happened
+    assert np.array_equal(d0, d1) and same_bits(r0, r1) and same_bits(s0, s1) and np.array_equal(w0, w1) and same_bits(c0, c1)
+    if track:
+        assert st0["episodes"] == st1["episodes"] > 0 and st0["length_sum"] == st1["length_sum"]
+        assert abs(st0["return_sum"] - st1["return_sum"]) <= 1e-9 * max(1.0, abs(st0["return_sum"]))
+
+
 @pytest.mark.parametrize("n,cap,block", [(128 * 41 + 18, 0, 0), (20000 + 5, 1, 32), (20000 + 6, 2, 128), (17, 0, 0), (63, 0, 0),
                                          ((1 << 19) + 77, 0, 0), ((1 << 20) + 2, 0, 0)])
 def test_step_stream_pair_bitwise(torch, rmv, n, cap, block):

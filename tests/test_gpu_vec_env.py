@@ -531,7 +531,7 @@ def test_row_state_handle_equals_tiled_handle(rmv, env_id):
     same()
     t_.reset_host(ho_t); r_.reset_host(ho_r)
     assert same_bits(ho_t, ho_r); same()
-    # step_many (row-state handles launch the row-state kernel once per step), every mode
+    # step_many, every mode (row-state handles: the stream with row transposes for mode 0, one row-state launch per step otherwise)
     T = 12
     acts = torch.empty((T, n, A), dtype=torch.float32, device=dev)
     for t in range(T):

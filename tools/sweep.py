@@ -18,7 +18,8 @@ BOUNDS = {"quadrotor2d-v0": (-10, 10), "quadrotor2d-slungload-v0": (-10, 10), "q
 def time_cfg(env_id, n, vec, block, layout, fused, steps, ring, peak, tma=0, ctas=0, obs=0, track=0, l2=0, rows=0,
              warps=0, sblock=0, apre=-1):
     dev = "cuda:0"
-    b = rmv.QuadBatch(env_id, n, seed=0, track_episodes=bool(track))
+    b = rmv.QuadBatch(env_id, n, seed=0, track_episodes=bool(track), state_layout="rows" if rows == 3 else "tiles")
+    row_state, rows = rows == 3, (0 if rows == 3 else rows)          # 3: a row-state handle through step_many
     b.set_tuning(vec=vec, block=block)
     b.set_kernel(tma=bool(tma), ctas_per_sm=ctas)
     b.set_stream(warps_per_sm=warps, block=sblock, action_prefetch=apre)
@@ -111,7 +112,7 @@ def main():
     ap.add_argument("--ctas", default="0", help="comma list: persistent CTAs per SM for the TMA kernel (0 = max)")
     ap.add_argument("--obs", type=int, default=0, help="1: the kernel also writes row-per-env observations [N][S] every step")
     ap.add_argument("--track", type=int, default=0, help="1: episode tracking (Monitor) on")
-    ap.add_argument("--rows", type=int, default=0, help="1: rmv_step_rows through a ring of row buffers, 2: rmv_step_rows in place")
+    ap.add_argument("--rows", type=int, default=0, help="1: rmv_step_rows through a ring of row buffers, 2: rmv_step_rows in place, 3: a RMV_STATE_ROWS handle through step_many")
     ap.add_argument("--l2", type=int, default=0, help="1: opt-in L2 access-policy window on the state (rmv_set_l2_persist)")
     args = ap.parse_args()
     print("%-26s %9s %3s %5s %4s %5s %9s %11s %9s %6s" % ("env", "n", "vec", "block", "lay", "fused", "us/step", "steps/s", "GB/s(alg)", "frac"))
