@@ -50,8 +50,9 @@ for env_id, (lo, hi) in BOUNDS.items():
         b.control(act[0]); b.step(act[0], rew[0], done[0])
         b.control_step(rew[1], done[1], actions_out=act[1])
         b.control_step_many(4, rew, done, out_ld=n, actions_out=act)
+        b.step_many(4, act, rew, done, out_ld=n, layout=0, fused=0)      # rows: the stream with the row transposes
         torch.cuda.synchronize()
-        print(env_id, layout, "control paths ok", flush=True)
+        print(env_id, layout, "control paths ok, step_many ->", b.last_kernel, flush=True)
         b.close()
 n2 = 128 * 9 + 64                                  # two envs per thread need even row offsets in the outputs
 b = rmv.QuadBatch("quadrotor3d-v0", n2, seed=3)
