@@ -878,9 +878,14 @@ static cudaError_t launch_stream_pair(rmv_env* e, const StepArgs& args, cudaStre
 template <int KIND>
 static cudaError_t launch_stream_k(rmv_env* e, const StepArgs& args, cudaStream_t st, bool ctrl = false) {
   const bool track = args.ep_return != nullptr;
-  if (e->rows) {                                   // row-state handle: the stream with the row transposes (no prefetch variants)
+  if (e->rows) {                                   // row-state handle: the stream with the row transposes (no episode-word prefetch)
     if (ctrl) return track ? launch_stream_t<KIND, true, false, true, false, true>(e, args, st)
                            : launch_stream_t<KIND, false, false, true, false, true>(e, args, st);
+    bool apre = !args.act_soa && args.n <= (int64_t)148 * 32 * 32;        // as below: small batches fetch the next action row early
+    if (g_stream_apre >= 0) apre = !args.act_soa && g_stream_apre != 0;
+    if (e->stream_apre >= 0) apre = !args.act_soa && e->stream_apre != 0;
+    if (apre) return track ? launch_stream_t<KIND, true, false, false, true, true>(e, args, st)
+                           : launch_stream_t<KIND, false, false, false, true, true>(e, args, st);
     return track ? launch_stream_t<KIND, true, false, false, false, true>(e, args, st)
                  : launch_stream_t<KIND, false, false, false, false, true>(e, args, st);
   }

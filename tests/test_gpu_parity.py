@@ -272,8 +272,8 @@ def test_step_stream_bitwise(torch, rmv, env_id, case):
         assert abs(st0["return_sum"] - st1["return_sum"]) <= 1e-9 * max(1.0, abs(st0["return_sum"]))   # atomic double sums
 
 
-ROW_STREAM_CASES = [(128 * 41 + 18, 0, 0, True, "aos"), (20000 + 5, 1, 32, False, "soa"), (20000 + 5, 2, 128, True, "aos"),
-                    (17, 0, 0, False, "aos"), ((1 << 19) + 77, 0, 0, True, "aos")]
+ROW_STREAM_CASES = [(128 * 41 + 18, 0, 0, True, "aos", -1), (128 * 41 + 18, 0, 0, False, "aos", 0), (20000 + 5, 1, 32, False, "soa", -1),
+                    (20000 + 5, 2, 128, True, "aos", 1), (17, 0, 0, False, "aos", 1), ((1 << 19) + 77, 0, 0, True, "aos", -1)]
 
 
 @pytest.mark.parametrize("case", range(len(ROW_STREAM_CASES)))
@@ -283,7 +283,7 @@ def test_step_stream_on_row_state_handles_bitwise(torch, rmv, env_id, case):
     finished env's row is stored and then overwritten by the re-draw) against T launches on a tiled handle: state,
     rewards, done flags, episode words and statistics bit for bit, mass finishes included; then the closed loop
     (rmv_control_step_many) the same way, actions included."""
-    n, cap, block, track, layout = ROW_STREAM_CASES[case]
+    n, cap, block, track, layout, apre = ROW_STREAM_CASES[case]
     kind = KIND_OF_ID[env_id]
     S, A = STATE_DIM[kind], ACTION_DIM[kind]
     lo, hi = ACTION_BOUNDS[kind]
@@ -304,7 +304,7 @@ def test_step_stream_on_row_state_handles_bitwise(torch, rmv, env_id, case):
     out = []
     for state_layout, mode in (("tiles", 2), ("rows", 0)):
         b = rmv.QuadBatch(env_id, n, seed=seed, track_episodes=track, state_layout=state_layout)
-        b.set_stream(warps_per_sm=cap, block=block)
+        b.set_stream(warps_per_sm=cap, block=block, action_prefetch=apre)
         b.reset()
         b.set_state(start)
         rew = torch.empty((3, T, n), dtype=torch.float32, device=dev)
