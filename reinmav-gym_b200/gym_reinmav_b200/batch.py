@@ -304,6 +304,11 @@ class QuadBatch:
         self.launches += 1
 
     # ---------------------------------------------------------------- state access
+    def get_state_device(self, rows, stream=None):
+        """Write the current state as [N, S] rows into a device buffer (a kernel on ``stream``; no synchronisation)."""
+        _need(rows, self.num_envs * self.state_dim, "rows")
+        check(lib().rmv_get_state(self._h, _ptr(rows, "float32", self.device, "rows"), 1, _stream(stream, self.device)))
+
     def get_state(self, stream=None):
         out = np.empty((self.num_envs, self.state_dim), dtype=np.float32)
         check(lib().rmv_get_state(self._h, out.ctypes.data, 0, _stream(stream, self.device)))

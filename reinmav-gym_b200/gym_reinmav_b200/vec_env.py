@@ -247,6 +247,26 @@ class QuadVecEnv:
         self.batch.step(actions, t["rew_ptr"], t["done_ptr"], obs=t["obs_ptr"] if (want_obs and not rows) else None, auto_reset=True)
         return (t["obs"] if want_obs else None), t["rew"], t["done"]
 
+    def step_many_tensor(self, actions, rewards=None, dones=None, want_obs=True):
+        """T steps with auto-reset from a pre-generated action block (replays, random-policy runs, shooting): ``actions``
+        float32 CUDA [T, N, A]; ``rewards`` float32 / ``dones`` uint8 [T, N] are filled (allocated if None).  ONE launch of
+        the step stream where the library finds it pays, else T launches; the same results as T ``step_tensor`` calls, bit
+        for bit.  Returns (obs after the last step [N, S] or None, rewards, dones); Monitor statistics keep counting."""
+        import torch
+        T = int(actions.shape[0])
+        if actions.dim() != 3 or tuple(actions.shape[1:]) != (self.num_envs, self.batch.action_dim):
+            raise ValueError("actions must have shape [T, %d, %d], got %s" % (self.num_envs, self.batch.action_dim, tuple(actions.shape)))
+        dev = "cuda:%d" % self.device
+        if rewards is None:
+            rewards = torch.empty((T, self.num_envs), dtype=torch.float32, device=dev)
+        if dones is None:
+            dones = torch.empty((T, self.num_envs), dtype=torch.uint8, device=dev)
+        t = self._tensors()
+        self.batch.step_many(T, actions, rewards, dones, out_ld=self.num_envs, layout=0, fused=0)
+        if want_obs and self.state_layout != "rows":
+            self.batch.get_state_device(t["obs"])       # tiled state -> observation rows (a row-state handle IS the rows)
+        return (t["obs"] if want_obs else None), rewards, dones
+
     def control_tensor(self, ref_pos=None, ref_vel=None):
         """Actions [N, A] of the reference's geometric controller for the current states (device tensor)."""
         import torch

@@ -567,3 +567,34 @@ def test_vec_env_zero_copy_mode(rmv):
         assert same_bits(o1, o2) and same_bits(r1, r2) and np.array_equal(d1, d2)
     venv.close()
     ref.close()
+
+
+@pytest.mark.parametrize("env_id", ["quadrotor2d-v0", "quadrotor3d-v0", "quadrotor3d-slungload-v0"])
+def test_step_many_tensor_equals_repeated_step_tensor(rmv, env_id):
+    """QuadVecEnv.step_many_tensor (T steps from an action block in one call: the step stream, on the row-state handle the
+    3D kinds default to as well) against T step_tensor calls: observations, rewards, done flags and Monitor statistics."""
+    import torch
+    kind = KIND_OF_ID[env_id]
+    A = ACTION_DIM[kind]
+    lo, hi = ACTION_BOUNDS[kind]
+    n, T, dev = 128 * 77 + 3, 48, "cuda:0"
+    acts = torch.empty((T, n, A), dtype=torch.float32, device=dev)
+    for t in range(T):
+        rmv.fill_uniform_actions(acts[t], n, A, 2 * lo, 2 * hi, 5, step_index=t)
+    one, many = rmv.QuadVecEnv(env_id, n, seed=5), rmv.QuadVecEnv(env_id, n, seed=5)
+    one.reset_tensor(); many.reset_tensor()
+    start = np.random.RandomState(6).uniform(-2.5, 2.5, (n, STATE_DIM[kind])).astype(np.float32)    # wide: episodes end in every kind
+    one.batch.set_state(start); many.batch.set_state(start)
+    rews, dones = [], []
+    for t in range(T):
+        obs1, r, d = one.step_tensor(acts[t])
+        rews.append(r.clone()); dones.append(d.clone())
+    obs2, rew2, done2 = many.step_many_tensor(acts)
+    assert many.batch.last_kernel == "k_step_stream" and many.batch.launches < one.batch.launches
+    assert torch.equal(torch.stack(rews).view(torch.int32), rew2.view(torch.int32)) and torch.equal(torch.stack(dones), done2)
+    assert torch.equal(obs1.view(torch.int32), obs2.view(torch.int32))
+    a, b = one.episode_stats(), many.episode_stats()
+    assert a["episodes"] == b["episodes"] > 0 and a["length_sum"] == b["length_sum"] and abs(a["return_sum"] - b["return_sum"]) < 1e-6 * abs(a["return_sum"])
+    with pytest.raises(ValueError):
+        many.step_many_tensor(acts[:, :-1])
+    one.close(); many.close()
