@@ -526,15 +526,18 @@ def measure_extras(torch, rmv, args, local):
         return best
 
     peak, _ = load_peak()
-    cases = [("fused_rollout", ENV_ID, 1 << 20, 64, 256, True),
-             ("quadrotor3d-slungload-v0", "quadrotor3d-slungload-v0", 1 << 20, 32, 300, False),
-             ("quadrotor2d-v0", "quadrotor2d-v0", 1 << 20, 32, 300, False),
-             ("quadrotor2d-slungload-v0", "quadrotor2d-slungload-v0", 1 << 20, 32, 300, False)]
+    cases = [("fused_rollout", ENV_ID, 1 << 20, 64, 256, True, "tiles"),
+             ("quadrotor3d-slungload-v0", "quadrotor3d-slungload-v0", 1 << 20, 32, 300, False, "tiles"),
+             ("quadrotor2d-v0", "quadrotor2d-v0", 1 << 20, 32, 300, False, "tiles"),
+             ("quadrotor2d-slungload-v0", "quadrotor2d-slungload-v0", 1 << 20, 32, 300, False, "tiles"),
+             # a row-state handle (the state buffer is the observation matrix; the VecEnv default for the 3D kinds)
+             ("row_state_stream_quadrotor3d_n65536", ENV_ID, 1 << 16, 64, 2048, False, "rows"),
+             ("row_state_stream_quadrotor3d_n262144", ENV_ID, 1 << 18, 64, 1024, False, "rows")]
     bytes_of = {"quadrotor2d-v0": 53, "quadrotor2d-slungload-v0": 85, "quadrotor3d-v0": 101, "quadrotor3d-slungload-v0": 149}
     bounds = {"quadrotor2d-v0": (-10, 10), "quadrotor2d-slungload-v0": (-10, 10), "quadrotor3d-v0": (0, 10),
               "quadrotor3d-slungload-v0": (-10, 10)}
-    for name, env_id, n, ring, k, fused in cases:
-        b = rmv.QuadBatch(env_id, n, device=local, seed=SEED)
+    for name, env_id, n, ring, k, fused, state_layout in cases:
+        b = rmv.QuadBatch(env_id, n, device=local, seed=SEED, state_layout=state_layout)
         b.set_tuning(vec=args.vec, block=args.block)
         b.reset()
         A = b.action_dim
@@ -549,6 +552,9 @@ def measure_extras(torch, rmv, args, local):
         out[name] = {"env_id": env_id, "n_envs": n, "us_per_step": ms * 1e3, "env_steps_per_s": sps,
                      "algorithmic_GBps": sps * bytes_of[env_id] / 1e9, "frac_of_hbm_peak": sps * bytes_of[env_id] / 1e9 / peak,
                      "mode": "one launch per %d steps, state in registers" % ring if fused else "step stream (one launch per %d steps, state through memory every step)" % ring}
+        if state_layout == "rows":
+            out[name]["mode"] += "; RMV_STATE_ROWS handle: rows through the warp's shared tile both ways"
+            out[name]["kernel"] = b.last_kernel
         b.close()
         del acts, rew, done
 
