@@ -35,6 +35,7 @@ class VecNormalize:
         self._rew = torch.empty((self.num_envs,), dtype=torch.float32, device=dev)
         self._obs_ptr, self._rew_ptr = self._obs.data_ptr(), self._rew.data_ptr()
         self._act = None
+        self._h_views = None
         self.closed = False
 
     # ------------------------------------------------------------------ device path
@@ -53,24 +54,48 @@ class VecNormalize:
         return self._obs, self._rew, done
 
     # ------------------------------------------------------------------ VecEnv protocol (host)
+    def _host(self):
+        """torch views of the env's page-locked host buffers + a device action buffer: the host protocol moves its arrays
+        with asynchronous copies and one synchronisation per call, as QuadVecEnv.step does through rmv_step_host."""
+        if self._h_views is None:
+            import torch
+            v = self.venv
+            self._h_views = dict(act=torch.from_numpy(v._act.array), obs=torch.from_numpy(v._obs.array),
+                                 rew=torch.from_numpy(v._rew.array), done=torch.from_numpy(v._done.array),
+                                 act_dev=torch.empty(v._act.array.shape, dtype=torch.float32, device="cuda:%d" % self.device))
+        return self._h_views
+
+    def _sync(self):
+        import torch
+        torch.cuda.current_stream(self.device).synchronize()
+
     def reset(self):
-        return self.reset_tensor().cpu().numpy()
+        h = self._host()
+        h["obs"].copy_(self.reset_tensor(), non_blocking=True)
+        self._sync()
+        return self.venv._out(self.venv._obs.array)
 
     def step_async(self, actions):
-        import torch
-        a = np.ascontiguousarray(actions, dtype=np.float32)
-        if a.shape != (self.num_envs, self.venv.batch.action_dim):
-            raise ValueError("actions must have shape %s, got %s" % ((self.num_envs, self.venv.batch.action_dim), a.shape))
-        self._act = torch.as_tensor(a, device="cuda:%d" % self.device)
+        h = self._host()
+        a = np.asarray(actions, dtype=np.float32)
+        if a.shape != self.venv._act.array.shape:
+            raise ValueError("actions must have shape %s, got %s" % (self.venv._act.array.shape, a.shape))
+        if actions is not self.venv._act.array:
+            self.venv._act.array[...] = a
+        h["act_dev"].copy_(h["act"], non_blocking=True)
+        self._act = h["act_dev"]
 
     def step_wait(self):
         if self._act is None:
             raise RuntimeError("step_wait() without step_async()")
         obs, rew, done = self.step_tensor(self._act)
         self._act = None
-        done_h = done.cpu().numpy().astype(bool)
-        infos = self.venv._finished(done_h) if self.venv.monitor else SparseInfos(self.num_envs)
-        return obs.cpu().numpy(), rew.cpu().numpy(), done_h, infos
+        h, v = self._host(), self.venv
+        h["obs"].copy_(obs, non_blocking=True); h["rew"].copy_(rew, non_blocking=True); h["done"].copy_(done, non_blocking=True)
+        self._sync()
+        done_h = v._done.array.astype(bool)
+        infos = v._finished(done_h) if v.monitor else SparseInfos(self.num_envs)
+        return v._out(v._obs.array), v._out(v._rew.array), done_h, infos
 
     def step(self, actions):
         self.step_async(actions)
@@ -103,6 +128,7 @@ class VecNormalize:
         if self.closed:
             return
         self.closed = True
+        self._h_views = None                           # views of buffers the env frees
         lib().rmv_norm_destroy(self._h)
         self._h = ctypes.c_void_p()
         self.venv.close()

@@ -114,3 +114,29 @@ def test_norm_step_with_unaligned_matrices_takes_the_scalar_walk():
         results.append(obs_out.cpu().numpy().copy())
         check(lib().rmv_norm_destroy(h))
     assert np.abs(results[0] - results[1]).max() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_host_protocol_equals_the_device_path():
+    """VecNormalize.reset() / step() (NumPy in, NumPy out through the env's page-locked buffers, asynchronous copies, one
+    synchronisation) returns the bits of reset_tensor() / step_tensor(); infos carry Monitor's record for finished envs."""
+    import torch
+    import gym_reinmav_b200 as rmv
+    n, seed = 128 * 9 + 40, 3
+    host = rmv.VecNormalize(rmv.QuadVecEnv("quadrotor3d-v0", n, seed=seed))
+    dev = rmv.VecNormalize(rmv.QuadVecEnv("quadrotor3d-v0", n, seed=seed))
+    o_h, o_d = host.reset(), dev.reset_tensor().cpu().numpy()
+    assert o_h.dtype == np.float32 and np.array_equal(o_h.view(np.int32), o_d.view(np.int32))
+    rng = np.random.RandomState(1)
+    finished = 0
+    for t in range(60):
+        a = rng.uniform(0, 25, size=(n, 4)).astype(np.float32)
+        oh, rh, dh, infos = host.step(a)
+        od, rd, dd = dev.step_tensor(torch.as_tensor(a, device="cuda:0"))
+        assert np.array_equal(oh.view(np.int32), od.cpu().numpy().view(np.int32)), t
+        assert np.array_equal(rh.view(np.int32), rd.cpu().numpy().view(np.int32)) and np.array_equal(dh, dd.cpu().numpy().astype(bool))
+        for i in np.flatnonzero(dh)[:5]:
+            assert set(infos[int(i)]["episode"]) == {"r", "l", "t"}
+        finished += int(dh.sum())
+    assert finished > 10
+    host.close(); dev.close()
