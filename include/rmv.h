@@ -229,7 +229,7 @@ RMV_API int rmv_step_rows(rmv_env* env, const float* rows_in_dev, const float* a
  *               previous step — no grid-wide barrier, one CTA barrier per step for the re-draws (csrc/rmv_stream.cuh);
  *               on an RMV_STATE_ROWS handle the unit's rows pass through the warp's shared tile both ways;
  *   RMV_MANY_ROLLOUT  (1): ONE launch, each thread keeps its envs' state in registers for all T steps
- *               (state is read and written once per call); tiled handles only — an RMV_STATE_ROWS handle takes mode 2;
+ *               (state is read and written once per call);
  *   RMV_MANY_LAUNCHES (2): T launches of the single-step kernel (what mode 0 was before the stream kernel; a
  *               repeated call is replayed from a CUDA graph).
  * Results are identical bit for bit in all three. */

@@ -754,6 +754,9 @@ template <int KIND, int V>
 static cudaError_t launch_step_kv(rmv_env* e, const StepArgs& args, cudaStream_t st) {
   if (args.n_steps > 1) {
     const int64_t groups = (args.n + V - 1) / V;
+    if constexpr (V == 1) {
+      if (e->rows) { k_rollout<KIND, 1, true><<<blocks_for(groups, 128), 128, 0, st>>>(args); return cudaGetLastError(); }
+    }
     k_rollout<KIND, V><<<blocks_for(groups, 128), 128, 0, st>>>(args);
     return cudaGetLastError();
   }
@@ -1009,9 +1012,9 @@ static int launch_step(rmv_env* e, const float* act, int act_layout, int64_t act
   a.rows_in = nullptr;
   const bool fused_ctrl = ctrl != nullptr;
   cudaError_t err;
-  if (e->rows && !stream) {
+  if (e->rows && n_steps > 1) vec = 1;             // the multi-step kernels on row-state handles are one env per thread
+  if (e->rows && !stream && n_steps == 1) {
     // RMV_STATE_ROWS: the state buffer is the [n][S] observation matrix; the row-state kernel updates it in place
-    if (n_steps != 1) return fail(RMV_EINVAL, "internal: multi-step launch of the row-state kernel");
     RMV_REQUIRE(rew != nullptr && done != nullptr, "reward_dev and done_dev must not be NULL");
     float* const rows = e->state + c0 * e->S;
     a.rows_in = rows; a.obs = rows;
@@ -1110,7 +1113,6 @@ extern "C" RMV_API int rmv_step_many(rmv_env* env, int n_steps, const float* act
     return launch_step(env, nullptr, RMV_ACT_AOS, 0, 0, reward_dev, done_dev, out_ld, nullptr, 0, n_steps, st);
   const int64_t stride = (act_layout == RMV_ACT_SOA) ? (int64_t)env->A * act_ld : env->n * env->A;
   RMV_REQUIRE(fused >= 0 && fused <= 2, "mode must be RMV_MANY_STREAM (0), RMV_MANY_ROLLOUT (1) or RMV_MANY_LAUNCHES (2)");
-  if (env->rows && fused == RMV_MANY_ROLLOUT) fused = RMV_MANY_LAUNCHES;   // the rollout kernel reads tiles: row-state handles take launches there
   if (fused == RMV_MANY_ROLLOUT)
     return launch_step(env, act_dev, act_layout, act_ld, stride, reward_dev, done_dev, out_ld, nullptr, 1, n_steps, st);
   if (!reward_dev || !done_dev) {                 // the step kernels always write both: park a missing one in scratch

@@ -604,21 +604,29 @@ k_step_rows(const StepArgs a) {
 // ---- fused multi-step rollout ---------------------------------------------------------------------
 // n_steps consecutive steps with auto-reset; each thread keeps its envs' state in registers in
 // between, so state is read and written once per call (actions in, reward/done out every step).
-template <int KIND, int V>
+// ROWS (RMV_STATE_ROWS handles, V = 1): a.state is the [n][S] observation matrix; a thread reads and writes its own row
+// (S consecutive floats) — twice per call, so the transposes of the per-step kernels are not worth their shared memory here.
+template <int KIND, int V, bool ROWS = false>
 __global__ void __launch_bounds__(128) k_rollout(const StepArgs a) {
+  static_assert(!ROWS || V == 1, "the row-state rollout is one env per thread");
   constexpr int S = Dims<KIND>::S, A = Dims<KIND>::A;
   const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (e0 >= a.n) return;
   const bool full = e0 + V <= a.n;
-  float* const sp = a.state + ((e0 >> 7) * (int64_t)(S * kTile) + (e0 & (kTile - 1)));
+  float* const sp = ROWS ? a.state + e0 * S : a.state + ((e0 >> 7) * (int64_t)(S * kTile) + (e0 & (kTile - 1)));
   float s[V][S];
   float ep_ret[V];
+  if constexpr (ROWS) {
 #pragma unroll
-  for (int c = 0; c < S; ++c) {
-    float t[V];
-    load_v<V, false>(sp + c * kTile, t);
+    for (int c = 0; c < S; ++c) s[0][c] = sp[c];
+  } else {
 #pragma unroll
-    for (int v = 0; v < V; ++v) s[v][c] = t[v];
+    for (int c = 0; c < S; ++c) {
+      float t[V];
+      load_v<V, false>(sp + c * kTile, t);
+#pragma unroll
+      for (int v = 0; v < V; ++v) s[v][c] = t[v];
+    }
   }
   if (a.ep_return) load_v<V, false>(a.ep_return + e0, ep_ret);
 
@@ -658,12 +666,17 @@ __global__ void __launch_bounds__(128) k_rollout(const StepArgs a) {
     store_outputs<V>(a, (int64_t)step * a.out_ld + e0, e0, full, rew, dn);
   }
 
+  if constexpr (ROWS) {
 #pragma unroll
-  for (int c = 0; c < S; ++c) {
-    float t[V];
+    for (int c = 0; c < S; ++c) sp[c] = s[0][c];
+  } else {
 #pragma unroll
-    for (int v = 0; v < V; ++v) t[v] = s[v][c];
-    store_v<V, false>(sp + c * kTile, t);
+    for (int c = 0; c < S; ++c) {
+      float t[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) t[v] = s[v][c];
+      store_v<V, false>(sp + c * kTile, t);
+    }
   }
   if (a.ep_return) store_v<V, false>(a.ep_return + e0, ep_ret);
 }

@@ -531,7 +531,7 @@ def test_row_state_handle_equals_tiled_handle(rmv, env_id):
     same()
     t_.reset_host(ho_t); r_.reset_host(ho_r)
     assert same_bits(ho_t, ho_r); same()
-    # step_many, every mode (row-state handles: the stream with row transposes for mode 0, one row-state launch per step otherwise)
+    # step_many, every mode (row-state handles: the stream with row transposes, the rollout kernel on rows, one row-state launch per step)
     T = 12
     acts = torch.empty((T, n, A), dtype=torch.float32, device=dev)
     for t in range(T):
@@ -541,6 +541,7 @@ def test_row_state_handle_equals_tiled_handle(rmv, env_id):
     for mode in (0, 1, 2):
         t_.step_many(T, acts, rt, dt, out_ld=n, layout=0, fused=mode); r_.step_many(T, acts, rr, dr, out_ld=n, layout=0, fused=mode)
         assert torch.equal(rt.view(torch.int32), rr.view(torch.int32)) and torch.equal(dt, dr); same()
+        assert r_.last_kernel == ("k_step_stream", "k_rollout", "k_step_rows")[mode]       # each mode has its row-state kernel
     # set_state from host and from device rows
     st = np.random.RandomState(5).uniform(-1, 1, (n, S)).astype(np.float32)
     t_.set_state(st); r_.set_state(st); same()
