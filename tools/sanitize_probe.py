@@ -50,6 +50,7 @@ for env_id, (lo, hi) in BOUNDS.items():
         b.control(act[0]); b.step(act[0], rew[0], done[0])
         b.control_step(rew[1], done[1], actions_out=act[1])
         b.control_step_many(4, rew, done, out_ld=n, actions_out=act)
+        b.step_many(4, act, rew, done, out_ld=n, layout=0, fused=1)      # rows: the rollout kernel on rows
         b.step_many(4, act, rew, done, out_ld=n, layout=0, fused=0)      # rows: the stream with the row transposes
         torch.cuda.synchronize()
         print(env_id, layout, "control paths ok, step_many ->", b.last_kernel, flush=True)
